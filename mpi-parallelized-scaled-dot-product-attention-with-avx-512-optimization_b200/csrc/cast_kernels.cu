@@ -1,0 +1,193 @@
+// cast_kernels.cu -- the I/O casts of the attention path as HBM-bound sm_100a kernels.
+//
+// Replaces cvt_d2f_avx512 (attention-mpi.c:31-64, fp64->fp32 round-to-nearest-even)
+// and cvt_f2d_avx512 (attention-mpi.c:68-101, exact widening); adds the fp64->bf16
+// cast that feeds the tensor-core kernel.  Algorithmic traffic: 12 B/element for
+// d2f and f2d, 10 B/element for d2bf16.  Each thread moves 16-byte vectors with
+// several independent loads in flight; a scalar kernel covers unaligned pointers and tails.
+#include "common.cuh"
+
+namespace sdpa {
+
+namespace {
+
+constexpr int kCastThreads = 256;
+
+__device__ __forceinline__ double2 ld_stream_f64x2(const double2* p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ float4 ld_stream_f32x4(const float4* p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// Every warp-level load/store below is contiguous across the warp (16 B per lane on the
+// wide side), and each thread keeps kUnroll independent loads in flight per step.
+constexpr int kUnroll = 4;
+
+// unit = 2 elements: one 16 B fp64 load -> one 8 B fp32 store.
+__global__ void __launch_bounds__(kCastThreads)
+cvt_d2f_vec_kernel(float2* __restrict__ dst, const double2* __restrict__ src, size_t units)
+{
+    const size_t total = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * total < units; i += kUnroll * total) {
+        double2 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream_f64x2(src + i + u * total);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            dst[i + u * total] = make_float2(__double2float_rn(v[u].x), __double2float_rn(v[u].y));
+    }
+    for (; i < units; i += total) {
+        const double2 v = ld_stream_f64x2(src + i);
+        dst[i] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+    }
+}
+
+__global__ void __launch_bounds__(kCastThreads)
+cvt_d2f_scalar_kernel(float* __restrict__ dst, const double* __restrict__ src, size_t begin, size_t count)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        dst[i] = __double2float_rn(src[i]);
+}
+
+// unit = 4 elements: one 16 B fp32 load -> two 16 B fp64 stores.
+__global__ void __launch_bounds__(kCastThreads)
+cvt_f2d_vec_kernel(double2* __restrict__ dst, const float4* __restrict__ src, size_t units)
+{
+    const size_t total = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * total < units; i += kUnroll * total) {
+        float4 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream_f32x4(src + i + u * total);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            dst[2 * (i + u * total) + 0] = make_double2((double)v[u].x, (double)v[u].y);
+            dst[2 * (i + u * total) + 1] = make_double2((double)v[u].z, (double)v[u].w);
+        }
+    }
+    for (; i < units; i += total) {
+        const float4 v = ld_stream_f32x4(src + i);
+        dst[2 * i + 0] = make_double2((double)v.x, (double)v.y);
+        dst[2 * i + 1] = make_double2((double)v.z, (double)v.w);
+    }
+}
+
+__global__ void __launch_bounds__(kCastThreads)
+cvt_f2d_scalar_kernel(double* __restrict__ dst, const float* __restrict__ src, size_t begin, size_t count)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        dst[i] = (double)src[i];
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    // cvt.rn.bf16x2.f32 d, a, b : a -> upper half, b -> lower half
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// unit = 2 elements: one 16 B fp64 load -> one 4 B bf16x2 store (fp64 -> fp32 RN -> bf16 RN).
+__global__ void __launch_bounds__(kCastThreads)
+cvt_d2bf16_vec_kernel(uint32_t* __restrict__ dst, const double2* __restrict__ src, size_t units)
+{
+    const size_t total = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * total < units; i += kUnroll * total) {
+        double2 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream_f64x2(src + i + u * total);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            dst[i + u * total] = pack_bf16x2(__double2float_rn(v[u].x), __double2float_rn(v[u].y));
+    }
+    for (; i < units; i += total) {
+        const double2 v = ld_stream_f64x2(src + i);
+        dst[i] = pack_bf16x2(__double2float_rn(v.x), __double2float_rn(v.y));
+    }
+}
+
+__global__ void __launch_bounds__(kCastThreads)
+cvt_d2bf16_scalar_kernel(__nv_bfloat16* __restrict__ dst, const double* __restrict__ src, size_t begin,
+                         size_t count)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        dst[i] = __float2bfloat16_rn(__double2float_rn(src[i]));
+}
+
+inline int cast_grid(size_t work_items)
+{
+    // 148 SMs x 8 resident CTAs of 256 threads; never more CTAs than work.
+    const size_t want = (work_items + kCastThreads - 1) / kCastThreads;
+    const size_t cap = 148 * 8;
+    size_t g = want < cap ? want : cap;
+    return (int)(g == 0 ? 1 : g);
+}
+
+inline bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+}  // namespace
+
+sdpa_status launch_cvt_d2f(float* dst, const double* src, size_t count, cudaStream_t stream)
+{
+    if (count == 0) return SDPA_OK;
+    size_t done = 0;
+    if (aligned(dst, 8) && aligned(src, 16) && count >= 2) {
+        const size_t units = count / 2;
+        cvt_d2f_vec_kernel<<<cast_grid(units / kUnroll), kCastThreads, 0, stream>>>(
+            reinterpret_cast<float2*>(dst), reinterpret_cast<const double2*>(src), units);
+        done = units * 2;
+    }
+    if (done < count)
+        cvt_d2f_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst, src, done, count);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_cvt_f2d(double* dst, const float* src, size_t count, cudaStream_t stream)
+{
+    if (count == 0) return SDPA_OK;
+    size_t done = 0;
+    if (aligned(dst, 16) && aligned(src, 16) && count >= 4) {
+        const size_t units = count / 4;
+        cvt_f2d_vec_kernel<<<cast_grid(units / kUnroll), kCastThreads, 0, stream>>>(
+            reinterpret_cast<double2*>(dst), reinterpret_cast<const float4*>(src), units);
+        done = units * 4;
+    }
+    if (done < count)
+        cvt_f2d_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst, src, done, count);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_cvt_d2bf16(__nv_bfloat16* dst, const double* src, size_t count, cudaStream_t stream)
+{
+    if (count == 0) return SDPA_OK;
+    size_t done = 0;
+    if (aligned(dst, 4) && aligned(src, 16) && count >= 2) {
+        const size_t units = count / 2;
+        cvt_d2bf16_vec_kernel<<<cast_grid(units / kUnroll), kCastThreads, 0, stream>>>(
+            reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const double2*>(src), units);
+        done = units * 2;
+    }
+    if (done < count)
+        cvt_d2bf16_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst, src, done, count);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+}  // namespace sdpa

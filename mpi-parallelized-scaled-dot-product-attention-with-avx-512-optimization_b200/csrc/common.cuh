@@ -1,0 +1,93 @@
+// common.cuh -- shared declarations of the sdpa_b200 engine (host + device).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/sdpa_b200.h"
+
+namespace sdpa {
+
+// ---- error plumbing -------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SDPA_CUDA_TRY(expr)                                                          \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            ::sdpa::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,          \
+                              cudaGetErrorString(_e));                               \
+            return SDPA_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+#define SDPA_TRY(expr)                                                               \
+    do {                                                                             \
+        sdpa_status _s = (expr);                                                     \
+        if (_s != SDPA_OK) return _s;                                                \
+    } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- partial softmax state -------------------------------------------------
+// One fused-kernel launch covers `rows` query rows against `splits` contiguous
+// key ranges of the resident shard and leaves, per (split,row):
+//   o    [split][row][dv]  un-normalised  sum_j 2^(t_j - tmax) V_j
+//   tmax [split][row]      running max of t_j = (q.k_j) * scale * log2(e)   (log2 domain)
+//   lsum [split][row]      sum_j 2^(t_j - tmax)
+// tmax * ln2 is the reference's lmax (mpi.c:188); lsum is identical.
+struct Partials {
+    float* o;
+    float* tmax;
+    float* lsum;
+    int splits;
+    int rows_capacity;
+};
+
+// ---- kernel launchers (each returns after enqueueing on `stream`) ----------
+sdpa_status launch_cvt_d2f(float* dst, const double* src, size_t count, cudaStream_t stream);
+sdpa_status launch_cvt_f2d(double* dst, const float* src, size_t count, cudaStream_t stream);
+sdpa_status launch_cvt_d2bf16(__nv_bfloat16* dst, const double* src, size_t count, cudaStream_t stream);
+
+// fp32 CUDA-core fused attention.  Q [rows x dk], K [n x dk], V [n x dv] fp32 row-major.
+// If out64 != nullptr (requires splits == 1) the normalised result is written as fp64
+// and no partials are produced.
+sdpa_status launch_attn_f32(const float* Q, const float* K, const float* V, int rows, int n, int dk,
+                            int dv, int splits, Partials part, double* out64, cudaStream_t stream);
+bool attn_f32_supported(int dk, int dv);
+int attn_f32_pick_splits(int rows, int n, int sm_count);
+
+// bf16 tcgen05 fused attention (attn_umma_bf16.cu).  Q, K [.. x dk], V [n x dv] bf16 row-major.
+struct UmmaPlan;  // holds the TMA descriptors for one (Q buffer, K/V shard) binding
+sdpa_status umma_plan_create(UmmaPlan** plan);
+void umma_plan_destroy(UmmaPlan* plan);
+sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv_bfloat16* V, int n,
+                              int dk, int dv);
+sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, int rows_capacity, int dk);
+sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part,
+                             double* out64, int sm_count, cudaStream_t stream);
+bool attn_umma_supported(int dk, int dv);
+int attn_umma_pick_splits(int rows, int n, int sm_count);
+
+// Merge of partial states (the arithmetic of mpi.c:340-362 in the log2 domain).
+//   mode FINAL   : out64[row][d] = sum_s o_s w_s / sum_s lsum_s w_s     (gsum==0 -> 0)
+//   mode PARTIAL : contrib/tmax/lsum of the merged state, un-normalised (feeds the cross-GPU merge)
+//   mode PUBLIC  : like PARTIAL but lmax is converted to the reference's natural-log units
+sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, float* contrib,
+                                float* tmax_out, float* lsum_out, bool natural_log_max,
+                                cudaStream_t stream);
+// Cross-shard steps of the NCCL merge (mpi.c:346-351 and mpi.c:358-362).
+sdpa_status launch_rescale_to_gmax(float* contrib, float* lsum, const float* tmax, const float* gmax,
+                                   int rows, int dv, cudaStream_t stream);
+sdpa_status launch_normalize(float* contrib, const float* gsum, int rows, int dv, cudaStream_t stream);
+// Fused device-side exchange: root reads every shard's (contrib,tmax,lsum) through peer pointers.
+sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
+                               const float* const* lsum_ptrs, int shards, int rows, int dv,
+                               double* out64, cudaStream_t stream);
+
+}  // namespace sdpa

@@ -1,0 +1,181 @@
+// dropin.cu -- the reference entry point `attention(...)` (attention-mpi.c:191-192) on top
+// of the context API.  Same contract as the reference: blocking, fp64 host arrays valid on
+// rank 0, result complete on rank 0 at return, fatal errors -> stderr + exit(1)
+// (the harness convention of mpi.c:419-422,436-448 -- the entry point has no error channel).
+#include "common.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <vector>
+
+using namespace sdpa;
+
+namespace {
+
+struct Cached {
+    sdpa_ctx* ctx = nullptr;
+    sdpa_config cfg;
+    int world = 0, rank = -1;
+};
+Cached g_cached;
+unsigned char g_boot_id[128];
+bool g_boot_id_set = false;
+
+[[noreturn]] void die(const char* what)
+{
+    fprintf(stderr, "sdpa_b200: %s: %s\n", what, sdpa_last_error());
+    exit(1);
+}
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int env_precision()
+{
+    const char* v = getenv("SDPA_PRECISION");
+    if (!v || !*v || !strcmp(v, "auto")) return SDPA_PREC_AUTO;
+    if (!strcmp(v, "f32") || !strcmp(v, "fp32")) return SDPA_PREC_F32;
+    if (!strcmp(v, "bf16")) return SDPA_PREC_BF16;
+    fprintf(stderr, "sdpa_b200: SDPA_PRECISION must be auto|f32|bf16 (got %s)\n", v);
+    exit(1);
+}
+
+// File rendezvous for the ncclUniqueId when the launcher did not call sdpa_set_bootstrap_id():
+// rank 0 writes <file>.tmp then renames it; the others poll.
+void bootstrap_id_via_file(int rank, unsigned char* id)
+{
+    const char* path = getenv("SDPA_NCCL_ID_FILE");
+    if (!path || !*path) {
+        fprintf(stderr, "sdpa_b200: mpi_size > 1 needs sdpa_set_bootstrap_id() or env SDPA_NCCL_ID_FILE\n");
+        exit(1);
+    }
+    if (rank == 0) {
+        if (sdpa_get_unique_id(id) != SDPA_OK) die("ncclGetUniqueId");
+        std::string tmp = std::string(path) + ".tmp";
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(id, 1, 128, f) != 128) {
+            fprintf(stderr, "sdpa_b200: cannot write %s\n", tmp.c_str());
+            exit(1);
+        }
+        fclose(f);
+        rename(tmp.c_str(), path);
+    } else {
+        for (int tries = 0; tries < 60000; ++tries) {
+            FILE* f = fopen(path, "rb");
+            if (f) {
+                size_t got = fread(id, 1, 128, f);
+                fclose(f);
+                if (got == 128) return;
+            }
+            usleep(1000);
+        }
+        fprintf(stderr, "sdpa_b200: timed out waiting for %s\n", path);
+        exit(1);
+    }
+}
+
+sdpa_ctx* get_ctx(int mpi_rank, int mpi_size)
+{
+    sdpa_config cfg;
+    sdpa_config_init(&cfg);
+    cfg.precision = env_precision();
+    cfg.q_batch = env_int("SDPA_Q_BATCH", 0);
+    cfg.kv_splits = env_int("SDPA_KV_SPLITS", 0);
+    const char* mg = getenv("SDPA_MERGE");
+    cfg.merge = (mg && !strcmp(mg, "peer")) ? SDPA_MERGE_PEER : SDPA_MERGE_NCCL;
+    if (mpi_size <= 1) {
+        cfg.num_local = env_int("SDPA_NGPUS", 1);
+        cfg.first_device = env_int("SDPA_FIRST_DEVICE", 0);
+        cfg.world_size = cfg.num_local;
+        cfg.rank_base = 0;
+    } else {
+        const int ndev = sdpa_device_count();
+        cfg.num_local = 1;
+        cfg.first_device = env_int("SDPA_FIRST_DEVICE", -1);
+        if (cfg.first_device < 0) cfg.first_device = ndev > 0 ? env_int("LOCAL_RANK", mpi_rank) % ndev : 0;
+        cfg.world_size = mpi_size;
+        cfg.rank_base = mpi_rank;
+    }
+    if (g_cached.ctx && g_cached.world == cfg.world_size && g_cached.rank == cfg.rank_base &&
+        !memcmp(&g_cached.cfg, &cfg, sizeof(cfg)))
+        return g_cached.ctx;
+    if (g_cached.ctx) {
+        sdpa_ctx_destroy(g_cached.ctx);
+        g_cached.ctx = nullptr;
+    }
+    const void* id = nullptr;
+    unsigned char idbuf[128];
+    if (mpi_size > 1) {
+        if (g_boot_id_set) memcpy(idbuf, g_boot_id, 128);
+        else bootstrap_id_via_file(mpi_rank, idbuf);
+        id = idbuf;
+    }
+    sdpa_ctx* ctx = nullptr;
+    if (sdpa_ctx_create(&ctx, &cfg, id) != SDPA_OK) die("context creation");
+    g_cached.ctx = ctx;
+    g_cached.cfg = cfg;
+    g_cached.world = cfg.world_size;
+    g_cached.rank = cfg.rank_base;
+    return ctx;
+}
+
+}  // namespace
+
+extern "C" {
+
+sdpa_status sdpa_set_bootstrap_id(const void* id128)
+{
+    if (!id128) {
+        g_boot_id_set = false;
+        return SDPA_OK;
+    }
+    memcpy(g_boot_id, id128, 128);
+    g_boot_id_set = true;
+    return SDPA_OK;
+}
+
+/* Creates the cached context (CUDA contexts, streams, NCCL communicator) ahead of the first
+ * attention() call -- the analogue of MPI_Init (mpi.c:504), which the reference also keeps
+ * outside its timed region (mpi.c:519-522). */
+sdpa_status sdpa_runtime_init(int mpi_rank, int mpi_size)
+{
+    get_ctx(mpi_rank, mpi_size);
+    return SDPA_OK;
+}
+
+void sdpa_runtime_shutdown(void)
+{
+    if (g_cached.ctx) sdpa_ctx_destroy(g_cached.ctx);
+    g_cached.ctx = nullptr;
+}
+
+sdpa_status sdpa_scatter_attention(sdpa_ctx* ctx, const double* Q, const double* K, const double* V,
+                                   double* result, int m, int n, int dk, int dv);
+
+void attention(double* Q, double* K, double* V, double* result, int m, int n, int dk, int dv, int mpi_rank,
+               int mpi_size)
+{
+    if (mpi_size < 1 || mpi_rank < 0 || mpi_rank >= mpi_size) {
+        fprintf(stderr, "sdpa_b200: attention(): bad mpi_rank/mpi_size %d/%d\n", mpi_rank, mpi_size);
+        exit(1);
+    }
+    sdpa_ctx* ctx = get_ctx(mpi_rank, mpi_size);
+    if (mpi_size == 1) {
+        if (m < 0 || n < 0 || dk < 1 || dv < 1) {
+            fprintf(stderr, "sdpa_b200: attention(): bad dimensions m=%d n=%d dk=%d dv=%d\n", m, n, dk, dv);
+            exit(1);
+        }
+        if (sdpa_load_kv_host_full(ctx, K, V, n, dk, dv) != SDPA_OK) die("K/V upload");
+        if (sdpa_attention_host(ctx, Q, result, m) != SDPA_OK) die("attention");
+        return;
+    }
+    // one process per GPU: dimensions and data live on rank 0 (mpi.c:193-197, 508-517)
+    if (sdpa_scatter_attention(ctx, Q, K, V, result, m, n, dk, dv) != SDPA_OK) die("sharded attention");
+}
+
+}  // extern "C"

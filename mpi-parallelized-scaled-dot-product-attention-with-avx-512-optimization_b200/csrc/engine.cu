@@ -1,0 +1,1019 @@
+// engine.cu -- host side of the sdpa_b200 engine: the B200 re-design of the body of
+// attention() (attention-mpi.c:191-407).
+//
+//   reference (MPI ranks, AVX-512)                     here (GPUs, streams, NCCL)
+//   ------------------------------------------------   -------------------------------------------
+//   owner_count/owner_disp K/V row shards (:19-27,199)  one K/V shard per GPU, same map
+//   root cvt_d2f of K,V + Bcast/Scatterv (:213-266)     per-GPU chunked H2D of its own rows, cast on
+//                                                       the device (fp32 or bf16), shard stays resident
+//   ping-pong Q batches via Ibcast (:268-330)           two Q buffers per GPU; H2D of batch i+1 on the
+//                                                       copy stream overlaps the kernel of batch i
+//   per-row online softmax loop (:333-338)              one fused kernel per batch (f32 SIMT / bf16 tcgen05)
+//   Iallreduce MAX, rescale, Iallreduce SUM,            same three collectives with NCCL on a comm stream
+//   normalise, Ireduce SUM to root (:340-380)           (overlapping the next batch), or one fused
+//                                                       peer-memory merge kernel on the root GPU
+//   cvt_f2d + copy into result (:365-376,387-399)       fused into the merge / kernel epilogue, D2H on the
+//                                                       copy-out stream
+#include "common.cuh"
+#include "nccl_loader.h"
+
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace sdpa {
+
+// ---------------------------------------------------------------------------
+// error string (thread local)
+// ---------------------------------------------------------------------------
+static thread_local char g_error[1024] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+const char* get_error() { return g_error; }
+
+// ---------------------------------------------------------------------------
+// NCCL loader
+// ---------------------------------------------------------------------------
+const NcclApi* nccl_api()
+{
+    static NcclApi api;
+    static int state = 0;  // 0 = untried, 1 = ok, -1 = failed
+    if (state == 1) return &api;
+    if (state == -1) {
+        set_error("NCCL is not loadable on this host (libnccl.so.2)");
+        return nullptr;
+    }
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        state = -1;
+        set_error("dlopen(libnccl.so.2) failed: %s", dlerror());
+        return nullptr;
+    }
+    bool ok = true;
+    auto sym = [&](const char* name) {
+        void* p = dlsym(h, name);
+        if (!p) ok = false;
+        return p;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+    api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    if (!ok) {
+        state = -1;
+        set_error("libnccl is missing a required symbol");
+        return nullptr;
+    }
+    state = 1;
+    return &api;
+}
+
+#define SDPA_NCCL_TRY(expr)                                                                   \
+    do {                                                                                      \
+        ::sdpa::ncclResult_t _r = (expr);                                                     \
+        if (_r != ::sdpa::ncclSuccess) {                                                      \
+            ::sdpa::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                   \
+                              ::sdpa::nccl_api() ? ::sdpa::nccl_api()->GetErrorString(_r) : "?"); \
+            return SDPA_ERR_NCCL;                                                             \
+        }                                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// One K/V shard = one GPU.
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    sdpa_status reserve(size_t want)
+    {
+        if (want <= bytes) return SDPA_OK;
+        if (p) {
+            SDPA_CUDA_TRY(cudaFree(p));
+            p = nullptr;
+            bytes = 0;
+        }
+        size_t sz = (want + 255) & ~(size_t)255;
+        SDPA_CUDA_TRY(cudaMalloc(&p, sz));
+        bytes = sz;
+        return SDPA_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Shard {
+    int dev = 0;
+    int grank = 0;  // global shard index (the reference's mpi_rank)
+    cudaStream_t s_in = nullptr, s_compute = nullptr, s_comm = nullptr, s_out = nullptr;
+    ncclComm_t comm = nullptr;
+
+    // resident shard in compute precision
+    DevBuf Kc, Vc;
+    int n_local = 0;
+    // staging for fp64 uploads of K/V (two chunks in flight)
+    DevBuf kv_stage[2];
+    cudaEvent_t ev_stage_ready[2] = {nullptr, nullptr}, ev_stage_free[2] = {nullptr, nullptr};
+    // ping-pong Q batches
+    DevBuf q64[2], qc[2];
+    cudaEvent_t ev_q_ready[2] = {nullptr, nullptr}, ev_q_free[2] = {nullptr, nullptr};
+    // per-batch state
+    DevBuf part_o, part_tmax, part_lsum;       // split-KV partials of the batch in flight
+    DevBuf contrib[2], tmax[2], lsum[2];        // merged local state (ping-pong with the collectives)
+    DevBuf gmax[2], gsum[2];                    // allreduce results
+    DevBuf out32[2], out64[2];                  // root: reduced fp32 batch / fp64 batch for D2H
+    cudaEvent_t ev_compute_done[2] = {nullptr, nullptr}, ev_slot_free[2] = {nullptr, nullptr};
+    cudaEvent_t ev_comm_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
+    // timing event pool: pairs around casts [0], fused kernel [1], merge+collectives [2]
+    std::vector<cudaEvent_t> tev[3];
+    size_t tev_used[3] = {0, 0, 0};
+    UmmaPlan* plan = nullptr;
+    int sm_count = 148;
+};
+
+}  // namespace sdpa
+
+using namespace sdpa;
+
+struct sdpa_ctx {
+    sdpa_config cfg;
+    std::vector<Shard> shards;
+    int world = 1;
+    int rank_base = 0;
+    int dk = 0, dv = 0;
+    int prec = SDPA_PREC_F32;   // resolved precision of the resident shard
+    int q_batch = 0;
+    bool peer_ok = false;
+    float last_timing[6] = {0, 0, 0, 0, 0, 0};
+    const char* last_kernel = "none";
+    bool has_root() const { return rank_base == 0; }
+};
+
+namespace sdpa {
+
+static sdpa_status time_begin(Shard& s, int which, cudaStream_t st)
+{
+    if (s.tev_used[which] + 2 > s.tev[which].size()) {
+        for (int i = 0; i < 2; ++i) {
+            cudaEvent_t e;
+            SDPA_CUDA_TRY(cudaEventCreate(&e));
+            s.tev[which].push_back(e);
+        }
+    }
+    SDPA_CUDA_TRY(cudaEventRecord(s.tev[which][s.tev_used[which]], st));
+    return SDPA_OK;
+}
+static sdpa_status time_end(Shard& s, int which, cudaStream_t st)
+{
+    SDPA_CUDA_TRY(cudaEventRecord(s.tev[which][s.tev_used[which] + 1], st));
+    s.tev_used[which] += 2;
+    return SDPA_OK;
+}
+
+static size_t elem_size(int prec) { return prec == SDPA_PREC_BF16 ? 2 : 4; }
+
+static sdpa_status cast_in(int prec, void* dst, const double* src, size_t count, cudaStream_t st)
+{
+    if (prec == SDPA_PREC_BF16) return launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst), src, count, st);
+    return launch_cvt_d2f(reinterpret_cast<float*>(dst), src, count, st);
+}
+
+static int resolve_precision(int requested, int dk, int dv)
+{
+    if (requested == SDPA_PREC_BF16) return SDPA_PREC_BF16;
+    if (requested == SDPA_PREC_F32) return SDPA_PREC_F32;
+    return attn_umma_supported(dk, dv) ? SDPA_PREC_BF16 : SDPA_PREC_F32;
+}
+
+static sdpa_status shard_init(Shard& s)
+{
+    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    SDPA_CUDA_TRY(cudaStreamCreateWithFlags(&s.s_in, cudaStreamNonBlocking));
+    SDPA_CUDA_TRY(cudaStreamCreateWithFlags(&s.s_compute, cudaStreamNonBlocking));
+    SDPA_CUDA_TRY(cudaStreamCreateWithFlags(&s.s_comm, cudaStreamNonBlocking));
+    SDPA_CUDA_TRY(cudaStreamCreateWithFlags(&s.s_out, cudaStreamNonBlocking));
+    auto mk = [](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming); };
+    for (int b = 0; b < 2; ++b) {
+        SDPA_CUDA_TRY(mk(&s.ev_stage_ready[b]));
+        SDPA_CUDA_TRY(mk(&s.ev_stage_free[b]));
+        SDPA_CUDA_TRY(mk(&s.ev_q_ready[b]));
+        SDPA_CUDA_TRY(mk(&s.ev_q_free[b]));
+        SDPA_CUDA_TRY(mk(&s.ev_compute_done[b]));
+        SDPA_CUDA_TRY(mk(&s.ev_slot_free[b]));
+        SDPA_CUDA_TRY(mk(&s.ev_comm_done[b]));
+    }
+    for (int j = 0; j < 3; ++j) SDPA_CUDA_TRY(mk(&s.ev_join[j]));
+    SDPA_CUDA_TRY(cudaEventCreate(&s.ev_begin));
+    SDPA_CUDA_TRY(cudaEventCreate(&s.ev_end));
+    int sms = 0;
+    SDPA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.dev));
+    s.sm_count = sms > 0 ? sms : 148;
+    return SDPA_OK;
+}
+
+static void shard_destroy(Shard& s, const NcclApi* api)
+{
+    cudaSetDevice(s.dev);
+    cudaDeviceSynchronize();
+    if (s.comm && api) api->CommDestroy(s.comm);
+    if (s.plan) umma_plan_destroy(s.plan);
+    DevBuf* bufs[] = {&s.Kc, &s.Vc, &s.kv_stage[0], &s.kv_stage[1], &s.q64[0], &s.q64[1], &s.qc[0], &s.qc[1],
+                      &s.part_o, &s.part_tmax, &s.part_lsum, &s.contrib[0], &s.contrib[1], &s.tmax[0],
+                      &s.tmax[1], &s.lsum[0], &s.lsum[1], &s.gmax[0], &s.gmax[1], &s.gsum[0], &s.gsum[1],
+                      &s.out32[0], &s.out32[1], &s.out64[0], &s.out64[1]};
+    for (DevBuf* b : bufs) b->release();
+    cudaEvent_t evs[] = {s.ev_stage_ready[0], s.ev_stage_ready[1], s.ev_stage_free[0], s.ev_stage_free[1],
+                         s.ev_q_ready[0], s.ev_q_ready[1], s.ev_q_free[0], s.ev_q_free[1],
+                         s.ev_compute_done[0], s.ev_compute_done[1], s.ev_slot_free[0], s.ev_slot_free[1],
+                         s.ev_comm_done[0], s.ev_comm_done[1], s.ev_begin, s.ev_end,
+                         s.ev_join[0], s.ev_join[1], s.ev_join[2]};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    for (int w = 0; w < 3; ++w)
+        for (cudaEvent_t e : s.tev[w]) cudaEventDestroy(e);
+    cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out};
+    for (cudaStream_t st : sts)
+        if (st) cudaStreamDestroy(st);
+}
+
+// K/V chunk size for the fp64 staging buffers (elements).
+static const size_t kStageElems = (size_t)4 << 20;  // 32 MiB of fp64 per chunk
+
+// Upload (or read in place) one operand of the shard and cast it into `dst`.
+static sdpa_status upload_cast(Shard& s, int prec, void* dst, const double* src, size_t count, bool src_on_device)
+{
+    const size_t esz = elem_size(prec);
+    if (src_on_device) {
+        SDPA_TRY(cast_in(prec, dst, src, count, s.s_compute));
+        return SDPA_OK;
+    }
+    size_t done = 0;
+    int c = 0;
+    while (done < count) {
+        const size_t len = std::min(kStageElems, count - done);
+        const int b = c & 1;
+        SDPA_TRY(s.kv_stage[b].reserve(std::min(kStageElems, count) * sizeof(double)));
+        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_stage_free[b], 0));
+        SDPA_CUDA_TRY(cudaMemcpyAsync(s.kv_stage[b].p, src + done, len * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
+        SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_ready[b], s.s_in));
+        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_stage_ready[b], 0));
+        SDPA_TRY(cast_in(prec, (char*)dst + done * esz, s.kv_stage[b].as<double>(), len, s.s_compute));
+        SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_free[b], s.s_compute));
+        done += len;
+        ++c;
+    }
+    return SDPA_OK;
+}
+
+static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
+                           const int* n_local, int dk, int dv, bool on_device)
+{
+    if (!ctx || !n_local || dk < 1 || dv < 1) {
+        set_error("load_kv: bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    const int prec = resolve_precision(ctx->cfg.precision, dk, dv);
+    if (prec == SDPA_PREC_BF16 && !attn_umma_supported(dk, dv)) {
+        set_error("bf16 tensor-core kernel supports dk == dv in {64,128} (got dk=%d dv=%d)", dk, dv);
+        return SDPA_ERR_UNSUPPORTED;
+    }
+    if (prec == SDPA_PREC_F32 && !attn_f32_supported(dk, dv)) {
+        set_error("fp32 kernel supports 1 <= dk, dv <= 256 (got dk=%d dv=%d)", dk, dv);
+        return SDPA_ERR_UNSUPPORTED;
+    }
+    ctx->dk = dk;
+    ctx->dv = dv;
+    ctx->prec = prec;
+    const size_t esz = elem_size(prec);
+    for (size_t i = 0; i < ctx->shards.size(); ++i) {
+        Shard& s = ctx->shards[i];
+        if (n_local[i] < 0 || (n_local[i] > 0 && (!K_shards || !V_shards || !K_shards[i] || !V_shards[i]))) {
+            set_error("load_kv: shard %zu has n_local=%d but a NULL K/V pointer", i, n_local[i]);
+            return SDPA_ERR_INVALID;
+        }
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        s.n_local = n_local[i];
+        // +128 rows of slack so TMA boxes / vector loads past the last row stay in bounds
+        SDPA_TRY(s.Kc.reserve(((size_t)s.n_local + 128) * dk * esz));
+        SDPA_TRY(s.Vc.reserve(((size_t)s.n_local + 128) * dv * esz));
+        if (s.n_local > 0) {
+            SDPA_TRY(upload_cast(s, prec, s.Kc.p, K_shards[i], (size_t)s.n_local * dk, on_device));
+            SDPA_TRY(upload_cast(s, prec, s.Vc.p, V_shards[i], (size_t)s.n_local * dv, on_device));
+        }
+        if (prec == SDPA_PREC_BF16) {
+            if (!s.plan) SDPA_TRY(umma_plan_create(&s.plan));
+            SDPA_TRY(umma_plan_bind_kv(s.plan, s.Kc.as<__nv_bfloat16>(), s.Vc.as<__nv_bfloat16>(), s.n_local, dk, dv));
+        }
+    }
+    for (Shard& s : ctx->shards) {
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+    }
+    return SDPA_OK;
+}
+
+static int pick_q_batch(const sdpa_ctx* ctx, int m)
+{
+    int B = ctx->cfg.q_batch;
+    if (B <= 0) {
+        // Engine default: the reference's B=512 (mpi.c:200) is sized for MPI latency on CPUs.
+        // On NVLink the per-batch exchange is ~tens of microseconds, so batches are made as large
+        // as keeps >= 2 batches in flight for the ping-pong overlap.
+        B = 4096;
+        if (m > 2 * B) B = 8192;
+    }
+    if (B > m) B = m;
+    if (B < 1) B = 1;
+    return B;
+}
+
+static sdpa_status reserve_batch_buffers(sdpa_ctx* ctx, Shard& s, int B, int splits, bool root)
+{
+    const size_t esz = elem_size(ctx->prec);
+    const int dk = ctx->dk, dv = ctx->dv;
+    const int Bpad = (B + 127) & ~127;
+    for (int b = 0; b < 2; ++b) {
+        SDPA_TRY(s.q64[b].reserve((size_t)B * dk * sizeof(double)));
+        SDPA_TRY(s.qc[b].reserve((size_t)(Bpad + 128) * dk * esz));
+        SDPA_TRY(s.contrib[b].reserve((size_t)B * dv * sizeof(float)));
+        SDPA_TRY(s.tmax[b].reserve((size_t)B * sizeof(float)));
+        SDPA_TRY(s.lsum[b].reserve((size_t)B * sizeof(float)));
+        SDPA_TRY(s.gmax[b].reserve((size_t)B * sizeof(float)));
+        SDPA_TRY(s.gsum[b].reserve((size_t)B * sizeof(float)));
+        if (root) {
+            SDPA_TRY(s.out32[b].reserve((size_t)B * dv * sizeof(float)));
+            SDPA_TRY(s.out64[b].reserve((size_t)B * dv * sizeof(double)));
+        }
+    }
+    SDPA_TRY(s.part_o.reserve((size_t)splits * B * dv * sizeof(float)));
+    SDPA_TRY(s.part_tmax.reserve((size_t)splits * B * sizeof(float)));
+    SDPA_TRY(s.part_lsum.reserve((size_t)splits * B * sizeof(float)));
+    return SDPA_OK;
+}
+
+// The fused kernel for one batch on one shard: fills the split partials, or writes fp64 directly.
+static sdpa_status run_fused(sdpa_ctx* ctx, Shard& s, int slot, int rows, int splits, Partials part, double* direct_out)
+{
+    if (ctx->prec == SDPA_PREC_BF16) {
+        return launch_attn_umma(s.plan, slot, rows, splits, part, direct_out, s.sm_count, s.s_compute);
+    }
+    return launch_attn_f32(s.qc[slot].as<float>(), s.Kc.as<float>(), s.Vc.as<float>(), rows, s.n_local, ctx->dk,
+                           ctx->dv, splits, part, direct_out, s.s_compute);
+}
+
+static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const double* const* Q_dev,
+                                  double* result, bool result_on_device, int m, bool q_from_root = false)
+{
+    if (!ctx || m < 0) {
+        set_error("attention: bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    if (ctx->dk == 0) {
+        set_error("attention: no K/V shard loaded (call sdpa_load_kv_* first)");
+        return SDPA_ERR_INVALID;
+    }
+    const bool on_device = Q_dev != nullptr;
+    if (m > 0 && !on_device && !Q_host && !(q_from_root && !ctx->has_root())) {
+        set_error("attention: Q is NULL");
+        return SDPA_ERR_INVALID;
+    }
+    if (m > 0 && ctx->has_root() && !result) {
+        set_error("attention: result is NULL on the process that owns shard 0");
+        return SDPA_ERR_INVALID;
+    }
+    const int dk = ctx->dk, dv = ctx->dv;
+    const int world = ctx->world;
+    const int L = (int)ctx->shards.size();
+    const NcclApi* api = nullptr;
+    const bool use_peer = world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && ctx->peer_ok && world == L;
+    if ((world > 1 && !use_peer) || q_from_root) {
+        api = nccl_api();
+        if (!api) return SDPA_ERR_NCCL;
+    }
+    ctx->last_kernel = ctx->prec == SDPA_PREC_BF16 ? "bf16_umma" : "f32_simt";
+    for (float& t : ctx->last_timing) t = 0.f;
+    if (m == 0) return SDPA_OK;
+
+    const int B = pick_q_batch(ctx, m);
+    const int num_iter = ceil_div(m, B);
+
+    // split-KV factor (same on every shard so the partial buffers match)
+    int splits = ctx->cfg.kv_splits;
+    if (splits <= 0) {
+        int nmax = 0;
+        for (Shard& s : ctx->shards) nmax = std::max(nmax, s.n_local);
+        splits = ctx->prec == SDPA_PREC_BF16 ? attn_umma_pick_splits(B, nmax, ctx->shards[0].sm_count)
+                                             : attn_f32_pick_splits(B, nmax, ctx->shards[0].sm_count);
+    }
+    splits = std::max(1, std::min(splits, 64));
+
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        SDPA_TRY(reserve_batch_buffers(ctx, s, B, splits, s.grank == 0));
+        for (int w = 0; w < 3; ++w) s.tev_used[w] = 0;
+        if (ctx->prec == SDPA_PREC_BF16)
+            for (int b = 0; b < 2; ++b)
+                SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk));
+        SDPA_CUDA_TRY(cudaEventRecord(s.ev_begin, s.s_compute));
+        // the other streams start after ev_begin so that "total" brackets everything
+        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_begin, 0));
+        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_begin, 0));
+        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, s.ev_begin, 0));
+    }
+
+    int fused_launches = 0, all_launches = 0;
+
+    for (int ii = 0; ii < num_iter; ++ii) {
+        const int row0 = ii * B;
+        const int bs = std::min(B, m - row0);
+        const int b = ii & 1;
+
+        // ---- per shard: Q batch in, cast, fused kernel, split merge -------------------------
+        for (int i = 0; i < L; ++i) {
+            Shard& s = ctx->shards[i];
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            const bool single = (world == 1);
+            const double* q_src_dev = nullptr;
+            const bool have_q = !q_from_root || s.grank == 0;  // q_from_root: only shard 0's process holds Q
+            if (on_device) {
+                q_src_dev = Q_dev[i] + (size_t)row0 * dk;
+            } else if (have_q) {
+                // copy stream: wait until the cast of batch ii-2 released this buffer
+                if (ii >= 2) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_q_free[b], 0));
+                SDPA_CUDA_TRY(cudaMemcpyAsync(s.q64[b].p, Q_host + (size_t)row0 * dk, (size_t)bs * dk * sizeof(double),
+                                              cudaMemcpyHostToDevice, s.s_in));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_ready[b], s.s_in));
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_q_ready[b], 0));
+                q_src_dev = s.q64[b].as<double>();
+            }
+            // slot b (contrib/out buffers) must have been drained by batch ii-2's collectives / D2H
+            if (ii >= 2) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_slot_free[b], 0));
+
+            SDPA_TRY(time_begin(s, 0, s.s_compute));
+            if (have_q) {
+                SDPA_TRY(cast_in(ctx->prec, s.qc[b].p, q_src_dev, (size_t)bs * dk, s.s_compute));
+                ++all_launches;
+            }
+            if (q_from_root)  // the Q batch travels in compute precision (mpi.c:305,327: Ibcast of the fp32 batch)
+                SDPA_NCCL_TRY(api->Broadcast(s.qc[b].p, s.qc[b].p, (size_t)bs * dk * elem_size(ctx->prec), ncclUint8, 0,
+                                             s.comm, s.s_compute));
+            SDPA_TRY(time_end(s, 0, s.s_compute));
+            if (!on_device && have_q) SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_free[b], s.s_compute));
+
+            Partials part{s.part_o.as<float>(), s.part_tmax.as<float>(), s.part_lsum.as<float>(), splits, B};
+            double* final_dst = nullptr;  // where the fp64 rows of this batch go when no cross-GPU merge is needed
+            if (single) final_dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+
+            SDPA_TRY(time_begin(s, 1, s.s_compute));
+            SDPA_TRY(run_fused(ctx, s, b, bs, splits, part, (single && splits == 1) ? final_dst : nullptr));
+            SDPA_TRY(time_end(s, 1, s.s_compute));
+            ++fused_launches;
+            ++all_launches;
+
+            if (!(single && splits == 1)) {
+                SDPA_TRY(time_begin(s, 2, s.s_compute));
+                if (single) {
+                    SDPA_TRY(launch_merge_splits(part, bs, dv, final_dst, nullptr, nullptr, nullptr, false, s.s_compute));
+                } else {
+                    SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, s.contrib[b].as<float>(), s.tmax[b].as<float>(),
+                                                 s.lsum[b].as<float>(), false, s.s_compute));
+                }
+                SDPA_TRY(time_end(s, 2, s.s_compute));
+                ++all_launches;
+            }
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
+        }
+
+        // ---- cross-shard merge ----------------------------------------------------------------
+        if (world > 1 && use_peer) {
+            // fused device-side exchange: the root GPU reads every shard's state over NVLink
+            Shard& r = ctx->shards[0];
+            SDPA_CUDA_TRY(cudaSetDevice(r.dev));
+            const float* cp[64];
+            const float* tp[64];
+            const float* lp[64];
+            for (int i = 0; i < L; ++i) {
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(r.s_comm, ctx->shards[i].ev_compute_done[b], 0));
+                cp[i] = ctx->shards[i].contrib[b].as<float>();
+                tp[i] = ctx->shards[i].tmax[b].as<float>();
+                lp[i] = ctx->shards[i].lsum[b].as<float>();
+            }
+            double* dst = result_on_device ? result + (size_t)row0 * dv : r.out64[b].as<double>();
+            SDPA_TRY(time_begin(r, 2, r.s_comm));
+            SDPA_TRY(launch_merge_peers(cp, tp, lp, L, bs, dv, dst, r.s_comm));
+            SDPA_TRY(time_end(r, 2, r.s_comm));
+            ++all_launches;
+            SDPA_CUDA_TRY(cudaEventRecord(r.ev_comm_done[b], r.s_comm));
+            for (int i = 1; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+                // shard i's slot is free once the root has read it
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, r.ev_comm_done[b], 0));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+            }
+        } else if (world > 1) {
+            // the reference's three collectives (mpi.c:342,354,380), one NCCL group per step
+            for (int i = 0; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
+                SDPA_TRY(time_begin(s, 2, s.s_comm));
+            }
+            SDPA_NCCL_TRY(api->GroupStart());
+            for (int i = 0; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                SDPA_NCCL_TRY(api->AllReduce(s.tmax[b].p, s.gmax[b].p, (size_t)bs, ncclFloat32, ncclMax, s.comm, s.s_comm));
+            }
+            SDPA_NCCL_TRY(api->GroupEnd());
+            for (int i = 0; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+                SDPA_TRY(launch_rescale_to_gmax(s.contrib[b].as<float>(), s.lsum[b].as<float>(), s.tmax[b].as<float>(),
+                                                s.gmax[b].as<float>(), bs, dv, s.s_comm));
+                ++all_launches;
+            }
+            SDPA_NCCL_TRY(api->GroupStart());
+            for (int i = 0; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                SDPA_NCCL_TRY(api->AllReduce(s.lsum[b].p, s.gsum[b].p, (size_t)bs, ncclFloat32, ncclSum, s.comm, s.s_comm));
+            }
+            SDPA_NCCL_TRY(api->GroupEnd());
+            for (int i = 0; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+                SDPA_TRY(launch_normalize(s.contrib[b].as<float>(), s.gsum[b].as<float>(), bs, dv, s.s_comm));
+                ++all_launches;
+            }
+            SDPA_NCCL_TRY(api->GroupStart());
+            for (int i = 0; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                void* recv = s.grank == 0 ? s.out32[b].p : nullptr;
+                SDPA_NCCL_TRY(api->Reduce(s.contrib[b].p, recv, (size_t)bs * dv, ncclFloat32, ncclSum, 0, s.comm, s.s_comm));
+            }
+            SDPA_NCCL_TRY(api->GroupEnd());
+            for (int i = 0; i < L; ++i) {
+                Shard& s = ctx->shards[i];
+                SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+                if (s.grank == 0) {
+                    double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+                    SDPA_TRY(launch_cvt_f2d(dst, s.out32[b].as<float>(), (size_t)bs * dv, s.s_comm));  // mpi.c:373
+                    ++all_launches;
+                }
+                SDPA_TRY(time_end(s, 2, s.s_comm));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
+                if (s.grank != 0) SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+            }
+        }
+
+        // ---- root: fp64 rows of this batch back to the host ------------------------------------
+        for (int i = 0; i < L; ++i) {
+            Shard& s = ctx->shards[i];
+            if (s.grank != 0) continue;
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            cudaEvent_t ready = world > 1 ? s.ev_comm_done[b] : s.ev_compute_done[b];
+            SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, ready, 0));
+            if (!result_on_device)
+                SDPA_CUDA_TRY(cudaMemcpyAsync(result + (size_t)row0 * dv, s.out64[b].p, (size_t)bs * dv * sizeof(double),
+                                              cudaMemcpyDeviceToHost, s.s_out));
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_out));
+        }
+    }
+
+    // ---- join: every stream back into the compute stream, then wait ----------------------------
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        cudaStream_t side[3] = {s.s_in, s.s_comm, s.s_out};
+        for (int j = 0; j < 3; ++j) {
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_join[j], side[j]));
+            SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_join[j], 0));
+        }
+        SDPA_CUDA_TRY(cudaEventRecord(s.ev_end, s.s_compute));
+    }
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+    }
+
+    // ---- timings (max over local shards) --------------------------------------------------------
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        float total = 0.f;
+        SDPA_CUDA_TRY(cudaEventElapsedTime(&total, s.ev_begin, s.ev_end));
+        float acc[3] = {0.f, 0.f, 0.f};
+        for (int w = 0; w < 3; ++w)
+            for (size_t k = 0; k + 1 < s.tev_used[w]; k += 2) {
+                float ms = 0.f;
+                SDPA_CUDA_TRY(cudaEventElapsedTime(&ms, s.tev[w][k], s.tev[w][k + 1]));
+                acc[w] += ms;
+            }
+        ctx->last_timing[0] = std::max(ctx->last_timing[0], total);
+        ctx->last_timing[1] = std::max(ctx->last_timing[1], acc[0]);
+        ctx->last_timing[2] = std::max(ctx->last_timing[2], acc[1]);
+        ctx->last_timing[3] = std::max(ctx->last_timing[3], acc[2]);
+    }
+    ctx->last_timing[4] = (float)fused_launches;
+    ctx->last_timing[5] = (float)all_launches;
+    return SDPA_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// One process per GPU, data on rank 0 only: the reference's own calling convention
+// (mpi.c:193-197 dims Bcast, mpi.c:213-266 K/V distribution, mpi.c:305,327 Q Ibcast).
+// Rank 0 uploads each destination's rows in fp64 chunks, casts them on its GPU and
+// ncclSend()s the compute-precision chunk; rank r ncclRecv()s straight into its shard.
+// ---------------------------------------------------------------------------
+static sdpa_status scatter_operand(sdpa_ctx* ctx, Shard& s, const NcclApi* api, int prec, void* my_dst,
+                                   const double* src_full, int n, int width, DevBuf* sendbuf)
+{
+    const size_t esz = elem_size(prec);
+    const int world = ctx->world;
+    if (s.grank == 0) {
+        for (int r = 0; r < world; ++r) {
+            const size_t count = (size_t)sdpa_owner_count(n, world, r) * width;
+            const double* src = src_full + (size_t)sdpa_owner_disp(n, world, r) * width;
+            size_t done = 0;
+            int c = 0;
+            while (done < count) {
+                const size_t len = std::min(kStageElems, count - done);
+                const int b = c & 1;
+                SDPA_TRY(s.kv_stage[b].reserve(kStageElems * sizeof(double)));
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_stage_free[b], 0));
+                SDPA_CUDA_TRY(cudaMemcpyAsync(s.kv_stage[b].p, src + done, len * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_ready[b], s.s_in));
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_stage_ready[b], 0));
+                void* dst = (char*)my_dst + done * esz;
+                if (r != 0) {
+                    SDPA_TRY(sendbuf[b].reserve(kStageElems * esz));
+                    dst = sendbuf[b].p;
+                }
+                SDPA_TRY(cast_in(prec, dst, s.kv_stage[b].as<double>(), len, s.s_compute));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_free[b], s.s_compute));
+                if (r != 0) SDPA_NCCL_TRY(api->Send(dst, len * esz, ncclUint8, r, s.comm, s.s_compute));
+                done += len;
+                ++c;
+            }
+        }
+    } else {
+        const size_t count = (size_t)sdpa_owner_count(n, world, s.grank) * width;
+        size_t done = 0;
+        while (done < count) {
+            const size_t len = std::min(kStageElems, count - done);
+            SDPA_NCCL_TRY(api->Recv((char*)my_dst + done * esz, len * esz, ncclUint8, 0, s.comm, s.s_compute));
+            done += len;
+        }
+    }
+    return SDPA_OK;
+}
+
+static sdpa_status scatter_attention_impl(sdpa_ctx* ctx, const double* Q, const double* K, const double* V,
+                                          double* result, int m, int n, int dk, int dv)
+{
+    if (!ctx || ctx->shards.size() != 1 || ctx->world < 2) {
+        set_error("scatter attention needs a one-GPU-per-process context with world_size > 1");
+        return SDPA_ERR_INVALID;
+    }
+    const NcclApi* api = nccl_api();
+    if (!api) return SDPA_ERR_NCCL;
+    Shard& s = ctx->shards[0];
+    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    // dims from rank 0 (mpi.c:193-197)
+    int dims[4] = {m, n, dk, dv};
+    SDPA_TRY(s.gmax[0].reserve(256));
+    if (s.grank == 0) SDPA_CUDA_TRY(cudaMemcpyAsync(s.gmax[0].p, dims, sizeof(dims), cudaMemcpyHostToDevice, s.s_compute));
+    SDPA_NCCL_TRY(api->Broadcast(s.gmax[0].p, s.gmax[0].p, 4, ncclInt32, 0, s.comm, s.s_compute));
+    SDPA_CUDA_TRY(cudaMemcpyAsync(dims, s.gmax[0].p, sizeof(dims), cudaMemcpyDeviceToHost, s.s_compute));
+    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+    m = dims[0]; n = dims[1]; dk = dims[2]; dv = dims[3];
+    if (m < 0 || n < 0 || dk < 1 || dv < 1) {
+        set_error("attention(): bad dimensions m=%d n=%d dk=%d dv=%d", m, n, dk, dv);
+        return SDPA_ERR_INVALID;
+    }
+    if (s.grank == 0 && ((n > 0 && (!K || !V)) || (m > 0 && (!Q || !result)))) {
+        set_error("attention(): NULL input on rank 0");
+        return SDPA_ERR_INVALID;
+    }
+    const int prec = resolve_precision(ctx->cfg.precision, dk, dv);
+    if ((prec == SDPA_PREC_BF16 && !attn_umma_supported(dk, dv)) || (prec == SDPA_PREC_F32 && !attn_f32_supported(dk, dv))) {
+        set_error("no kernel for dk=%d dv=%d at the requested precision", dk, dv);
+        return SDPA_ERR_UNSUPPORTED;
+    }
+    ctx->dk = dk;
+    ctx->dv = dv;
+    ctx->prec = prec;
+    const size_t esz = elem_size(prec);
+    s.n_local = sdpa_owner_count(n, ctx->world, s.grank);
+    SDPA_TRY(s.Kc.reserve(((size_t)s.n_local + 128) * dk * esz));
+    SDPA_TRY(s.Vc.reserve(((size_t)s.n_local + 128) * dv * esz));
+    DevBuf sendbuf[2];
+    sdpa_status st = scatter_operand(ctx, s, api, prec, s.Kc.p, K, n, dk, sendbuf);
+    if (st == SDPA_OK) st = scatter_operand(ctx, s, api, prec, s.Vc.p, V, n, dv, sendbuf);
+    if (st == SDPA_OK && cudaStreamSynchronize(s.s_compute) != cudaSuccess) {
+        set_error("K/V scatter failed: %s", cudaGetErrorString(cudaGetLastError()));
+        st = SDPA_ERR_CUDA;
+    }
+    sendbuf[0].release();
+    sendbuf[1].release();
+    SDPA_TRY(st);
+    if (prec == SDPA_PREC_BF16) {
+        if (!s.plan) SDPA_TRY(umma_plan_create(&s.plan));
+        SDPA_TRY(umma_plan_bind_kv(s.plan, s.Kc.as<__nv_bfloat16>(), s.Vc.as<__nv_bfloat16>(), s.n_local, dk, dv));
+    }
+    return attention_impl(ctx, Q, nullptr, result, false, m, /*q_from_root=*/true);
+}
+
+}  // namespace sdpa
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* sdpa_last_error(void) { return sdpa::get_error(); }
+const char* sdpa_version(void) { return "sdpa_b200 0.1 (sm_100a)"; }
+
+int sdpa_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+/* mpi.c:19-22 */
+int sdpa_owner_count(int n, int size, int rank)
+{
+    if (size <= 0) return 0;
+    const int q = n / size, r = n % size;
+    return q + (rank < r ? 1 : 0);
+}
+
+/* mpi.c:24-27 */
+int sdpa_owner_disp(int n, int size, int rank)
+{
+    if (size <= 0) return 0;
+    const int q = n / size, r = n % size;
+    return rank * q + (rank < r ? rank : r);
+}
+
+void sdpa_config_init(sdpa_config* cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->precision = SDPA_PREC_AUTO;
+    cfg->merge = SDPA_MERGE_NCCL;
+    cfg->num_local = 1;
+}
+
+sdpa_status sdpa_get_unique_id(void* out128)
+{
+    if (!out128) {
+        set_error("sdpa_get_unique_id: NULL output");
+        return SDPA_ERR_INVALID;
+    }
+    const NcclApi* api = nccl_api();
+    if (!api) return SDPA_ERR_NCCL;
+    ncclUniqueId id;
+    SDPA_NCCL_TRY(api->GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return SDPA_OK;
+}
+
+sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const void* nccl_id)
+{
+    if (!out) {
+        set_error("sdpa_ctx_create: NULL output");
+        return SDPA_ERR_INVALID;
+    }
+    *out = nullptr;
+    sdpa_config cfg;
+    if (cfg_in) cfg = *cfg_in;
+    else sdpa_config_init(&cfg);
+    const int L = cfg.num_local > 0 ? cfg.num_local : 1;
+    const int world = cfg.world_size > 0 ? cfg.world_size : L;
+    if (cfg.rank_base < 0 || cfg.rank_base + L > world || L > 64 || world > 64) {
+        set_error("sdpa_ctx_create: inconsistent shard layout (num_local=%d rank_base=%d world=%d; max 64)", L,
+                  cfg.rank_base, world);
+        return SDPA_ERR_INVALID;
+    }
+    int ndev = sdpa_device_count();
+    if (ndev <= 0) {
+        set_error("no CUDA device visible: this engine has no CPU fallback");
+        return SDPA_ERR_CUDA;
+    }
+    if (cfg.first_device < 0 || cfg.first_device + L > ndev) {
+        set_error("sdpa_ctx_create: devices [%d,%d) requested but %d visible", cfg.first_device, cfg.first_device + L, ndev);
+        return SDPA_ERR_INVALID;
+    }
+    if (world > L && !nccl_id) {
+        set_error("sdpa_ctx_create: world_size %d > num_local %d needs a shared ncclUniqueId", world, L);
+        return SDPA_ERR_INVALID;
+    }
+    sdpa_ctx* ctx = new sdpa_ctx();
+    ctx->cfg = cfg;
+    ctx->world = world;
+    ctx->rank_base = cfg.rank_base;
+    ctx->shards.resize(L);
+    sdpa_status st = SDPA_OK;
+    for (int i = 0; i < L && st == SDPA_OK; ++i) {
+        ctx->shards[i].dev = cfg.first_device + i;
+        ctx->shards[i].grank = cfg.rank_base + i;
+        st = shard_init(ctx->shards[i]);
+    }
+    // peer access among the local GPUs (for the fused exchange)
+    if (st == SDPA_OK && L > 1) {
+        bool all = true;
+        for (int i = 0; i < L; ++i)
+            for (int j = 0; j < L; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, ctx->shards[i].dev, ctx->shards[j].dev);
+                if (!can) { all = false; continue; }
+                cudaSetDevice(ctx->shards[i].dev);
+                cudaError_t e = cudaDeviceEnablePeerAccess(ctx->shards[j].dev, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) all = false;
+                cudaGetLastError();
+            }
+        ctx->peer_ok = all;
+    }
+    // NCCL communicator(s)
+    const bool need_nccl = world > 1 && !(cfg.merge == SDPA_MERGE_PEER && ctx->peer_ok && world == L);
+    if (st == SDPA_OK && need_nccl) {
+        const NcclApi* api = nccl_api();
+        if (!api) st = SDPA_ERR_NCCL;
+        else {
+            ncclUniqueId id;
+            if (nccl_id) memcpy(&id, nccl_id, sizeof(id));
+            else if (api->GetUniqueId(&id) != ncclSuccess) st = SDPA_ERR_NCCL;
+            if (st == SDPA_OK) {
+                ncclResult_t r = api->GroupStart();
+                for (int i = 0; i < L && r == ncclSuccess; ++i) {
+                    cudaSetDevice(ctx->shards[i].dev);
+                    r = api->CommInitRank(&ctx->shards[i].comm, world, id, ctx->shards[i].grank);
+                }
+                ncclResult_t r2 = api->GroupEnd();
+                if (r != ncclSuccess || r2 != ncclSuccess) {
+                    set_error("ncclCommInitRank failed: %s", api->GetErrorString(r != ncclSuccess ? r : r2));
+                    st = SDPA_ERR_NCCL;
+                }
+            }
+        }
+    }
+    if (st != SDPA_OK) {
+        for (Shard& s : ctx->shards) shard_destroy(s, nullptr);
+        delete ctx;
+        return st;
+    }
+    *out = ctx;
+    return SDPA_OK;
+}
+
+sdpa_status sdpa_ctx_destroy(sdpa_ctx* ctx)
+{
+    if (!ctx) return SDPA_OK;
+    const NcclApi* api = nullptr;
+    for (Shard& s : ctx->shards)
+        if (s.comm) api = nccl_api();
+    for (Shard& s : ctx->shards) shard_destroy(s, api);
+    delete ctx;
+    return SDPA_OK;
+}
+
+sdpa_status sdpa_load_kv_host(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
+                              const int* n_local, int dk, int dv)
+{
+    return load_kv(ctx, K_shards, V_shards, n_local, dk, dv, false);
+}
+
+sdpa_status sdpa_load_kv_device(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
+                                const int* n_local, int dk, int dv)
+{
+    return load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true);
+}
+
+sdpa_status sdpa_load_kv_host_full(sdpa_ctx* ctx, const double* K, const double* V, int n, int dk, int dv)
+{
+    if (!ctx || n < 0) {
+        set_error("sdpa_load_kv_host_full: bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    if (ctx->world != (int)ctx->shards.size()) {
+        set_error("sdpa_load_kv_host_full needs a single-process context (world == num_local)");
+        return SDPA_ERR_INVALID;
+    }
+    const int L = (int)ctx->shards.size();
+    std::vector<const double*> kp(L), vp(L);
+    std::vector<int> cnt(L);
+    for (int i = 0; i < L; ++i) {
+        cnt[i] = sdpa_owner_count(n, L, i);
+        const int d = sdpa_owner_disp(n, L, i);
+        kp[i] = K ? K + (size_t)d * dk : nullptr;
+        vp[i] = V ? V + (size_t)d * dv : nullptr;
+    }
+    return load_kv(ctx, kp.data(), vp.data(), cnt.data(), dk, dv, false);
+}
+
+sdpa_status sdpa_attention_host(sdpa_ctx* ctx, const double* Q, double* result, int m)
+{
+    return attention_impl(ctx, Q, nullptr, result, false, m);
+}
+
+sdpa_status sdpa_attention_device(sdpa_ctx* ctx, const double* const* Q_dev, double* result_dev, int m)
+{
+    if (m > 0 && !Q_dev) {
+        set_error("sdpa_attention_device: Q_dev is NULL");
+        return SDPA_ERR_INVALID;
+    }
+    return attention_impl(ctx, nullptr, Q_dev, result_dev, true, m);
+}
+
+sdpa_status sdpa_online_softmax_partials(sdpa_ctx* ctx, int local, const float* Qf_dev, int m, float* contrib_dev,
+                                         float* lmax_dev, float* lsum_dev)
+{
+    if (!ctx || local < 0 || local >= (int)ctx->shards.size() || m < 0) {
+        set_error("sdpa_online_softmax_partials: bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    if (ctx->dk == 0 || ctx->prec != SDPA_PREC_F32) {
+        set_error("sdpa_online_softmax_partials needs a resident fp32 K/V shard (precision f32)");
+        return SDPA_ERR_INVALID;
+    }
+    if (m == 0) return SDPA_OK;
+    Shard& s = ctx->shards[local];
+    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    int splits = ctx->cfg.kv_splits > 0 ? ctx->cfg.kv_splits : attn_f32_pick_splits(m, s.n_local, s.sm_count);
+    splits = std::max(1, std::min(splits, 64));
+    SDPA_TRY(s.part_o.reserve((size_t)splits * m * ctx->dv * sizeof(float)));
+    SDPA_TRY(s.part_tmax.reserve((size_t)splits * m * sizeof(float)));
+    SDPA_TRY(s.part_lsum.reserve((size_t)splits * m * sizeof(float)));
+    Partials part{s.part_o.as<float>(), s.part_tmax.as<float>(), s.part_lsum.as<float>(), splits, m};
+    SDPA_TRY(launch_attn_f32(Qf_dev, s.Kc.as<float>(), s.Vc.as<float>(), m, s.n_local, ctx->dk, ctx->dv, splits, part,
+                             nullptr, s.s_compute));
+    SDPA_TRY(launch_merge_splits(part, m, ctx->dv, nullptr, contrib_dev, lmax_dev, lsum_dev, true, s.s_compute));
+    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+    return SDPA_OK;
+}
+
+sdpa_status sdpa_scatter_attention(sdpa_ctx* ctx, const double* Q, const double* K, const double* V, double* result,
+                                   int m, int n, int dk, int dv)
+{
+    return scatter_attention_impl(ctx, Q, K, V, result, m, n, dk, dv);
+}
+
+sdpa_status sdpa_last_timings(sdpa_ctx* ctx, float* out6)
+{
+    if (!ctx || !out6) {
+        set_error("sdpa_last_timings: bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    memcpy(out6, ctx->last_timing, sizeof(ctx->last_timing));
+    return SDPA_OK;
+}
+
+const char* sdpa_last_kernel(sdpa_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+
+sdpa_status sdpa_cvt_d2f(float* dst_dev, const double* src_dev, size_t count, void* stream)
+{
+    return launch_cvt_d2f(dst_dev, src_dev, count, (cudaStream_t)stream);
+}
+sdpa_status sdpa_cvt_f2d(double* dst_dev, const float* src_dev, size_t count, void* stream)
+{
+    return launch_cvt_f2d(dst_dev, src_dev, count, (cudaStream_t)stream);
+}
+sdpa_status sdpa_cvt_d2bf16(uint16_t* dst_dev, const double* src_dev, size_t count, void* stream)
+{
+    return launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst_dev), src_dev, count, (cudaStream_t)stream);
+}
+
+}  // extern "C"

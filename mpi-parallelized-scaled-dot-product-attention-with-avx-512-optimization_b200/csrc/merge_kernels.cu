@@ -1,0 +1,164 @@
+// merge_kernels.cu -- merging partial softmax states (split-KV inside a GPU and K/V shards
+// across GPUs).  All of them evaluate the merge of attention-mpi.c:340-362 / SURVEY 3.3,
+//     gmax = max_r lmax_r ; c_r = e^(lmax_r - gmax) ; gsum = sum_r lsum_r c_r ;
+//     out  = sum_r contrib_r c_r / gsum          (gsum == 0 -> 0, mpi.c:359)
+// with the max kept in the log2 domain (tmax = lmax * log2 e, so c_r = 2^(tmax_r - gmax)).
+// These are O(rows * dv) HBM-bound passes; one warp owns one row, lanes stride over dv with
+// 16-byte vectors, and the row statistics are combined with warp shuffles.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace sdpa {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Generic combine over `count` partial states addressed through per-state base pointers.
+// Each state s: o_s[row*dv + d], tmax_s[row], lsum_s[row].
+struct StatePtrs {
+    const float* o[64];
+    const float* tmax[64];
+    const float* lsum[64];
+};
+
+template <bool FINAL>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict__ out64,
+                    float* __restrict__ contrib, float* __restrict__ tmax_out,
+                    float* __restrict__ lsum_out, float max_unit)
+{
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= rows) return;
+
+    // lanes hold the per-state statistics (count <= 64: two per lane)
+    float t0 = lane < count ? st.tmax[lane][row] : -CUDART_INF_F;
+    float t1 = lane + 32 < count ? st.tmax[lane + 32][row] : -CUDART_INF_F;
+    float gmax = fmaxf(t0, t1);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+    // all states empty (-inf): weights 0, output 0
+    const float w0 = (t0 == -CUDART_INF_F) ? 0.f : exp2f(t0 - gmax);
+    const float w1 = (t1 == -CUDART_INF_F) ? 0.f : exp2f(t1 - gmax);
+    float gsum = (lane < count ? st.lsum[lane][row] * w0 : 0.f) +
+                 (lane + 32 < count ? st.lsum[lane + 32][row] * w1 : 0.f);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
+    const float inv = (gsum == 0.f) ? 0.f : 1.f / gsum;
+
+    for (int d = lane; d < dv; d += 32) {
+        float acc = 0.f;
+        for (int s = 0; s < count; ++s) {
+            const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
+            acc = fmaf(st.o[s][(size_t)row * dv + d], w, acc);
+        }
+        if (FINAL) out64[(size_t)row * dv + d] = (double)(acc * inv);
+        else contrib[(size_t)row * dv + d] = acc;
+    }
+    if (!FINAL && lane == 0) {
+        tmax_out[row] = gmax * max_unit;  // max_unit = 1 (log2 domain) or ln2 (reference's lmax)
+        lsum_out[row] = gsum;
+    }
+}
+
+// contrib *= 2^(tmax - gmax), lsum *= 2^(tmax - gmax)        (mpi.c:346-351)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+rescale_kernel(float* __restrict__ contrib, float* __restrict__ lsum, const float* __restrict__ tmax,
+               const float* __restrict__ gmax, int rows, int dv)
+{
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= rows) return;
+    const float t = tmax[row];
+    const float c = (t == -CUDART_INF_F) ? 0.f : exp2f(t - gmax[row]);
+    for (int d = lane; d < dv; d += 32) contrib[(size_t)row * dv + d] *= c;
+    if (lane == 0) lsum[row] *= c;
+}
+
+// contrib *= (gsum == 0 ? 0 : 1/gsum)                         (mpi.c:358-362)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+normalize_kernel(float* __restrict__ contrib, const float* __restrict__ gsum, int rows, int dv)
+{
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= rows) return;
+    const float g = gsum[row];
+    const float inv = (g == 0.f) ? 0.f : 1.f / g;
+    for (int d = lane; d < dv; d += 32) contrib[(size_t)row * dv + d] *= inv;
+}
+
+}  // namespace
+
+sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, float* contrib,
+                                float* tmax_out, float* lsum_out, bool natural_log_max,
+                                cudaStream_t stream)
+{
+    if (rows <= 0) return SDPA_OK;
+    if (part.splits < 1 || part.splits > 64) {
+        set_error("merge supports 1..64 split states (got %d)", part.splits);
+        return SDPA_ERR_INVALID;
+    }
+    StatePtrs st;
+    for (int s = 0; s < part.splits; ++s) {
+        st.o[s] = part.o + (size_t)s * part.rows_capacity * dv;
+        st.tmax[s] = part.tmax + (size_t)s * part.rows_capacity;
+        st.lsum[s] = part.lsum + (size_t)s * part.rows_capacity;
+    }
+    const int blocks = ceil_div(rows, kWarpsPerBlock);
+    if (out64 != nullptr)
+        merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+            st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f);
+    else
+        merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
+            st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, natural_log_max ? kLn2 : 1.f);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
+                               const float* const* lsum_ptrs, int shards, int rows, int dv,
+                               double* out64, cudaStream_t stream)
+{
+    if (rows <= 0) return SDPA_OK;
+    if (shards < 1 || shards > 64) {
+        set_error("peer merge supports 1..64 shards (got %d)", shards);
+        return SDPA_ERR_INVALID;
+    }
+    StatePtrs st;
+    for (int s = 0; s < shards; ++s) {
+        st.o[s] = contrib_ptrs[s];
+        st.tmax[s] = tmax_ptrs[s];
+        st.lsum[s] = lsum_ptrs[s];
+    }
+    const int blocks = ceil_div(rows, kWarpsPerBlock);
+    merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr,
+                                                                         nullptr, nullptr, 1.f);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_rescale_to_gmax(float* contrib, float* lsum, const float* tmax, const float* gmax,
+                                   int rows, int dv, cudaStream_t stream)
+{
+    if (rows <= 0) return SDPA_OK;
+    rescale_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(contrib, lsum, tmax,
+                                                                                       gmax, rows, dv);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_normalize(float* contrib, const float* gsum, int rows, int dv, cudaStream_t stream)
+{
+    if (rows <= 0) return SDPA_OK;
+    normalize_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(contrib, gsum, rows, dv);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+}  // namespace sdpa

@@ -1,0 +1,52 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/sdpa_b200.h declares."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _declared_symbols():
+    text = (ROOT / "include" / "sdpa_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)
+    keep = [n for n in names if n == "attention" or n.startswith("sdpa_")]
+    return sorted(set(keep))
+
+
+def test_header_symbols_are_exported_and_bound(sdpa):
+    declared = _declared_symbols()
+    assert "attention" in declared and len(declared) >= 20
+    L = sdpa.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/sdpa_b200.h but not exported"
+    assert sorted(sdpa.ABI) == declared, "host.py ABI table and the header disagree"
+
+
+def test_config_struct_layout(sdpa):
+    assert ctypes.sizeof(sdpa.Config) == 16 * 4
+    cfg = sdpa.Config()
+    sdpa.lib().sdpa_config_init(ctypes.byref(cfg))
+    assert cfg.precision == sdpa.PREC_AUTO and cfg.num_local == 1 and cfg.merge == sdpa.MERGE_NCCL
+
+
+def test_owner_map_matches_reference_formula(sdpa, oracle):
+    for n in (0, 1, 5, 13, 4096, 65536, 1048576):
+        for size in (1, 2, 3, 4, 8):
+            for r in range(size):
+                assert sdpa.owner_count(n, size, r) == oracle.owner_count(n, size, r)
+                assert sdpa.owner_disp(n, size, r) == oracle.owner_disp(n, size, r)
+
+
+def test_no_cpu_fallback(sdpa):
+    """Without a CUDA device the engine refuses to create a context (and says why)."""
+    if sdpa.device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(sdpa.SdpaError, match="no CPU fallback"):
+        sdpa.Context()
+
+
+def test_version_string(sdpa):
+    assert "sm_100a" in sdpa.version()
