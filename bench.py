@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the attention hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W      # the reference's CPU path
+
+Workload (BASELINE.json): the tensor-core configuration c3 -- m=8192 query rows, d_k=d_v=128,
+K/V rows sharded over the GPUs with 65536 rows per GPU (n = 65536*N; N=1 is exactly c3, and
+c4's per-GPU shard).  Weak scaling: per-GPU K/V shard fixed, Q replicated, so whole-job
+FLOPs = 2*m*n*(dk+dv) grow with N.  `--config c2` runs the fp32 configuration instead.
+
+A step is one full pass of the path on fp64 inputs: cast K/V shard, cast Q batches, fused
+QK^T->softmax->.V kernel, split/shard merge (NCCL MAX/SUM/SUM for N>1), fp64 result on rank 0.
+  value : inputs resident in HBM as fp64 (the contract's input type) when the timed region starts
+  e2e   : the same through the C ABI with pinned HOST buffers (H2D of K/V shard + Q, D2H of result)
+Timing: CUDA events around exactly K steps, barrier + synchronize on both sides, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+DK = DV = 128
+CONFIGS = {
+    # name: (m, keys per GPU, precision, description)
+    "c3": (8192, 65536, "bf16", "c3: m=8192 n=65536/GPU dk=dv=128 bf16->fp32 tensor-core path"),
+    "c2": (4096, 4096, "f32", "c2: m=4096 n=4096 dk=dv=128 fp32, no sharding"),
+}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            return d, "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _loop(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run([exe, f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference / CPU baseline
+def cpu_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def physical_cores() -> int:
+    """Ranks for the reference's MPI path: physical cores (its authors ran 16 ranks on 36-core nodes)."""
+    try:
+        pairs = set()
+        phys = core = None
+        for line in Path("/proc/cpuinfo").read_text().splitlines():
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+                pairs.add((phys, core))
+        n = len(pairs)
+        return max(1, min(n if n else cpu_cores(), cpu_cores()))
+    except Exception:
+        return cpu_cores()
+
+
+class ReferenceSample:
+    """A bounded sample of the workload for the CPU arm: `rows` Q rows against the FULL K/V of the
+    configuration, written in the reference's file format with a correct answer block (its harness
+    prints the elapsed time only when its own verify() passes, attention-mpi.c:526-532)."""
+
+    def __init__(self, n: int, target_pairs: float = 2.0 ** 27):
+        from oracle import oracle
+        import numpy as np
+        self.oracle = oracle
+        self.n = n
+        self.rows = int(max(64, min(4096, target_pairs // max(1, n))))
+        Q, K, V = oracle.make_inputs(self.rows, n, DK, DV, seed=4242)
+        ans = oracle.attention_f64_numpy(Q, K, V)
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        self.dir = tempfile.mkdtemp(prefix="sdpa_ref_", dir=base)
+        self.path = os.path.join(self.dir, "sample.bin")
+        oracle.write_data_file(self.path, Q, K, V, ans)
+        self.Q, self.K, self.V, self.ans = Q, K, V, ans
+        self.np = np
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+    def kind_and_cores(self):
+        if self.oracle.ref_available("mpi"):
+            return "reference", physical_cores()
+        return "port", int(self.oracle.lib().oracle_num_threads())
+
+    def run_once(self) -> float:
+        """Seconds for one pass over the sample (the program's own Elapsed time for kind=reference)."""
+        kind, cores = self.kind_and_cores()
+        if kind == "reference":
+            ok, us, out = self.oracle.run_reference(self.path, "mpi", ranks=cores, timeout=1800)
+            if not ok or us is None:
+                raise RuntimeError(f"reference binary did not verify: {out[-400:]}")
+            return us * 1e-6
+        t0 = time.perf_counter()
+        got = self.oracle.sharded_attention_f32(self.Q, self.K, self.V, shards=1)
+        dt = time.perf_counter() - t0
+        if not self.oracle.verify_rule(got, self.ans):
+            raise RuntimeError("oracle port failed its own check")
+        return dt
+
+    def describe(self):
+        return f"{self.rows} Q rows x full K/V (n={self.n}, dk=dv={DK}), program's own timer"
+
+
+def tflops_from_rows_per_s(rows_per_s: float, n: int) -> float:
+    return rows_per_s * 2.0 * n * (DK + DV) / 1e12
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    m, n_per_gpu, prec, desc = CONFIGS[args.config]
+    n = n_per_gpu * args.gpus
+    sample = ReferenceSample(n)
+    try:
+        kind, cores = sample.kind_and_cores()
+        for _ in range(max(0, args.warmup)):
+            sample.run_once()
+        times = [sample.run_once() for _ in range(max(1, args.steps))]
+    finally:
+        sample.close()
+    total = sum(times)
+    rows_per_s = sample.rows * len(times) / total
+    value = tflops_from_rows_per_s(rows_per_s, n)
+    line = {
+        "impl": "reference", "metric": "attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,1), seeded",
+        "q_rows_per_s": rows_per_s,
+        "config": {"workload": desc, "m": m, "n": n, "dk": DK, "dv": DV, "sharding": f"kv-rows/{args.gpus}",
+                   "note": "CPU arm runs a bounded Q-row sample against the full K/V; FLOP rate is size-independent"},
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample.describe(),
+                         "q_rows_per_s": rows_per_s},
+        "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    import sdpa_b200
+    from sdpa_b200 import parallel
+
+    m, n_local, prec, desc = CONFIGS[args.config]
+    if args.m:
+        m = args.m
+    if args.n_per_gpu:
+        n_local = args.n_per_gpu
+    if args.precision:
+        prec = args.precision
+    n = n_local * world
+    flops_step = 2.0 * m * n * (DK + DV)
+
+    # ---- synthetic inputs: Q replicated (same seed), one K/V shard per rank -----------------
+    g = torch.Generator().manual_seed(1234)
+    Qh = torch.randn(m, DK, dtype=torch.float64, generator=g).pin_memory()
+    g = torch.Generator().manual_seed(1000 + rank)
+    Kh = torch.randn(n_local, DK, dtype=torch.float64, generator=g).pin_memory()
+    Vh = torch.randn(n_local, DV, dtype=torch.float64, generator=g).pin_memory()
+    Rh = torch.zeros(m, DV, dtype=torch.float64).pin_memory() if rank == 0 else None
+    Qd, Kd, Vd = Qh.cuda(), Kh.cuda(), Vh.cuda()
+    Rd = torch.zeros(m, DV, dtype=torch.float64, device="cuda") if rank == 0 else None
+
+    if world > 1:
+        ctx = parallel.bootstrap_context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, local_rank=local_rank)
+    else:
+        ctx = sdpa_b200.Context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, first_device=local_rank)
+
+    def step_device():
+        ctx.load_kv_device_ptrs([Kd.data_ptr()], [Vd.data_ptr()], [n_local], DK, DV)
+        ctx.attention_device_ptrs([Qd.data_ptr()], Rd.data_ptr() if Rd is not None else None, m)
+
+    def step_host():
+        ctx.load_kv_host_ptrs([Kh.data_ptr()], [Vh.data_ptr()], [n_local], DK, DV)
+        ctx.attention_host_ptr(Qh.data_ptr(), Rh.data_ptr() if Rh is not None else None, m)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, collect=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+            if collect is not None:
+                collect(ctx.last_timings())
+        e1.record()
+        barrier()
+        return parallel.max_over_ranks(e0.elapsed_time(e1))  # ms, max over ranks
+
+    W, K = max(3, args.warmup), max(1, args.steps)
+    for _ in range(W):
+        step_device()
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------
+    fused = {"ms": 0.0, "launches": 0.0, "cast_ms": 0.0, "merge_ms": 0.0}
+
+    def collect(t):
+        fused["ms"] += t["fused_ms"]
+        fused["launches"] += t["fused_launches"]
+        fused["cast_ms"] += t["cast_ms"]
+        fused["merge_ms"] += t["merge_ms"]
+
+    launches0 = sdpa_b200.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms_dev = timed(step_device, K, collect)
+        # keep the sampler alive for at least a few samples on very short runs
+        t_end = time.time() + max(0.0, 0.35 - ms_dev / 1e3)
+        while time.time() < t_end:
+            step_device()
+    launches = sdpa_b200.launch_count() - launches0
+    clocks = clk.summary()
+    kernel_name = ctx.last_kernel()
+
+    # ---- e2e: pinned host buffers through the C ABI -------------------------------------------
+    for _ in range(2):
+        step_host()
+    ms_host = timed(step_host, K)
+
+    # ---- correctness guard on rank 0: device and host paths agree, result is finite -----------
+    ok = True
+    if rank == 0:
+        a, b = Rd.cpu().numpy(), Rh.numpy()
+        ok = bool(np.isfinite(a).all() and np.abs(a - b).max() < 1e-6)
+
+    value = flops_step * K / (ms_dev * 1e-3) / 1e12
+    e2e_value = flops_step * K / (ms_host * 1e-3) / 1e12
+    h2d = world * (n_local * (DK + DV) + m * DK) * 8
+    d2h = m * DV * 8
+
+    # ---- roofline of the dominant kernel (the fused attention kernel), this rank ---------------
+    peaks, peaks_src = load_peaks()
+    flops_per_launch = 2.0 * m * n_local * (DK + DV) * K / max(1.0, fused["launches"])
+    avg_ms = fused["ms"] / max(1.0, fused["launches"])
+    achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+    if kernel_name == "bf16_umma":
+        peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+        bound_note = "tcgen05 bf16 dense; peak = cuBLAS bf16 burst"
+    else:
+        peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+        bound_note = "fp32 CUDA-core kernel reported against the bf16 tensor peak (its own FFMA ceiling is ~72 TFLOP/s)"
+    traffic = None
+    prof = ROOT / "profiles" / "fused_kernel_traffic.json"
+    if prof.exists():
+        try:
+            traffic = json.loads(prof.read_text()).get(kernel_name, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": traffic, "kernel": kernel_name, "avg_launch_ms": avg_ms, "launches": fused["launches"],
+                "flops_per_launch": flops_per_launch, "peak_source": peaks_src, "note": bound_note,
+                "frac_of_sustained": achieved / float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if kernel_name == "bf16_umma" else "f32", "data": "synthetic N(0,1), seeded",
+            "q_rows_per_s": m * K / (ms_dev * 1e-3),
+            "config": {"workload": desc, "m": m, "n": n, "n_per_gpu": n_local, "dk": DK, "dv": DV,
+                       "parallelism": f"kv-shard x{world} (owner_count/owner_disp), Q replicated",
+                       "merge": "none" if world == 1 else "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)",
+                       "l2": "inputs_larger_than_l2 (fp64 Q+K+V per GPU = %d MiB)" % ((n_local * (DK + DV) + m * DK) * 8 >> 20),
+                       "kernel": kernel_name},
+            "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_host / K, "q_rows_per_s": m * K / (ms_host * 1e-3)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "stage_ms_per_step": {"cast_q": fused["cast_ms"] / K, "fused": fused["ms"] / K, "merge": fused["merge_ms"] / K},
+            "self_check": "ok" if ok else "MISMATCH between device-resident and host paths",
+        }
+    # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sample = ReferenceSample(n)
+            try:
+                kind, cores = sample.kind_and_cores()
+                dt = sample.run_once()
+            finally:
+                sample.close()
+            rps = sample.rows / dt
+            line["cpu_baseline"] = {"value": tflops_from_rows_per_s(rps, n), "unit": "TFLOP/s", "cores": cores, "kind": kind,
+                                    "sample": sample.describe(), "q_rows_per_s": rps, "seconds": dt}
+        except Exception as exc:  # the baseline must not sink the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "TFLOP/s", "cores": 0, "kind": "unavailable", "sample": str(exc)[:200]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="c3")
+    ap.add_argument("--precision", choices=["auto", "f32", "bf16"], default=None)
+    ap.add_argument("--m", type=int, default=0)
+    ap.add_argument("--n-per-gpu", type=int, default=0)
+    ap.add_argument("--q-batch", type=int, default=0)
+    ap.add_argument("--kv-splits", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -164,7 +164,9 @@ sdpa_status sdpa_cvt_d2bf16(uint16_t* dst_dev, const double* src_dev, size_t cou
  * ------------------------------------------------------------------------- */
 const char* sdpa_last_error(void);
 const char* sdpa_version(void);
-int sdpa_device_count(void); /* CUDA devices visible; 0 when there is none (never falls back to CPU) */
+int sdpa_device_count(void);
+/* Kernels launched by this library in this process so far (all GPUs). */
+unsigned long long sdpa_launch_count(void); /* CUDA devices visible; 0 when there is none (never falls back to CPU) */
 
 #ifdef __cplusplus
 }

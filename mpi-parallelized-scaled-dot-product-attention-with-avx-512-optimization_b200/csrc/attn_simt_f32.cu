@@ -279,6 +279,7 @@ sdpa_status launch_d(const float* Q, const float* K, const float* V, int rows, i
     attn_f32_kernel<D><<<grid, NTHREADS, Smem<D>::bytes, stream>>>(
         Q, K, V, rows, n, dk, dv, scale_log2, tiles_per_split, part.o, part.tmax, part.lsum,
         part.rows_capacity, out64, vec_flags);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }

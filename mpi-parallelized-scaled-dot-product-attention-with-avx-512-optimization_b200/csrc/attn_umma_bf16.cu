@@ -1,16 +1,681 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// attn_umma_bf16.cu -- fused QK^T -> online softmax -> .V on the 5th-generation tensor cores
+// (tcgen05.mma, accumulators in TMEM, operands staged by TMA), bf16 operands / fp32 accumulate.
+//
+// The B200 counterpart of online_softmax_attention (attention-mpi.c:168-189): where the
+// reference does one AVX-512 dot (dot_avx512, :103-121) and one axpy (axpy_avx512, :123-140)
+// per (query, key) pair, this kernel does two 128x128x128 tensor-core GEMMs per
+// (128-query tile, 128-key tile) pair; the running max / running sum of mpi.c:177-180 live in
+// registers, one query row per thread.
+//
+// CTA = 256 query rows (two 128-row tiles A and B, ping-ponged) x one contiguous range of
+// 128-key tiles (split-KV over blockIdx.y).  12 warps:
+//   warp 0      TMA producer   : Q tiles once, then K/V tiles through 2-stage mbarrier rings
+//                                (cp.async.bulk.tensor, 128-byte swizzle)
+//   warp 1      MMA issuer     : one thread issues   S_t = Q_t K^T   (SS, both K-major)
+//                                and                 O_t += P_t V    (TS: P from TMEM, V MN-major)
+//                                order  S_A(0) S_B(0) | PV_A(j) S_A(j+1) PV_B(j) S_B(j+1) | ...
+//                                so the softmax of one tile overlaps the MMAs of the other
+//   warps 2-3   idle (keep the softmax warpgroups aligned to the TMEM lane quadrants)
+//   warps 4-7   softmax of tile A, warps 8-11 softmax of tile B: tcgen05.ld the S row,
+//               row max (no shuffles needed: a thread owns a whole row), lazy rescale of O
+//               (only when the max grew by > 2^8, decided per warp with a vote), exp2 with the
+//               1/sqrt(dk)*log2(e) scale folded into one FFMA, bf16 P written back into the
+//               TMEM columns of S (tcgen05.st), finally the epilogue (O, tmax, lsum).
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P_t aliases the
+// first 64 columns of S_t (the tensor pipe executes MMAs in issue order, so S_t(j+1) cannot
+// overwrite P_t(j) before PV_t(j) has consumed it).
+// Shared memory: Q_A, Q_B, 2 x K, 2 x V tiles of 32 KiB = 192 KiB.
+// Roofline: tensor pipe, 4*128^3 flops per tile pair; algorithmic HBM bytes are the bf16
+// Q/K/V and the fp32 partial outputs.
 #include "common.cuh"
+
+#include <cuda.h>
+#include <math_constants.h>
+
 namespace sdpa {
-struct UmmaPlan { int unused; };
-sdpa_status umma_plan_create(UmmaPlan** plan) { *plan = new UmmaPlan(); return SDPA_OK; }
-void umma_plan_destroy(UmmaPlan* plan) { delete plan; }
-sdpa_status umma_plan_bind_kv(UmmaPlan*, const __nv_bfloat16*, const __nv_bfloat16*, int, int, int) { return SDPA_OK; }
-sdpa_status umma_plan_bind_q(UmmaPlan*, int, const __nv_bfloat16*, int, int) { return SDPA_OK; }
-sdpa_status launch_attn_umma(UmmaPlan*, int, int, int, Partials, double*, int, cudaStream_t)
+
+namespace {
+
+constexpr int TILE = 128;            // rows per Q tile, keys per K/V tile
+constexpr int HEAD = 128;            // dk == dv
+constexpr int BLOCK_ROWS = 2 * TILE; // Q rows per CTA
+constexpr int NTHREADS = 384;
+constexpr int STAGES = 2;
+constexpr uint32_t TILE_BYTES = TILE * HEAD * 2;      // 32 KiB
+constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;       // one 64-column TMA box
+constexpr float kLazyThreshold = 8.0f;                // rescale O only if the max grew by > 2^8
+
+constexpr uint32_t TMEM_S = 0;    // + 128 * tile
+constexpr uint32_t TMEM_O = 256;  // + 128 * tile
+
+struct __align__(1024) SharedStorage {
+    uint8_t q[2][TILE_BYTES];
+    uint8_t k[STAGES][TILE_BYTES];
+    uint8_t v[STAGES][TILE_BYTES];
+    uint64_t q_full[2];
+    uint64_t k_full[STAGES], k_empty[STAGES];
+    uint64_t v_full[STAGES], v_empty[STAGES];
+    uint64_t s_full[2], p_ready[2], o_done[2];
+    uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    set_error("bf16 tcgen05 kernel not built yet");
-    return SDPA_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-bool attn_umma_supported(int, int) { return false; }
-int attn_umma_pick_splits(int, int, int) { return 1; }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("sdpa_b200: mbarrier timeout tag=%d block=(%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
+                   threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+#define SDPA_TMEM_LD32(taddr, r)                                                                             \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),            \
+          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),          \
+          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),          \
+          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                               \
+        : "r"(taddr)                                                                                         \
+        : "memory")
+
+#define SDPA_TMEM_ST32(taddr, r)                                                                             \
+    asm volatile(                                                                                            \
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                      \
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                           \
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"                   \
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),       \
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),     \
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])      \
+        : "memory")
+
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float fast_exp2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---------------------------------------------------------------- UMMA descriptors
+// Shared-memory matrix descriptor (sm_100): start address [0,14) (>>4), leading byte offset
+// [16,30) (>>4), stride byte offset [32,46) (>>4), version = 1 at [46,48), layout type at
+// [61,64) (2 = 128-byte swizzle).
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// K-major operand tile [128 rows][128 cols] bf16 stored as two [128][64] 128B-swizzled boxes:
+// 8-row groups are 1024 B apart (SBO); the k-th 16-column slice starts (k%4)*32 B into box k/4.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k16)
+{
+    return make_desc(tile_addr + (uint32_t)(k16 >> 2) * HALF_BYTES + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
+}
+// MN-major operand tile (V: [128 keys][128 dv], dv contiguous) stored as two [128 keys][64 dv]
+// swizzled boxes: 64-column groups are HALF_BYTES apart (LBO), 8-key groups 1024 B apart (SBO);
+// the k-th 16-key slice starts k*16 rows = k*2048 B into the tile.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int k16)
+{
+    return make_desc(tile_addr + (uint32_t)k16 * 2048u, HALF_BYTES, 1024u);
+}
+// Instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1),
+// b_major at bit 16, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int b_mn_major)
+{
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(m >> 4) << 24);
+}
+
+struct KernelParams {
+    int rows;            // valid Q rows
+    int n;               // keys in the shard
+    int tiles_total;     // ceil(n / 128)
+    int splits;
+    float scale_log2;    // 1/sqrt(dk) * log2(e)
+    float* part_o;
+    float* part_tmax;
+    float* part_lsum;
+    int rows_capacity;
+    double* out64;       // non-null (splits == 1): normalised fp64 output
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                 const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
+{
+    extern __shared__ uint8_t smem_raw[];
+    SharedStorage& sm = *reinterpret_cast<SharedStorage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row_block = blockIdx.x;
+    const int split = blockIdx.y;
+
+    // balanced contiguous partition of the key tiles over the splits (same rule as owner_count/owner_disp)
+    const int tq = prm.tiles_total / prm.splits, tr = prm.tiles_total % prm.splits;
+    const int tile_begin = split * tq + min(split, tr);
+    const int num_tiles = tq + (split < tr ? 1 : 0);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_q);
+        prefetch_tensormap(&map_k);
+        prefetch_tensormap(&map_v);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.q_full[i], 1);
+            mbar_init(&sm.s_full[i], 1);
+            mbar_init(&sm.p_ready[i], 128);
+            mbar_init(&sm.o_done[i], 1);
+        }
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&sm.k_full[i], 1);
+            mbar_init(&sm.k_empty[i], 1);
+            mbar_init(&sm.v_full[i], 1);
+            mbar_init(&sm.v_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    // Register re-allocation between the warpgroups (each branch is dominated by its own
+    // setmaxnreg, so ptxas budgets it separately): the producer / MMA warpgroup needs few
+    // registers, each softmax thread holds a whole 128-column S row (128*96 + 256*200 <= 384*168).
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        if (num_tiles > 0) {
+        if (warp == 0) {
+            // ================================ TMA producer ================================
+            if (lane == 0) {
+                const int qrow = row_block * BLOCK_ROWS;
+                for (int j = 0; j < num_tiles; ++j) {
+                    const int stage = j % STAGES;
+                    const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+                    const int key0 = (tile_begin + j) * TILE;
+                    if (j == 0) {
+                        mbar_arrive_expect_tx(&sm.q_full[0], TILE_BYTES);
+                        tma_load_2d(sm.q[0], &map_q, &sm.q_full[0], 0, qrow);
+                        tma_load_2d(sm.q[0] + HALF_BYTES, &map_q, &sm.q_full[0], 64, qrow);
+                    }
+                    mbar_wait(&sm.k_empty[stage], ph ^ 1u, 100 + stage);
+                    mbar_arrive_expect_tx(&sm.k_full[stage], TILE_BYTES);
+                    tma_load_2d(sm.k[stage], &map_k, &sm.k_full[stage], 0, key0);
+                    tma_load_2d(sm.k[stage] + HALF_BYTES, &map_k, &sm.k_full[stage], 64, key0);
+                    if (j == 0) {
+                        mbar_arrive_expect_tx(&sm.q_full[1], TILE_BYTES);
+                        tma_load_2d(sm.q[1], &map_q, &sm.q_full[1], 0, qrow + TILE);
+                        tma_load_2d(sm.q[1] + HALF_BYTES, &map_q, &sm.q_full[1], 64, qrow + TILE);
+                    }
+                    mbar_wait(&sm.v_empty[stage], ph ^ 1u, 110 + stage);
+                    mbar_arrive_expect_tx(&sm.v_full[stage], TILE_BYTES);
+                    tma_load_2d(sm.v[stage], &map_v, &sm.v_full[stage], 0, key0);
+                    tma_load_2d(sm.v[stage] + HALF_BYTES, &map_v, &sm.v_full[stage], 64, key0);
+                }
+            }
+        } else if (warp == 1) {
+            // ================================ MMA issuer ==================================
+            if (lane == 0) {
+                constexpr uint32_t idesc_qk = make_idesc(TILE, TILE, 0);
+                constexpr uint32_t idesc_pv = make_idesc(TILE, HEAD, 1);
+                const uint32_t q_addr[2] = {smem_u32(sm.q[0]), smem_u32(sm.q[1])};
+
+                auto issue_s = [&](int t, int stage) {
+                    const uint32_t k_addr = smem_u32(sm.k[stage]);
+#pragma unroll
+                    for (int kk = 0; kk < HEAD / 16; ++kk)
+                        umma_ss(tmem + TMEM_S + 128u * t, desc_kmajor(q_addr[t], kk), desc_kmajor(k_addr, kk), idesc_qk,
+                                kk > 0 ? 1u : 0u);
+                    umma_commit(&sm.s_full[t]);
+                };
+                auto issue_pv = [&](int t, int stage, int j) {
+                    const uint32_t v_addr = smem_u32(sm.v[stage]);
+#pragma unroll
+                    for (int kk = 0; kk < TILE / 16; ++kk)
+                        umma_ts(tmem + TMEM_O + 128u * t, tmem + TMEM_S + 128u * t + 8u * kk, desc_mnmajor(v_addr, kk),
+                                idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                };
+
+                // prologue: S_A(0), S_B(0)
+                mbar_wait(&sm.k_full[0], 0, 200);
+                mbar_wait(&sm.q_full[0], 0, 201);
+                tcgen05_fence_after();
+                issue_s(0, 0);
+                mbar_wait(&sm.q_full[1], 0, 202);
+                tcgen05_fence_after();
+                issue_s(1, 0);
+                umma_commit(&sm.k_empty[0]);   // K(0) is free once S_A(0), S_B(0) have completed
+
+                for (int j = 0; j < num_tiles; ++j) {
+                    const int stage = j % STAGES;
+                    const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+                    const int nstage = (j + 1) % STAGES;
+                    const uint32_t nph = (uint32_t)((j + 1) / STAGES) & 1u;
+                    const bool more = (j + 1) < num_tiles;
+
+                    mbar_wait(&sm.v_full[stage], ph, 210);
+                    // ---- tile A ----
+                    mbar_wait(&sm.p_ready[0], (uint32_t)j & 1u, 211);
+                    tcgen05_fence_after();
+                    issue_pv(0, stage, j);
+                    if (more) {
+                        mbar_wait(&sm.k_full[nstage], nph, 212);
+                        tcgen05_fence_after();
+                        issue_s(0, nstage);
+                    } else {
+                        umma_commit(&sm.o_done[0]);
+                    }
+                    // ---- tile B ----
+                    mbar_wait(&sm.p_ready[1], (uint32_t)j & 1u, 213);
+                    tcgen05_fence_after();
+                    issue_pv(1, stage, j);
+                    umma_commit(&sm.v_empty[stage]);
+                    if (more) {
+                        issue_s(1, nstage);
+                        umma_commit(&sm.k_empty[nstage]);
+                    } else {
+                        umma_commit(&sm.o_done[1]);
+                    }
+                }
+            }
+        }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        if (num_tiles > 0) {
+            // ================================ softmax + epilogue ==========================
+            const int t = (warp >= 8) ? 1 : 0;            // which Q tile
+            const int quad = warp & 3;                     // TMEM lane quadrant of this warp
+            const int row_in_tile = quad * 32 + lane;
+            const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+            const uint32_t s_addr = tmem + lane_base + TMEM_S + 128u * t;
+            const uint32_t o_addr = tmem + lane_base + TMEM_O + 128u * t;
+            const float scale = prm.scale_log2;
+
+            float m_ref = -CUDART_INF_F;   // raw-score reference max used by every exponent so far
+            float lsum = 0.f;
+
+            for (int j = 0; j < num_tiles; ++j) {
+                mbar_wait(&sm.s_full[t], (uint32_t)j & 1u, 300 + t);
+                tcgen05_fence_after();
+
+                uint32_t sr[128];
+                SDPA_TMEM_LD32(s_addr + 0, (sr + 0));
+                SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
+                SDPA_TMEM_LD32(s_addr + 64, (sr + 64));
+                SDPA_TMEM_LD32(s_addr + 96, (sr + 96));
+                tmem_wait_ld();
+
+                const int keys_left = prm.n - (tile_begin + j) * TILE;   // >= 1
+                if (keys_left < TILE) {
+#pragma unroll
+                    for (int c = 0; c < 128; ++c)
+                        if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
+                }
+
+                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+                for (int c = 0; c < 128; c += 4) {
+                    mx0 = fmaxf(mx0, __uint_as_float(sr[c + 0]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
+                    mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
+                    mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+                }
+                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+                // lazy rescale: keep the old reference unless the max grew by more than 2^kLazyThreshold
+                bool need = false;
+                float corr = 1.f;
+                if (j == 0) {
+                    m_ref = tile_max;
+                } else if ((tile_max - m_ref) * scale > kLazyThreshold) {
+                    need = true;
+                    corr = fast_exp2((m_ref - tile_max) * scale);
+                    m_ref = tile_max;
+                }
+                if (__any_sync(0xffffffffu, need)) {
+                    // O_t is stable here: PV_t(j-1) completed before s_full(j) fired, and PV_t(j)
+                    // is not issued until this warpgroup signals p_ready(j).
+                    lsum *= corr;
+#pragma unroll
+                    for (int c0 = 0; c0 < HEAD; c0 += 32) {
+                        uint32_t orr[32];
+                        SDPA_TMEM_LD32(o_addr + c0, orr);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) orr[c] = __float_as_uint(__uint_as_float(orr[c]) * corr);
+                        SDPA_TMEM_ST32(o_addr + c0, orr);
+                    }
+                }
+
+                const float neg_ref = -m_ref * scale;
+                float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+                // two halves of 64 keys: the bf16 P of a half (32 packed columns) is stored to TMEM
+                // as soon as it is complete, which frees its registers for the second half
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t pr[32];
+#pragma unroll
+                    for (int c = 0; c < 64; c += 4) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 0]), scale, neg_ref));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 1]), scale, neg_ref));
+                        const float p2 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 2]), scale, neg_ref));
+                        const float p3 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 3]), scale, neg_ref));
+                        sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
+                        pr[c / 2 + 0] = pack_bf16x2(p0, p1);
+                        pr[c / 2 + 1] = pack_bf16x2(p2, p3);
+                    }
+                    SDPA_TMEM_ST32(s_addr + 32 * h, pr);
+                }
+                lsum += (sum0 + sum1) + (sum2 + sum3);
+
+                tmem_wait_st();
+                tcgen05_fence_before();
+                mbar_arrive(&sm.p_ready[t]);
+            }
+
+            // ---------------- epilogue: O_t, reference max, row sum ----------------
+            mbar_wait(&sm.o_done[t], 0, 320 + t);
+            tcgen05_fence_after();
+            const int grow = row_block * BLOCK_ROWS + t * TILE + row_in_tile;
+            const bool valid = grow < prm.rows;
+            const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
+#pragma unroll
+            for (int c0 = 0; c0 < HEAD; c0 += 32) {
+                uint32_t orr[32];
+                SDPA_TMEM_LD32(o_addr + c0, orr);
+                tmem_wait_ld();
+                if (valid) {
+                    if (prm.out64 != nullptr) {
+                        double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + c0);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2)
+                            dst[c / 2] = make_double2((double)(__uint_as_float(orr[c]) * inv),
+                                                      (double)(__uint_as_float(orr[c + 1]) * inv));
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + c0);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            dst[c / 4] = make_float4(__uint_as_float(orr[c]), __uint_as_float(orr[c + 1]),
+                                                     __uint_as_float(orr[c + 2]), __uint_as_float(orr[c + 3]));
+                    }
+                }
+            }
+            if (valid && prm.out64 == nullptr) {
+                prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = m_ref * scale;
+                prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = lsum;
+            }
+        } else {
+        // empty key range (n == 0 or more splits than tiles): the neutral state (0, -inf, 0), mpi.c:172,188
+        const int t = (warp >= 8) ? 1 : 0;
+        const int grow = row_block * BLOCK_ROWS + t * TILE + (warp & 3) * 32 + lane;
+        if (grow < prm.rows) {
+            if (prm.out64 != nullptr) {
+                for (int c = 0; c < HEAD; ++c) prm.out64[(size_t)grow * HEAD + c] = 0.0;
+            } else {
+                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD;
+                for (int c = 0; c < HEAD; ++c) dst[c] = 0.f;
+                prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
+                prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
+            }
+        }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows][128] tensor, box = 64 columns x 128 rows, 128-byte swizzle, OOB rows -> 0.
+sdpa_status encode_map(CUtensorMap* map, const void* base, int rows)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return SDPA_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)HEAD, (cuuint64_t)(rows > 0 ? rows : 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)HEAD * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (base=%p rows=%d)", (int)r, base, rows);
+        return SDPA_ERR_CUDA;
+    }
+    return SDPA_OK;
+}
+
+}  // namespace
+
+struct UmmaPlan {
+    CUtensorMap map_k, map_v, map_q[2];
+    int n = 0;
+    bool kv_bound = false, q_bound[2] = {false, false};
+    const void* q_base[2] = {nullptr, nullptr};
+    int q_rows[2] = {0, 0};
+    bool attr_set[64] = {};
+};
+
+sdpa_status umma_plan_create(UmmaPlan** plan)
+{
+    *plan = new UmmaPlan();
+    return SDPA_OK;
+}
+void umma_plan_destroy(UmmaPlan* plan) { delete plan; }
+
+bool attn_umma_supported(int dk, int dv) { return dk == HEAD && dv == HEAD; }
+
+sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv_bfloat16* V, int n, int dk, int dv)
+{
+    if (!attn_umma_supported(dk, dv)) {
+        set_error("bf16 tensor-core kernel supports dk == dv == 128 (got dk=%d dv=%d)", dk, dv);
+        return SDPA_ERR_UNSUPPORTED;
+    }
+    SDPA_TRY(encode_map(&plan->map_k, K, n));
+    SDPA_TRY(encode_map(&plan->map_v, V, n));
+    plan->n = n;
+    plan->kv_bound = true;
+    return SDPA_OK;
+}
+
+sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, int rows_capacity, int dk)
+{
+    if (slot < 0 || slot > 1 || dk != HEAD) {
+        set_error("umma_plan_bind_q: bad slot/dk");
+        return SDPA_ERR_INVALID;
+    }
+    if (plan->q_bound[slot] && plan->q_base[slot] == Q && plan->q_rows[slot] == rows_capacity) return SDPA_OK;
+    SDPA_TRY(encode_map(&plan->map_q[slot], Q, rows_capacity));
+    plan->q_bound[slot] = true;
+    plan->q_base[slot] = Q;
+    plan->q_rows[slot] = rows_capacity;
+    return SDPA_OK;
+}
+
+int attn_umma_pick_splits(int rows, int n, int sm_count)
+{
+    const int row_blocks = ceil_div(rows, BLOCK_ROWS);
+    const int tiles = ceil_div(n, TILE);
+    if (row_blocks <= 0 || tiles <= 1) return 1;
+    // choose the split count (<= 64, >= 4 key tiles each) with the best wave efficiency of the
+    // grid row_blocks x splits over sm_count CTAs-at-a-time; prefer fewer splits on ties.
+    int best = 1;
+    double best_eff = -1.0;
+    const int max_splits = std::min(64, std::max(1, tiles / 4));
+    for (int s = 1; s <= max_splits; ++s) {
+        const int ctas = row_blocks * s;
+        const int waves = ceil_div(ctas, sm_count);
+        const int tiles_per = ceil_div(tiles, s);  // the slowest CTA of a wave sets its length
+        const double eff = (double)row_blocks * tiles / ((double)waves * sm_count * tiles_per);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = s;
+        }
+    }
+    return best;
+}
+
+sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part, double* out64,
+                             int sm_count, cudaStream_t stream)
+{
+    (void)sm_count;
+    if (!plan || !plan->kv_bound || q_slot < 0 || q_slot > 1 || !plan->q_bound[q_slot]) {
+        set_error("launch_attn_umma: plan is not bound");
+        return SDPA_ERR_INVALID;
+    }
+    if (rows <= 0) return SDPA_OK;
+    if (splits < 1) splits = 1;
+    if (out64 != nullptr && splits != 1) {
+        set_error("direct fp64 output requires splits == 1");
+        return SDPA_ERR_INVALID;
+    }
+    const size_t smem_bytes = sizeof(SharedStorage) + 1024;
+    int dev = 0;
+    SDPA_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 64 && !plan->attr_set[dev]) {
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        plan->attr_set[dev] = true;
+    }
+    KernelParams prm;
+    prm.rows = rows;
+    prm.n = plan->n;
+    prm.tiles_total = ceil_div(plan->n, TILE);
+    prm.splits = splits;
+    prm.scale_log2 = (1.0f / sqrtf((float)HEAD)) * 1.4426950408889634f;
+    prm.part_o = part.o;
+    prm.part_tmax = part.tmax;
+    prm.part_lsum = part.lsum;
+    prm.rows_capacity = part.rows_capacity;
+    prm.out64 = out64;
+    dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);
+    attn_umma_kernel<<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
 }  // namespace sdpa

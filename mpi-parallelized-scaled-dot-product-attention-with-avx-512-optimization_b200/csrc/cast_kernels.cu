@@ -150,10 +150,13 @@ sdpa_status launch_cvt_d2f(float* dst, const double* src, size_t count, cudaStre
         const size_t units = count / 2;
         cvt_d2f_vec_kernel<<<cast_grid(units / kUnroll), kCastThreads, 0, stream>>>(
             reinterpret_cast<float2*>(dst), reinterpret_cast<const double2*>(src), units);
+        count_launch();
         done = units * 2;
     }
-    if (done < count)
+    if (done < count) {
         cvt_d2f_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst, src, done, count);
+        count_launch();
+    }
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -166,10 +169,13 @@ sdpa_status launch_cvt_f2d(double* dst, const float* src, size_t count, cudaStre
         const size_t units = count / 4;
         cvt_f2d_vec_kernel<<<cast_grid(units / kUnroll), kCastThreads, 0, stream>>>(
             reinterpret_cast<double2*>(dst), reinterpret_cast<const float4*>(src), units);
+        count_launch();
         done = units * 4;
     }
-    if (done < count)
+    if (done < count) {
         cvt_f2d_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst, src, done, count);
+        count_launch();
+    }
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -182,10 +188,13 @@ sdpa_status launch_cvt_d2bf16(__nv_bfloat16* dst, const double* src, size_t coun
         const size_t units = count / 2;
         cvt_d2bf16_vec_kernel<<<cast_grid(units / kUnroll), kCastThreads, 0, stream>>>(
             reinterpret_cast<uint32_t*>(dst), reinterpret_cast<const double2*>(src), units);
+        count_launch();
         done = units * 2;
     }
-    if (done < count)
+    if (done < count) {
         cvt_d2bf16_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst, src, done, count);
+        count_launch();
+    }
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }

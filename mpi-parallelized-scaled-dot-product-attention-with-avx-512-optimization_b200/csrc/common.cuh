@@ -34,6 +34,10 @@ const char* get_error();
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// process-wide count of kernels this library has launched (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
+unsigned long long launch_count();
+
 // ---- partial softmax state -------------------------------------------------
 // One fused-kernel launch covers `rows` query rows against `splits` contiguous
 // key ranges of the resident shard and leaves, per (split,row):

@@ -117,6 +117,7 @@ sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, 
     else
         merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
             st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, natural_log_max ? kLn2 : 1.f);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -139,6 +140,7 @@ sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* co
     const int blocks = ceil_div(rows, kWarpsPerBlock);
     merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr,
                                                                          nullptr, nullptr, 1.f);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -149,6 +151,7 @@ sdpa_status launch_rescale_to_gmax(float* contrib, float* lsum, const float* tma
     if (rows <= 0) return SDPA_OK;
     rescale_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(contrib, lsum, tmax,
                                                                                        gmax, rows, dv);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -157,6 +160,7 @@ sdpa_status launch_normalize(float* contrib, const float* gsum, int rows, int dv
 {
     if (rows <= 0) return SDPA_OK;
     normalize_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(contrib, gsum, rows, dv);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }

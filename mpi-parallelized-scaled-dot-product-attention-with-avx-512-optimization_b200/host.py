@@ -84,6 +84,7 @@ ABI = {
     "sdpa_last_error": (ctypes.c_char_p, []),
     "sdpa_version": (ctypes.c_char_p, []),
     "sdpa_device_count": (ctypes.c_int, []),
+    "sdpa_launch_count": (ctypes.c_ulonglong, []),
 }
 
 _lib = None
@@ -114,6 +115,10 @@ def _check(status: int, what: str) -> None:
 
 def device_count() -> int:
     return int(lib().sdpa_device_count())
+
+
+def launch_count() -> int:
+    return int(lib().sdpa_launch_count())
 
 
 def version() -> str:

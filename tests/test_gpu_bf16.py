@@ -1,0 +1,91 @@
+"""GPU parity of the bf16 tcgen05 kernel (the tensor-core path of BASELINE c3-c5).
+Stated tolerance: max abs error <= 1e-2 against the fp64 definition on N(0,1) inputs, and
+<= 2e-3 against fp64 math on the bf16-rounded operands (isolates the kernel's own fp32
+accumulation / bf16 P rounding from the input rounding).  Always within the reference's
+0.02 acceptance rule (attention-mpi.c:476)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BF16_ATOL = 1e-2
+BF16_KERNEL_ATOL = 2e-3
+
+
+def _run(sdpa, oracle, m, n, seed, **cfg):
+    Q, K, V = oracle.make_inputs(m, n, 128, 128, seed=seed)
+    with sdpa.Context(precision="bf16", **cfg) as ctx:
+        ctx.load_kv_host_full(K, V)
+        got = ctx.attention_host(Q)
+        assert ctx.last_kernel() == "bf16_umma"
+    return Q, K, V, got
+
+
+@pytest.mark.parametrize("m,n", [(128, 128), (256, 128), (128, 384), (100, 200), (1, 130), (300, 1000), (777, 2049)])
+@pytest.mark.parametrize("splits", [0, 1, 3])
+def test_bf16_vs_oracle(sdpa, oracle, m, n, splits):
+    Q, K, V, got = _run(sdpa, oracle, m, n, seed=m + 3 * n, kv_splits=splits)
+    ref = oracle.attention_f64_numpy(Q, K, V)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=BF16_ATOL)
+    Qb, Kb, Vb = (oracle.bf16_round(a).astype(np.float64) for a in (Q, K, V))
+    np.testing.assert_allclose(got, oracle.attention_f64_numpy(Qb, Kb, Vb), rtol=0, atol=BF16_KERNEL_ATOL)
+    assert oracle.verify_rule(got, ref)
+
+
+def test_bf16_golden_d128(sdpa, oracle, golden):
+    meta, data = golden
+    mt = meta["d128"]
+    Q, K, V = oracle.make_inputs(mt["m"], mt["n"], mt["dk"], mt["dv"], mt["seed"], mt["gain"])
+    with sdpa.Context(precision="bf16") as ctx:
+        ctx.load_kv_host_full(K, V)
+        got = ctx.attention_host(Q)
+    np.testing.assert_allclose(got, data["d128/serial"], rtol=0, atol=BF16_ATOL)
+    assert oracle.verify_rule(got, data["d128/mpi"])
+
+
+def test_bf16_ping_pong_batches_and_lazy_rescale(sdpa, oracle):
+    """Several Q batches (mpi.c:268-330) and a key order that forces the running max to grow
+    late (keys sorted by increasing norm), which exercises the lazy O rescale."""
+    Q, K, V = oracle.make_inputs(1000, 3000, 128, 128, seed=5)
+    order = np.argsort(np.linalg.norm(K, axis=1))
+    K, V = K[order] * np.linspace(0.2, 3.0, 3000)[:, None], V[order]
+    with sdpa.Context(precision="bf16", q_batch=384) as ctx:
+        ctx.load_kv_host_full(K, V)
+        got = ctx.attention_host(Q)
+        assert ctx.last_timings()["fused_launches"] == 3
+    Qb, Kb, Vb = (oracle.bf16_round(a).astype(np.float64) for a in (Q, K, V))
+    np.testing.assert_allclose(got, oracle.attention_f64_numpy(Qb, Kb, Vb), rtol=0, atol=5e-3)
+
+
+def test_bf16_auto_precision_selects_tensor_cores(sdpa, oracle):
+    Q, K, V = oracle.make_inputs(256, 512, 128, 128, seed=2)
+    with sdpa.Context(precision="auto") as ctx:
+        ctx.load_kv_host_full(K, V)
+        ctx.attention_host(Q)
+        assert ctx.last_kernel() == "bf16_umma"
+    Q, K, V = oracle.make_inputs(64, 128, 80, 80, seed=2)
+    with sdpa.Context(precision="auto") as ctx:
+        ctx.load_kv_host_full(K, V)
+        ctx.attention_host(Q)
+        assert ctx.last_kernel() == "f32_simt"
+    with pytest.raises(sdpa.SdpaError):
+        with sdpa.Context(precision="bf16") as ctx:
+            ctx.load_kv_host_full(K, V)   # dk = 80: no tensor-core kernel, and no silent fallback
+
+
+def test_bf16_full_size_c3_row_subset(sdpa, oracle):
+    """BASELINE c3 (m=8192, n=65536, d=128) at full size: seeded row subset vs the fp64 oracle,
+    plus key-permutation invariance of the whole output."""
+    m, n = 8192, 65536
+    Q, K, V = oracle.make_inputs(m, n, 128, 128, seed=2)
+    with sdpa.Context(precision="bf16") as ctx:
+        ctx.load_kv_host_full(K, V)
+        got = ctx.attention_host(Q)
+        rows = np.random.default_rng(0).choice(m, 48, replace=False)
+        ref = oracle.attention_f64_numpy(Q[rows], K, V)
+        np.testing.assert_allclose(got[rows], ref, rtol=0, atol=BF16_ATOL)
+        assert np.isfinite(got).all()
+        perm = np.random.default_rng(1).permutation(n)
+        ctx.load_kv_host_full(K[perm], V[perm])
+        got_p = ctx.attention_host(Q)
+        np.testing.assert_allclose(got_p, got, rtol=0, atol=2e-3)
