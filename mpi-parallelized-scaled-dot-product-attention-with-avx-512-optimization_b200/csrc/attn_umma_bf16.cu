@@ -623,19 +623,22 @@ int attn_umma_pick_splits(int rows, int n, int sm_count)
     if (row_blocks <= 0 || tiles <= 1) return 1;
     // choose the split count (<= 64, >= 4 key tiles each) with the best wave efficiency of the
     // grid row_blocks x splits over sm_count CTAs-at-a-time; prefer fewer splits on ties.
-    int best = 1;
-    double best_eff = -1.0;
     const int max_splits = std::min(64, std::max(1, tiles / 4));
-    for (int s = 1; s <= max_splits; ++s) {
+    auto efficiency = [&](int s) {
         const int ctas = row_blocks * s;
         const int waves = ceil_div(ctas, sm_count);
         const int tiles_per = ceil_div(tiles, s);  // the slowest CTA of a wave sets its length
-        const double eff = (double)row_blocks * tiles / ((double)waves * sm_count * tiles_per);
-        if (eff > best_eff + 1e-9) {
-            best_eff = eff;
+        return (double)row_blocks * tiles / ((double)waves * sm_count * tiles_per);
+    };
+    double best_eff = 0.0;
+    for (int s = 1; s <= max_splits; ++s) best_eff = std::max(best_eff, efficiency(s));
+    // fewest splits within 4% of the best: every extra split costs rows*dv*8 bytes of partial traffic
+    int best = 1;
+    for (int s = 1; s <= max_splits; ++s)
+        if (efficiency(s) >= 0.96 * best_eff) {
             best = s;
+            break;
         }
-    }
     return best;
 }
 

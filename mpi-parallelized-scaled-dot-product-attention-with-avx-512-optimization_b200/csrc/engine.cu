@@ -348,9 +348,8 @@ static int pick_q_batch(const sdpa_ctx* ctx, int m)
     if (B <= 0) {
         // Engine default: the reference's B=512 (mpi.c:200) is sized for MPI latency on CPUs.
         // On NVLink the per-batch exchange is ~tens of microseconds, so batches are made as large
-        // as keeps >= 2 batches in flight for the ping-pong overlap.
-        B = 4096;
-        if (m > 2 * B) B = 8192;
+        // as the buffers allow (8192 rows); the ping-pong overlap matters once m exceeds one batch (c4, c5).
+        B = 8192;
     }
     if (B > m) B = m;
     if (B < 1) B = 1;

@@ -16,6 +16,8 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr float kLn2 = 0.6931471805599453f;
 
+inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 // Generic combine over `count` partial states addressed through per-state base pointers.
 // Each state s: o_s[row*dv + d], tmax_s[row], lsum_s[row].
 struct StatePtrs {
@@ -28,7 +30,7 @@ template <bool FINAL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict__ out64,
                     float* __restrict__ contrib, float* __restrict__ tmax_out,
-                    float* __restrict__ lsum_out, float max_unit)
+                    float* __restrict__ lsum_out, float max_unit, bool vec_ok)
 {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -50,14 +52,38 @@ merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restric
     for (int off = 16; off > 0; off >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
     const float inv = (gsum == 0.f) ? 0.f : 1.f / gsum;
 
-    for (int d = lane; d < dv; d += 32) {
-        float acc = 0.f;
-        for (int s = 0; s < count; ++s) {
-            const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
-            acc = fmaf(st.o[s][(size_t)row * dv + d], w, acc);
+    // weights of the states, one per lane (two if count > 32), broadcast with shuffles below
+    if ((dv & 3) == 0 && vec_ok) {
+        // 16-byte vectors: lane owns 4 consecutive output columns per step
+        for (int d = lane * 4; d < dv; d += 128) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int s = 0; s < count; ++s) {
+                const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
+                const float4 v = *reinterpret_cast<const float4*>(st.o[s] + (size_t)row * dv + d);
+                acc.x = fmaf(v.x, w, acc.x);
+                acc.y = fmaf(v.y, w, acc.y);
+                acc.z = fmaf(v.z, w, acc.z);
+                acc.w = fmaf(v.w, w, acc.w);
+            }
+            if (FINAL) {
+                double2* dst = reinterpret_cast<double2*>(out64 + (size_t)row * dv + d);
+                dst[0] = make_double2((double)(acc.x * inv), (double)(acc.y * inv));
+                dst[1] = make_double2((double)(acc.z * inv), (double)(acc.w * inv));
+            } else {
+                *reinterpret_cast<float4*>(contrib + (size_t)row * dv + d) = acc;
+            }
         }
-        if (FINAL) out64[(size_t)row * dv + d] = (double)(acc * inv);
-        else contrib[(size_t)row * dv + d] = acc;
+    } else {
+        for (int d = lane; d < dv; d += 32) {
+            float acc = 0.f;
+            for (int s = 0; s < count; ++s) {
+                const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
+                acc = fmaf(st.o[s][(size_t)row * dv + d], w, acc);
+            }
+            if (FINAL) out64[(size_t)row * dv + d] = (double)(acc * inv);
+            else contrib[(size_t)row * dv + d] = acc;
+        }
     }
     if (!FINAL && lane == 0) {
         tmax_out[row] = gmax * max_unit;  // max_unit = 1 (log2 domain) or ln2 (reference's lmax)
@@ -111,12 +137,14 @@ sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, 
         st.lsum[s] = part.lsum + (size_t)s * part.rows_capacity;
     }
     const int blocks = ceil_div(rows, kWarpsPerBlock);
+    bool vec_ok = al16(out64) && al16(contrib);
+    for (int s = 0; s < part.splits; ++s) vec_ok = vec_ok && al16(st.o[s]);
     if (out64 != nullptr)
         merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-            st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f);
+            st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f, vec_ok);
     else
         merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-            st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, natural_log_max ? kLn2 : 1.f);
+            st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, natural_log_max ? kLn2 : 1.f, vec_ok);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
@@ -138,8 +166,10 @@ sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* co
         st.lsum[s] = lsum_ptrs[s];
     }
     const int blocks = ceil_div(rows, kWarpsPerBlock);
+    bool vec_ok = al16(out64);
+    for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
     merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr,
-                                                                         nullptr, nullptr, 1.f);
+                                                                         nullptr, nullptr, 1.f, vec_ok);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

@@ -1,0 +1,28 @@
+"""Short device-resident run of the headline workload for ncu (few launches, no CPU baseline)."""
+import argparse
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch  # noqa: E402
+import sdpa_b200  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--m", type=int, default=8192)
+ap.add_argument("--n", type=int, default=65536)
+ap.add_argument("--precision", default="bf16")
+ap.add_argument("--steps", type=int, default=2)
+ap.add_argument("--q-batch", type=int, default=0)
+ap.add_argument("--kv-splits", type=int, default=0)
+a = ap.parse_args()
+g = torch.Generator().manual_seed(0)
+Q = torch.randn(a.m, 128, dtype=torch.float64, generator=g).cuda()
+K = torch.randn(a.n, 128, dtype=torch.float64, generator=g).cuda()
+V = torch.randn(a.n, 128, dtype=torch.float64, generator=g).cuda()
+R = torch.zeros(a.m, 128, dtype=torch.float64, device="cuda")
+with sdpa_b200.Context(precision=a.precision, q_batch=a.q_batch, kv_splits=a.kv_splits) as ctx:
+    for _ in range(a.steps):
+        ctx.load_kv_device_ptrs([K.data_ptr()], [V.data_ptr()], [a.n], 128, 128)
+        ctx.attention_device_ptrs([Q.data_ptr()], R.data_ptr(), a.m)
+    torch.cuda.synchronize()
+    print(ctx.last_kernel(), ctx.last_timings())
