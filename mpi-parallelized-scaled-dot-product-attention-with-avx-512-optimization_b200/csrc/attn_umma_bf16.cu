@@ -8,7 +8,7 @@
 // registers, one query row per thread.
 //
 // CTA = 256 query rows (two 128-row tiles A and B, ping-ponged) x one contiguous range of
-// 128-key tiles (split-KV over blockIdx.y).  12 warps:
+// 128-key tiles (split-KV over blockIdx.y).  20 warps:
 //   warp 0      TMA producer   : Q tiles once, then K/V tiles through 2-stage mbarrier rings
 //                                (cp.async.bulk.tensor, 128-byte swizzle)
 //   warp 1      MMA issuer     : one thread issues   S_t = Q_t K^T   (SS, both K-major)
@@ -16,11 +16,16 @@
 //                                order  S_A(0) S_B(0) | PV_A(j) S_A(j+1) PV_B(j) S_B(j+1) | ...
 //                                so the softmax of one tile overlaps the MMAs of the other
 //   warps 2-3   idle (keep the softmax warpgroups aligned to the TMEM lane quadrants)
-//   warps 4-7   softmax of tile A, warps 8-11 softmax of tile B: tcgen05.ld the S row,
-//               row max (no shuffles needed: a thread owns a whole row), lazy rescale of O
-//               (only when the max grew by > 2^8, decided per warp with a vote), exp2 with the
-//               1/sqrt(dk)*log2(e) scale folded into one FFMA, bf16 P written back into the
-//               TMEM columns of S (tcgen05.st), finally the epilogue (O, tmax, lsum).
+//   warps 4-11  softmax of tile A, warps 12-19 softmax of tile B.  A tile has TWO warpgroups:
+//               a thread owns one query row and one 64-key half of it, so every SM sub-partition
+//               runs two warps of the same tile and the MUFU (ex2) pipe of one is fed while the
+//               other issues its FFMA2/FADD2/F2FP (measured on v1: one warp per sub-partition
+//               reaches only ~0.3 IPC and the per-tile chain softmax -> PV -> next S is serial,
+//               see profiles/r01).  Per tile: tcgen05.ld the half row, 8-chain FMNMX3 max, the two
+//               halves' maxima are exchanged through shared memory (named barrier, 256 threads),
+//               lazy rescale of O (only when the max grew by > 2^8, warp vote), exp2 with the
+//               1/sqrt(dk)*log2(e) scale folded into packed FFMA2, packed FADD2 row sums, bf16 P
+//               written back into the TMEM columns of S (tcgen05.st); finally the epilogue.
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P_t aliases the
 // first 64 columns of S_t (the tensor pipe executes MMAs in issue order, so S_t(j+1) cannot
 // overwrite P_t(j) before PV_t(j) has consumed it).
@@ -32,6 +37,8 @@
 #include <cuda.h>
 #include <math_constants.h>
 
+#include <type_traits>
+
 namespace sdpa {
 
 namespace {
@@ -39,7 +46,7 @@ namespace {
 constexpr int TILE = 128;            // rows per Q tile, keys per K/V tile
 constexpr int HEAD = 128;            // dk == dv
 constexpr int BLOCK_ROWS = 2 * TILE; // Q rows per CTA
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 640;
 constexpr int STAGES = 2;
 constexpr uint32_t TILE_BYTES = TILE * HEAD * 2;      // 32 KiB
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;       // one 64-column TMA box
@@ -57,6 +64,7 @@ struct __align__(1024) SharedStorage {
     uint64_t v_full[STAGES], v_empty[STAGES];
     uint64_t s_full[2], p_ready[2], o_done[2];
     uint32_t tmem_base;
+    float xchg[2][2][2][TILE];   // [tile][parity][column half][row]: row-max / row-sum exchange
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -173,6 +181,52 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])      \
         : "memory")
 
+
+#define SDPA_TMEM_LD16(taddr, r)                                                                             \
+    asm volatile(                                                                                            \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),            \
+          "=r"(r[15])                                                                                         \
+        : "r"(taddr)                                                                                         \
+        : "memory")
+
+#define SDPA_TMEM_ST16(taddr, r)                                                                             \
+    asm volatile(                                                                                            \
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                      \
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"                           \
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])        \
+        : "memory")
+
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -261,7 +315,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.q_full[i], 1);
             mbar_init(&sm.s_full[i], 1);
-            mbar_init(&sm.p_ready[i], 128);
+            mbar_init(&sm.p_ready[i], 256);
             mbar_init(&sm.o_done[i], 1);
         }
         for (int i = 0; i < STAGES; ++i) {
@@ -280,9 +334,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 
     // Register re-allocation between the warpgroups (each branch is dominated by its own
     // setmaxnreg, so ptxas budgets it separately): the producer / MMA warpgroup needs few
-    // registers, each softmax thread holds a whole 128-column S row (128*96 + 256*200 <= 384*168).
+    // registers, each softmax thread holds a 64-column half of an S row (128*64 + 512*104 = 640*96).
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (num_tiles > 0) {
         if (warp == 0) {
             // ================================ TMA producer ================================
@@ -380,47 +434,58 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         if (num_tiles > 0) {
             // ================================ softmax + epilogue ==========================
-            const int t = (warp >= 8) ? 1 : 0;            // which Q tile
+            const int sw = warp - 4;                       // 0..15
+            const int t = sw >> 3;                         // which Q tile
+            const int half = (sw >> 2) & 1;                // which 64-key half of the row
             const int quad = warp & 3;                     // TMEM lane quadrant of this warp
             const int row_in_tile = quad * 32 + lane;
             const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-            const uint32_t s_addr = tmem + lane_base + TMEM_S + 128u * t;
-            const uint32_t o_addr = tmem + lane_base + TMEM_O + 128u * t;
+            const uint32_t s_addr = tmem + lane_base + TMEM_S + 128u * t + 64u * half;   // my S columns
+            const uint32_t p_addr = tmem + lane_base + TMEM_S + 128u * t + 32u * half;   // my packed P columns
+            const uint32_t o_addr = tmem + lane_base + TMEM_O + 128u * t + 64u * half;   // my O columns
             const float scale = prm.scale_log2;
+            const uint64_t scale2 = pack_f32x2(scale, scale);
+            const int bar_id = 1 + t;
 
             float m_ref = -CUDART_INF_F;   // raw-score reference max used by every exponent so far
-            float lsum = 0.f;
+            uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);
 
-            for (int j = 0; j < num_tiles; ++j) {
+            // one key tile; MASKED = the last tile of the shard when n is not a multiple of 128
+            auto tile_step = [&](int j, auto masked_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
                 mbar_wait(&sm.s_full[t], (uint32_t)j & 1u, 300 + t);
                 tcgen05_fence_after();
 
-                uint32_t sr[128];
+                uint32_t sr[64];
                 SDPA_TMEM_LD32(s_addr + 0, (sr + 0));
                 SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
-                SDPA_TMEM_LD32(s_addr + 64, (sr + 64));
-                SDPA_TMEM_LD32(s_addr + 96, (sr + 96));
                 tmem_wait_ld();
 
-                const int keys_left = prm.n - (tile_begin + j) * TILE;   // >= 1
-                if (keys_left < TILE) {
+                if constexpr (MASKED) {
+                    const int keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;   // valid keys in my half
 #pragma unroll
-                    for (int c = 0; c < 128; ++c)
+                    for (int c = 0; c < 64; ++c)
                         if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
                 }
 
-                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+                float mx[8];
 #pragma unroll
-                for (int c = 0; c < 128; c += 4) {
-                    mx0 = fmaxf(mx0, __uint_as_float(sr[c + 0]));
-                    mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
-                    mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
-                    mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+                for (int q = 0; q < 8; ++q) mx[q] = -CUDART_INF_F;
+#pragma unroll
+                for (int c = 0; c < 64; c += 16) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        mx[q] = fmaxf(mx[q], fmaxf(__uint_as_float(sr[c + 2 * q]), __uint_as_float(sr[c + 2 * q + 1])));
                 }
-                const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                const float my_max = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
+                                           fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
+                // exchange with the thread that owns the other half of this row
+                sm.xchg[t][j & 1][half][row_in_tile] = my_max;
+                named_barrier_sync(bar_id, 256);
+                const float tile_max = fmaxf(my_max, sm.xchg[t][j & 1][half ^ 1][row_in_tile]);
 
                 // lazy rescale: keep the old reference unless the max grew by more than 2^kLazyThreshold
                 bool need = false;
@@ -434,65 +499,83 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 if (__any_sync(0xffffffffu, need)) {
                     // O_t is stable here: PV_t(j-1) completed before s_full(j) fired, and PV_t(j)
-                    // is not issued until this warpgroup signals p_ready(j).
-                    lsum *= corr;
-#pragma unroll
-                    for (int c0 = 0; c0 < HEAD; c0 += 32) {
-                        uint32_t orr[32];
-                        SDPA_TMEM_LD32(o_addr + c0, orr);
+                    // is not issued until all 256 threads of the tile signal p_ready(j).
+                    const uint64_t corr2 = pack_f32x2(corr, corr);
+                    uint64_t zero2 = pack_f32x2(0.f, 0.f);
+                    lsum2 = fma_f32x2(lsum2, corr2, zero2);
+                    lsum2b = fma_f32x2(lsum2b, corr2, zero2);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 64; c0 += 16) {   // small chunks: this path is rare, keep it out of the register budget
+                        uint32_t orr[16];
+                        SDPA_TMEM_LD16(o_addr + c0, orr);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) orr[c] = __float_as_uint(__uint_as_float(orr[c]) * corr);
-                        SDPA_TMEM_ST32(o_addr + c0, orr);
+                        for (int c = 0; c < 16; ++c) orr[c] = __float_as_uint(__uint_as_float(orr[c]) * corr);
+                        SDPA_TMEM_ST16(o_addr + c0, orr);
                     }
                 }
 
-                const float neg_ref = -m_ref * scale;
-                float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-                // two halves of 64 keys: the bf16 P of a half (32 packed columns) is stored to TMEM
-                // as soon as it is complete, which frees its registers for the second half
+                const float neg_ref_s = -m_ref * scale;
+                const uint64_t neg_ref2 = pack_f32x2(neg_ref_s, neg_ref_s);
+                // four chunks of 16 keys: packed FFMA2 (scale, subtract), 2 x ex2, packed FADD2 (row sum),
+                // F2FP pack; a chunk's 8 bf16x2 words go to TMEM as soon as the 16-key pair is complete
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    uint32_t pr[32];
+                    uint32_t pr[16];
 #pragma unroll
-                    for (int c = 0; c < 64; c += 4) {
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 0]), scale, neg_ref));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 1]), scale, neg_ref));
-                        const float p2 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 2]), scale, neg_ref));
-                        const float p3 = fast_exp2(fmaf(__uint_as_float(sr[64 * h + c + 3]), scale, neg_ref));
-                        sum0 += p0; sum1 += p1; sum2 += p2; sum3 += p3;
-                        pr[c / 2 + 0] = pack_bf16x2(p0, p1);
-                        pr[c / 2 + 1] = pack_bf16x2(p2, p3);
+                    for (int c = 0; c < 32; c += 2) {
+                        const uint64_t x2 = pack_f32x2(__uint_as_float(sr[32 * h + c]), __uint_as_float(sr[32 * h + c + 1]));
+                        const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
+                        float t0, t1;
+                        unpack_f32x2(t2, t0, t1);
+                        const float p0 = fast_exp2(t0);
+                        const float p1 = fast_exp2(t1);
+                        const uint64_t p2 = pack_f32x2(p0, p1);
+                        if (c & 2) lsum2b = add_f32x2(lsum2b, p2);
+                        else lsum2 = add_f32x2(lsum2, p2);
+                        pr[c / 2] = pack_bf16x2(p0, p1);
                     }
-                    SDPA_TMEM_ST32(s_addr + 32 * h, pr);
+                    SDPA_TMEM_ST16(p_addr + 16 * h, pr);
                 }
-                lsum += (sum0 + sum1) + (sum2 + sum3);
 
                 tmem_wait_st();
                 tcgen05_fence_before();
                 mbar_arrive(&sm.p_ready[t]);
-            }
+            };
+            const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
+            const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
+            for (int j = 0; j < full_tiles; ++j) tile_step(j, std::false_type{});
+            if (ragged) tile_step(num_tiles - 1, std::true_type{});
 
             // ---------------- epilogue: O_t, reference max, row sum ----------------
+            float l0, l1, l2, l3;
+            unpack_f32x2(lsum2, l0, l1);
+            unpack_f32x2(lsum2b, l2, l3);
+            const float my_sum = (l0 + l1) + (l2 + l3);
+            sm.xchg[t][num_tiles & 1][half][row_in_tile] = my_sum;
+            named_barrier_sync(bar_id, 256);
+            const float lsum = my_sum + sm.xchg[t][num_tiles & 1][half ^ 1][row_in_tile];
+
             mbar_wait(&sm.o_done[t], 0, 320 + t);
             tcgen05_fence_after();
             const int grow = row_block * BLOCK_ROWS + t * TILE + row_in_tile;
             const bool valid = grow < prm.rows;
             const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
 #pragma unroll
-            for (int c0 = 0; c0 < HEAD; c0 += 32) {
+            for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t orr[32];
                 SDPA_TMEM_LD32(o_addr + c0, orr);
                 tmem_wait_ld();
                 if (valid) {
+                    const int col = 64 * half + c0;
                     if (prm.out64 != nullptr) {
-                        double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + c0);
+                        double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + col);
 #pragma unroll
                         for (int c = 0; c < 32; c += 2)
                             dst[c / 2] = make_double2((double)(__uint_as_float(orr[c]) * inv),
                                                       (double)(__uint_as_float(orr[c + 1]) * inv));
                     } else {
-                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + c0);
+                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + col);
 #pragma unroll
                         for (int c = 0; c < 32; c += 4)
                             dst[c / 4] = make_float4(__uint_as_float(orr[c]), __uint_as_float(orr[c + 1]),
@@ -500,22 +583,25 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     }
                 }
             }
-            if (valid && prm.out64 == nullptr) {
+            if (valid && half == 0 && prm.out64 == nullptr) {
                 prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = m_ref * scale;
                 prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = lsum;
             }
         } else {
         // empty key range (n == 0 or more splits than tiles): the neutral state (0, -inf, 0), mpi.c:172,188
-        const int t = (warp >= 8) ? 1 : 0;
+        const int sw = warp - 4;
+        const int t = sw >> 3, half = (sw >> 2) & 1;
         const int grow = row_block * BLOCK_ROWS + t * TILE + (warp & 3) * 32 + lane;
         if (grow < prm.rows) {
             if (prm.out64 != nullptr) {
-                for (int c = 0; c < HEAD; ++c) prm.out64[(size_t)grow * HEAD + c] = 0.0;
+                for (int c = 0; c < 64; ++c) prm.out64[(size_t)grow * HEAD + 64 * half + c] = 0.0;
             } else {
-                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD;
-                for (int c = 0; c < HEAD; ++c) dst[c] = 0.f;
-                prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
-                prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
+                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + 64 * half;
+                for (int c = 0; c < 64; ++c) dst[c] = 0.f;
+                if (half == 0) {
+                    prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
+                    prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
+                }
             }
         }
         }
