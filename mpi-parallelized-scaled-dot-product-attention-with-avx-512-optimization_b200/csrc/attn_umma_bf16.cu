@@ -120,6 +120,19 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map)
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// One lane of a converged warp (the instruction is warp-uniform, so everything around it can
+// stay on the uniform datapath; a divergent `lane == 0` branch forces R2UR/ELECT traffic per MMA).
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -298,7 +311,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     SharedStorage& sm = *reinterpret_cast<SharedStorage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
     const int lane = threadIdx.x & 31;
     const int row_block = blockIdx.x;
     const int split = blockIdx.y;
@@ -340,96 +353,109 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         if (num_tiles > 0) {
         if (warp == 0) {
             // ================================ TMA producer ================================
-            if (lane == 0) {
-                const int qrow = row_block * BLOCK_ROWS;
-                for (int j = 0; j < num_tiles; ++j) {
-                    const int stage = j % STAGES;
-                    const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-                    const int key0 = (tile_begin + j) * TILE;
-                    if (j == 0) {
-                        mbar_arrive_expect_tx(&sm.q_full[0], TILE_BYTES);
-                        tma_load_2d(sm.q[0], &map_q, &sm.q_full[0], 0, qrow);
-                        tma_load_2d(sm.q[0] + HALF_BYTES, &map_q, &sm.q_full[0], 64, qrow);
-                    }
-                    mbar_wait(&sm.k_empty[stage], ph ^ 1u, 100 + stage);
+            // all 32 lanes walk the loop (uniform control flow); one elected lane issues
+            const int qrow = row_block * BLOCK_ROWS;
+            for (int j = 0; j < num_tiles; ++j) {
+                const int stage = j % STAGES;
+                const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+                const int key0 = (tile_begin + j) * TILE;
+                if (j == 0 && elect_one_sync()) {
+                    mbar_arrive_expect_tx(&sm.q_full[0], TILE_BYTES);
+                    tma_load_2d(sm.q[0], &map_q, &sm.q_full[0], 0, qrow);
+                    tma_load_2d(sm.q[0] + HALF_BYTES, &map_q, &sm.q_full[0], 64, qrow);
+                }
+                mbar_wait(&sm.k_empty[stage], ph ^ 1u, 100 + stage);
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&sm.k_full[stage], TILE_BYTES);
                     tma_load_2d(sm.k[stage], &map_k, &sm.k_full[stage], 0, key0);
                     tma_load_2d(sm.k[stage] + HALF_BYTES, &map_k, &sm.k_full[stage], 64, key0);
-                    if (j == 0) {
-                        mbar_arrive_expect_tx(&sm.q_full[1], TILE_BYTES);
-                        tma_load_2d(sm.q[1], &map_q, &sm.q_full[1], 0, qrow + TILE);
-                        tma_load_2d(sm.q[1] + HALF_BYTES, &map_q, &sm.q_full[1], 64, qrow + TILE);
-                    }
-                    mbar_wait(&sm.v_empty[stage], ph ^ 1u, 110 + stage);
+                }
+                if (j == 0 && elect_one_sync()) {
+                    mbar_arrive_expect_tx(&sm.q_full[1], TILE_BYTES);
+                    tma_load_2d(sm.q[1], &map_q, &sm.q_full[1], 0, qrow + TILE);
+                    tma_load_2d(sm.q[1] + HALF_BYTES, &map_q, &sm.q_full[1], 64, qrow + TILE);
+                }
+                mbar_wait(&sm.v_empty[stage], ph ^ 1u, 110 + stage);
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&sm.v_full[stage], TILE_BYTES);
                     tma_load_2d(sm.v[stage], &map_v, &sm.v_full[stage], 0, key0);
                     tma_load_2d(sm.v[stage] + HALF_BYTES, &map_v, &sm.v_full[stage], 64, key0);
                 }
+                __syncwarp();
             }
         } else if (warp == 1) {
             // ================================ MMA issuer ==================================
-            if (lane == 0) {
-                constexpr uint32_t idesc_qk = make_idesc(TILE, TILE, 0);
-                constexpr uint32_t idesc_pv = make_idesc(TILE, HEAD, 1);
-                const uint32_t q_addr[2] = {smem_u32(sm.q[0]), smem_u32(sm.q[1])};
+            // Uniform control flow for the whole warp; descriptors are base + constant, the
+            // tcgen05.mma / tcgen05.commit instructions sit under elect_one_sync().
+            constexpr uint32_t idesc_qk = make_idesc(TILE, TILE, 0);
+            constexpr uint32_t idesc_pv = make_idesc(TILE, HEAD, 1);
+            const uint64_t dq[2] = {desc_kmajor(smem_u32(sm.q[0]), 0), desc_kmajor(smem_u32(sm.q[1]), 0)};
+            const uint64_t dkk[STAGES] = {desc_kmajor(smem_u32(sm.k[0]), 0), desc_kmajor(smem_u32(sm.k[1]), 0)};
+            const uint64_t dvv[STAGES] = {desc_mnmajor(smem_u32(sm.v[0]), 0), desc_mnmajor(smem_u32(sm.v[1]), 0)};
 
-                auto issue_s = [&](int t, int stage) {
-                    const uint32_t k_addr = smem_u32(sm.k[stage]);
+            // S_t = Q_t K(stage)^T ; commit -> s_full[t]  (+ optionally release the K stage)
+            auto issue_s = [&](int t, int stage, bool release_k) {
+                if (elect_one_sync()) {
+                    const uint64_t a0 = dq[t], b0 = dkk[stage];
+                    const uint32_t d = tmem + TMEM_S + 128u * t;
 #pragma unroll
-                    for (int kk = 0; kk < HEAD / 16; ++kk)
-                        umma_ss(tmem + TMEM_S + 128u * t, desc_kmajor(q_addr[t], kk), desc_kmajor(k_addr, kk), idesc_qk,
-                                kk > 0 ? 1u : 0u);
+                    for (int kk = 0; kk < HEAD / 16; ++kk) {
+                        // 16-column slice kk: (kk%4)*32 B into box kk/4 -> +((kk>>2)*HALF_BYTES + (kk&3)*32) >> 4
+                        const uint64_t off = (uint64_t)(((kk >> 2) * HALF_BYTES + (kk & 3) * 32u) >> 4);
+                        umma_ss(d, a0 + off, b0 + off, idesc_qk, kk > 0 ? 1u : 0u);
+                    }
                     umma_commit(&sm.s_full[t]);
-                };
-                auto issue_pv = [&](int t, int stage, int j) {
-                    const uint32_t v_addr = smem_u32(sm.v[stage]);
+                    if (release_k) umma_commit(&sm.k_empty[stage]);
+                }
+                __syncwarp();
+            };
+            // O_t (+)= P_t V(stage) ; optionally release the V stage / signal o_done
+            auto issue_pv = [&](int t, int stage, bool accumulate_first, bool release_v, bool last) {
+                if (elect_one_sync()) {
+                    const uint64_t b0 = dvv[stage];
+                    const uint32_t d = tmem + TMEM_O + 128u * t;
+                    const uint32_t a = tmem + TMEM_S + 128u * t;
 #pragma unroll
                     for (int kk = 0; kk < TILE / 16; ++kk)
-                        umma_ts(tmem + TMEM_O + 128u * t, tmem + TMEM_S + 128u * t + 8u * kk, desc_mnmajor(v_addr, kk),
-                                idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                };
-
-                // prologue: S_A(0), S_B(0)
-                mbar_wait(&sm.k_full[0], 0, 200);
-                mbar_wait(&sm.q_full[0], 0, 201);
-                tcgen05_fence_after();
-                issue_s(0, 0);
-                mbar_wait(&sm.q_full[1], 0, 202);
-                tcgen05_fence_after();
-                issue_s(1, 0);
-                umma_commit(&sm.k_empty[0]);   // K(0) is free once S_A(0), S_B(0) have completed
-
-                for (int j = 0; j < num_tiles; ++j) {
-                    const int stage = j % STAGES;
-                    const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-                    const int nstage = (j + 1) % STAGES;
-                    const uint32_t nph = (uint32_t)((j + 1) / STAGES) & 1u;
-                    const bool more = (j + 1) < num_tiles;
-
-                    mbar_wait(&sm.v_full[stage], ph, 210);
-                    // ---- tile A ----
-                    mbar_wait(&sm.p_ready[0], (uint32_t)j & 1u, 211);
-                    tcgen05_fence_after();
-                    issue_pv(0, stage, j);
-                    if (more) {
-                        mbar_wait(&sm.k_full[nstage], nph, 212);
-                        tcgen05_fence_after();
-                        issue_s(0, nstage);
-                    } else {
-                        umma_commit(&sm.o_done[0]);
-                    }
-                    // ---- tile B ----
-                    mbar_wait(&sm.p_ready[1], (uint32_t)j & 1u, 213);
-                    tcgen05_fence_after();
-                    issue_pv(1, stage, j);
-                    umma_commit(&sm.v_empty[stage]);
-                    if (more) {
-                        issue_s(1, nstage);
-                        umma_commit(&sm.k_empty[nstage]);
-                    } else {
-                        umma_commit(&sm.o_done[1]);
-                    }
+                        umma_ts(d, a + 8u * kk, b0 + (uint64_t)((kk * 2048u) >> 4), idesc_pv,
+                                (accumulate_first || kk > 0) ? 1u : 0u);
+                    if (release_v) umma_commit(&sm.v_empty[stage]);
+                    if (last) umma_commit(&sm.o_done[t]);
                 }
+                __syncwarp();
+            };
+
+            // prologue: S_A(0), S_B(0)
+            mbar_wait(&sm.k_full[0], 0, 200);
+            mbar_wait(&sm.q_full[0], 0, 201);
+            tcgen05_fence_after();
+            issue_s(0, 0, false);
+            mbar_wait(&sm.q_full[1], 0, 202);
+            tcgen05_fence_after();
+            issue_s(1, 0, true);   // K(0) is free once S_A(0), S_B(0) have completed
+
+            for (int j = 0; j < num_tiles; ++j) {
+                const int stage = j % STAGES;
+                const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+                const int nstage = (j + 1) % STAGES;
+                const uint32_t nph = (uint32_t)((j + 1) / STAGES) & 1u;
+                const bool more = (j + 1) < num_tiles;
+
+                mbar_wait(&sm.v_full[stage], ph, 210);
+                // ---- tile A ----
+                mbar_wait(&sm.p_ready[0], (uint32_t)j & 1u, 211);
+                tcgen05_fence_after();
+                issue_pv(0, stage, j > 0, false, !more);
+                if (more) {
+                    mbar_wait(&sm.k_full[nstage], nph, 212);
+                    tcgen05_fence_after();
+                    issue_s(0, nstage, false);
+                }
+                // ---- tile B ----
+                mbar_wait(&sm.p_ready[1], (uint32_t)j & 1u, 213);
+                tcgen05_fence_after();
+                issue_pv(1, stage, j > 0, true, !more);
+                if (more) issue_s(1, nstage, true);
             }
         }
         }
