@@ -38,6 +38,8 @@
 #include <math_constants.h>
 
 #include <type_traits>
+#include <vector>
+#include <stdlib.h>
 
 namespace sdpa {
 
@@ -302,8 +304,12 @@ struct KernelParams {
     float* part_lsum;
     int rows_capacity;
     double* out64;       // non-null (splits == 1): normalised fp64 output
+    long long* trace;    // TRACE build only: clock64 stamps of CTA (0,0), [role][iteration][event]
 };
 
+constexpr int TRACE_ITERS = 24, TRACE_EVENTS = 8, TRACE_ROLES = 6;
+
+template <bool TRACE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
@@ -344,6 +350,12 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem = sm.tmem_base;
+    auto stamp = [&](int role, int j, int ev) {
+        if constexpr (TRACE) {
+            if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < TRACE_ITERS)
+                prm.trace[(role * TRACE_ITERS + j) * TRACE_EVENTS + ev] = clock64();
+        }
+    };
 
     // Register re-allocation between the warpgroups (each branch is dominated by its own
     // setmaxnreg, so ptxas budgets it separately): the producer / MMA warpgroup needs few
@@ -365,6 +377,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     tma_load_2d(sm.q[0] + HALF_BYTES, &map_q, &sm.q_full[0], 64, qrow);
                 }
                 mbar_wait(&sm.k_empty[stage], ph ^ 1u, 100 + stage);
+                stamp(5, j, 0);
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&sm.k_full[stage], TILE_BYTES);
                     tma_load_2d(sm.k[stage], &map_k, &sm.k_full[stage], 0, key0);
@@ -376,6 +389,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     tma_load_2d(sm.q[1] + HALF_BYTES, &map_q, &sm.q_full[1], 64, qrow + TILE);
                 }
                 mbar_wait(&sm.v_empty[stage], ph ^ 1u, 110 + stage);
+                stamp(5, j, 1);
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&sm.v_full[stage], TILE_BYTES);
                     tma_load_2d(sm.v[stage], &map_v, &sm.v_full[stage], 0, key0);
@@ -442,20 +456,26 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const bool more = (j + 1) < num_tiles;
 
                 mbar_wait(&sm.v_full[stage], ph, 210);
+                stamp(4, j, 0);
                 // ---- tile A ----
                 mbar_wait(&sm.p_ready[0], (uint32_t)j & 1u, 211);
+                stamp(4, j, 1);
                 tcgen05_fence_after();
                 issue_pv(0, stage, j > 0, false, !more);
+                stamp(4, j, 2);
                 if (more) {
                     mbar_wait(&sm.k_full[nstage], nph, 212);
                     tcgen05_fence_after();
                     issue_s(0, nstage, false);
                 }
+                stamp(4, j, 3);
                 // ---- tile B ----
                 mbar_wait(&sm.p_ready[1], (uint32_t)j & 1u, 213);
+                stamp(4, j, 4);
                 tcgen05_fence_after();
                 issue_pv(1, stage, j > 0, true, !more);
                 if (more) issue_s(1, nstage, true);
+                stamp(4, j, 5);
             }
         }
         }
@@ -483,12 +503,14 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             auto tile_step = [&](int j, auto masked_tag) {
                 constexpr bool MASKED = decltype(masked_tag)::value;
                 mbar_wait(&sm.s_full[t], (uint32_t)j & 1u, 300 + t);
+                if (quad == 0) stamp(sw >> 2, j, 0);
                 tcgen05_fence_after();
 
                 uint32_t sr[64];
                 SDPA_TMEM_LD32(s_addr + 0, (sr + 0));
                 SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
                 tmem_wait_ld();
+                if (quad == 0) stamp(sw >> 2, j, 1);
 
                 if constexpr (MASKED) {
                     const int keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;   // valid keys in my half
@@ -509,6 +531,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 const float my_max = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
                                            fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
                 // exchange with the thread that owns the other half of this row
+                if (quad == 0) stamp(sw >> 2, j, 2);
                 sm.xchg[t][j & 1][half][row_in_tile] = my_max;
                 named_barrier_sync(bar_id, 256);
                 const float tile_max = fmaxf(my_max, sm.xchg[t][j & 1][half ^ 1][row_in_tile]);
@@ -541,6 +564,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     }
                 }
 
+                if (quad == 0) stamp(sw >> 2, j, 3);
                 const float neg_ref_s = -m_ref * scale;
                 const uint64_t neg_ref2 = pack_f32x2(neg_ref_s, neg_ref_s);
                 // four chunks of 16 keys: packed FFMA2 (scale, subtract), 2 x ex2, packed FADD2 (row sum),
@@ -564,9 +588,11 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     SDPA_TMEM_ST16(p_addr + 16 * h, pr);
                 }
 
+                if (quad == 0) stamp(sw >> 2, j, 4);
                 tmem_wait_st();
                 tcgen05_fence_before();
                 mbar_arrive(&sm.p_ready[t]);
+                if (quad == 0) stamp(sw >> 2, j, 5);
             };
             const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
             const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
@@ -772,7 +798,7 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     int dev = 0;
     SDPA_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && !plan->attr_set[dev]) {
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         plan->attr_set[dev] = true;
     }
     KernelParams prm;
@@ -786,8 +812,34 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.part_lsum = part.lsum;
     prm.rows_capacity = part.rows_capacity;
     prm.out64 = out64;
+    prm.trace = nullptr;
     dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);
-    attn_umma_kernel<<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+    const char* trace_path = getenv("SDPA_UMMA_TRACE");   // developer aid: dump a clock64 timeline of CTA (0,0)
+    if (trace_path && *trace_path) {
+        const size_t count = (size_t)TRACE_ROLES * TRACE_ITERS * TRACE_EVENTS;
+        long long* dtrace = nullptr;
+        SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
+        SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
+        prm.trace = dtrace;
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attn_umma_kernel<true><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        count_launch();
+        std::vector<long long> host(count);
+        SDPA_CUDA_TRY(cudaMemcpyAsync(host.data(), dtrace, count * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(stream));
+        SDPA_CUDA_TRY(cudaFree(dtrace));
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "role iteration event clock\n");
+            for (int r = 0; r < TRACE_ROLES; ++r)
+                for (int j = 0; j < TRACE_ITERS; ++j)
+                    for (int e = 0; e < TRACE_EVENTS; ++e)
+                        if (host[(r * TRACE_ITERS + j) * TRACE_EVENTS + e])
+                            fprintf(f, "%d %d %d %lld\n", r, j, e, host[(r * TRACE_ITERS + j) * TRACE_EVENTS + e]);
+            fclose(f);
+        }
+        return SDPA_OK;
+    }
+    attn_umma_kernel<false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
