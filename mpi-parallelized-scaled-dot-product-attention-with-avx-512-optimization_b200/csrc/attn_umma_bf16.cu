@@ -197,6 +197,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
         : "memory")
 
 
+#define SDPA_TMEM_ST8(taddr, r)                                                                              \
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"             \
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),  \
+                   "r"(r[7])                                                                                  \
+                 : "memory")
+
 #define SDPA_TMEM_LD16(taddr, r)                                                                             \
     asm volatile(                                                                                            \
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
@@ -430,9 +436,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     const uint32_t d = tmem + TMEM_O + 128u * t;
                     const uint32_t a = tmem + TMEM_S + 128u * t;
 #pragma unroll
-                    for (int kk = 0; kk < TILE / 16; ++kk)
-                        umma_ts(d, a + 8u * kk, b0 + (uint64_t)((kk * 2048u) >> 4), idesc_pv,
-                                (accumulate_first || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < TILE / 16; ++kk)   // P of keys 0-63 at S+0.., of keys 64-127 at S+64..
+                        umma_ts(d, a + (kk < 4 ? 8u * kk : 64u + 8u * (kk - 4)), b0 + (uint64_t)((kk * 2048u) >> 4),
+                                idesc_pv, (accumulate_first || kk > 0) ? 1u : 0u);
                     if (release_v) umma_commit(&sm.v_empty[stage]);
                     if (last) umma_commit(&sm.o_done[t]);
                 }
@@ -489,17 +495,40 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int quad = warp & 3;                     // TMEM lane quadrant of this warp
             const int row_in_tile = quad * 32 + lane;
             const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-            const uint32_t s_addr = tmem + lane_base + TMEM_S + 128u * t + 64u * half;   // my S columns
-            const uint32_t p_addr = tmem + lane_base + TMEM_S + 128u * t + 32u * half;   // my packed P columns
+            const uint32_t s_addr = tmem + lane_base + TMEM_S + 128u * t + 64u * half;   // my 64 S columns;
+            const uint32_t p_addr = s_addr;   // my bf16 P (32 packed columns) overwrites the start of my own S columns
             const uint32_t o_addr = tmem + lane_base + TMEM_O + 128u * t + 64u * half;   // my O columns
             const float scale = prm.scale_log2;
             const uint64_t scale2 = pack_f32x2(scale, scale);
-            const int bar_id = 1 + t;
+            const int bar_id = 1 + 4 * t + quad;           // pair barrier: the two warps that share these 32 rows
 
             float m_ref = -CUDART_INF_F;   // raw-score reference max used by every exponent so far
-            uint64_t lsum2 = pack_f32x2(0.f, 0.f), lsum2b = pack_f32x2(0.f, 0.f);
+            float lsum = 0.f;
 
-            // one key tile; MASKED = the last tile of the shard when n is not a multiple of 128
+            // exp2(s*scale - ref*scale) of 16 keys: packed FFMA2, 2 x ex2 per pair, packed FADD2 row sum, F2FP pack
+            auto exp_chunk = [&](const uint32_t* sv, uint64_t neg_ref2, uint64_t& acc0, uint64_t& acc1, uint32_t* pr) {
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+                    const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
+                    float t0, t1;
+                    unpack_f32x2(t2, t0, t1);
+                    const float p0 = fast_exp2(t0);
+                    const float p1 = fast_exp2(t1);
+                    const uint64_t p2 = pack_f32x2(p0, p1);
+                    if (c & 2) acc1 = add_f32x2(acc1, p2);
+                    else acc0 = add_f32x2(acc0, p2);
+                    pr[c / 2] = pack_bf16x2(p0, p1);
+                }
+            };
+
+            // One key tile.  The exponentials are SPECULATIVE on the reference max of the previous tiles
+            // so they can start as soon as the first 16 columns arrive from TMEM (the remaining
+            // tcgen05.ld's stream behind the MUFU work); the tile's own max is computed alongside and
+            // exchanged with the other half of the row at the end.  Only if the max grew by more than
+            // 2^kLazyThreshold (or on the very first tile, reference = -inf) is the tile redone with the
+            // new reference and O rescaled -- the lazy rescale, decided per warp with a vote.
+            // MASKED = the last tile of the shard when n is not a multiple of 128.
             auto tile_step = [&](int j, auto masked_tag) {
                 constexpr bool MASKED = decltype(masked_tag)::value;
                 mbar_wait(&sm.s_full[t], (uint32_t)j & 1u, 300 + t);
@@ -507,54 +536,54 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 tcgen05_fence_after();
 
                 uint32_t sr[64];
-                SDPA_TMEM_LD32(s_addr + 0, (sr + 0));
-                SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
-                tmem_wait_ld();
-                if (quad == 0) stamp(sw >> 2, j, 1);
+                const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
+                uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+                int keys_left = 64;
+                if constexpr (MASKED) keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;   // valid keys in my half
 
-                if constexpr (MASKED) {
-                    const int keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;   // valid keys in my half
+                SDPA_TMEM_LD16(s_addr, sr);
 #pragma unroll
-                    for (int c = 0; c < 64; ++c)
-                        if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
+                for (int ch = 0; ch < 4; ++ch) {
+                    tmem_wait_ld();
+                    if (ch == 0 && quad == 0) stamp(sw >> 2, j, 1);
+                    if (ch < 3) SDPA_TMEM_LD16(s_addr + 16 * (ch + 1), (sr + 16 * (ch + 1)));   // in flight during this chunk
+                    uint32_t* sv = sr + 16 * ch;
+                    if constexpr (MASKED) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c)
+                            if (16 * ch + c >= keys_left) sv[c] = 0xff800000u;  // -inf
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; c += 8) {
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[c + 0]), __uint_as_float(sv[c + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])));
+                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5])));
+                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7])));
+                    }
+                    uint32_t pr[8];
+                    exp_chunk(sv, neg_ref2, acc0, acc1, pr);
+                    SDPA_TMEM_ST8(p_addr + 8 * ch, pr);   // columns [8ch, 8ch+8) of my region: S values already in registers
                 }
-
-                float mx[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) mx[q] = -CUDART_INF_F;
-#pragma unroll
-                for (int c = 0; c < 64; c += 16) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        mx[q] = fmaxf(mx[q], fmaxf(__uint_as_float(sr[c + 2 * q]), __uint_as_float(sr[c + 2 * q + 1])));
-                }
-                const float my_max = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])),
-                                           fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-                // exchange with the thread that owns the other half of this row
                 if (quad == 0) stamp(sw >> 2, j, 2);
-                sm.xchg[t][j & 1][half][row_in_tile] = my_max;
-                named_barrier_sync(bar_id, 256);
-                const float tile_max = fmaxf(my_max, sm.xchg[t][j & 1][half ^ 1][row_in_tile]);
 
-                // lazy rescale: keep the old reference unless the max grew by more than 2^kLazyThreshold
-                bool need = false;
-                float corr = 1.f;
-                if (j == 0) {
-                    m_ref = tile_max;
-                } else if ((tile_max - m_ref) * scale > kLazyThreshold) {
-                    need = true;
-                    corr = fast_exp2((m_ref - tile_max) * scale);
-                    m_ref = tile_max;
-                }
+                // agree on the tile max with the thread that owns the other half of this row
+                const float my_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                sm.xchg[t][j & 1][half][row_in_tile] = my_max;
+                named_barrier_sync(bar_id, 64);
+                const float tile_max = fmaxf(my_max, sm.xchg[t][j & 1][half ^ 1][row_in_tile]);
+                if (quad == 0) stamp(sw >> 2, j, 3);
+
+                const bool need = (tile_max - m_ref) * scale > kLazyThreshold;   // first tile: -inf reference -> true
                 if (__any_sync(0xffffffffu, need)) {
-                    // O_t is stable here: PV_t(j-1) completed before s_full(j) fired, and PV_t(j)
-                    // is not issued until all 256 threads of the tile signal p_ready(j).
-                    const uint64_t corr2 = pack_f32x2(corr, corr);
-                    uint64_t zero2 = pack_f32x2(0.f, 0.f);
-                    lsum2 = fma_f32x2(lsum2, corr2, zero2);
-                    lsum2b = fma_f32x2(lsum2b, corr2, zero2);
+                    // Rare path.  O_t is stable here: PV_t(j-1) completed before s_full(j) fired, and
+                    // PV_t(j) is not issued until all 256 threads of the tile signal p_ready(j).
+                    const float new_ref = need ? tile_max : m_ref;
+                    const float corr = need ? fast_exp2((m_ref - new_ref) * scale) : 1.f;   // -inf reference -> 0
+                    m_ref = new_ref;
+                    lsum *= corr;
 #pragma unroll 1
-                    for (int c0 = 0; c0 < 64; c0 += 16) {   // small chunks: this path is rare, keep it out of the register budget
+                    for (int c0 = 0; c0 < 64; c0 += 16) {   // small chunks: keep this path out of the register budget
                         uint32_t orr[16];
                         SDPA_TMEM_LD16(o_addr + c0, orr);
                         tmem_wait_ld();
@@ -562,31 +591,20 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         for (int c = 0; c < 16; ++c) orr[c] = __float_as_uint(__uint_as_float(orr[c]) * corr);
                         SDPA_TMEM_ST16(o_addr + c0, orr);
                     }
-                }
-
-                if (quad == 0) stamp(sw >> 2, j, 3);
-                const float neg_ref_s = -m_ref * scale;
-                const uint64_t neg_ref2 = pack_f32x2(neg_ref_s, neg_ref_s);
-                // four chunks of 16 keys: packed FFMA2 (scale, subtract), 2 x ex2, packed FADD2 (row sum),
-                // F2FP pack; a chunk's 8 bf16x2 words go to TMEM as soon as the 16-key pair is complete
+                    const uint64_t neg_new2 = pack_f32x2(-new_ref * scale, -new_ref * scale);
+                    acc0 = pack_f32x2(0.f, 0.f);
+                    acc1 = acc0;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t pr[16];
-#pragma unroll
-                    for (int c = 0; c < 32; c += 2) {
-                        const uint64_t x2 = pack_f32x2(__uint_as_float(sr[32 * h + c]), __uint_as_float(sr[32 * h + c + 1]));
-                        const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
-                        float t0, t1;
-                        unpack_f32x2(t2, t0, t1);
-                        const float p0 = fast_exp2(t0);
-                        const float p1 = fast_exp2(t1);
-                        const uint64_t p2 = pack_f32x2(p0, p1);
-                        if (c & 2) lsum2b = add_f32x2(lsum2b, p2);
-                        else lsum2 = add_f32x2(lsum2, p2);
-                        pr[c / 2] = pack_bf16x2(p0, p1);
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t pr[8];
+                        exp_chunk(sr + 16 * ch, neg_new2, acc0, acc1, pr);
+                        SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
                     }
-                    SDPA_TMEM_ST16(p_addr + 16 * h, pr);
                 }
+                float a0, a1, a2, a3;
+                unpack_f32x2(acc0, a0, a1);
+                unpack_f32x2(acc1, a2, a3);
+                lsum += (a0 + a1) + (a2 + a3);
 
                 if (quad == 0) stamp(sw >> 2, j, 4);
                 tmem_wait_st();
@@ -600,13 +618,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             if (ragged) tile_step(num_tiles - 1, std::true_type{});
 
             // ---------------- epilogue: O_t, reference max, row sum ----------------
-            float l0, l1, l2, l3;
-            unpack_f32x2(lsum2, l0, l1);
-            unpack_f32x2(lsum2b, l2, l3);
-            const float my_sum = (l0 + l1) + (l2 + l3);
-            sm.xchg[t][num_tiles & 1][half][row_in_tile] = my_sum;
-            named_barrier_sync(bar_id, 256);
-            const float lsum = my_sum + sm.xchg[t][num_tiles & 1][half ^ 1][row_in_tile];
+            sm.xchg[t][num_tiles & 1][half][row_in_tile] = lsum;
+            named_barrier_sync(bar_id, 64);
+            lsum += sm.xchg[t][num_tiles & 1][half ^ 1][row_in_tile];
 
             mbar_wait(&sm.o_done[t], 0, 320 + t);
             tcgen05_fence_after();
