@@ -52,7 +52,9 @@ constexpr int NTHREADS = 640;
 constexpr int STAGES = 2;
 constexpr uint32_t TILE_BYTES = TILE * HEAD * 2;      // 32 KiB
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;       // one 64-column TMA box
-constexpr float kLazyThreshold = 8.0f;                // rescale O only if the max grew by > 2^8
+constexpr float kLazyThreshold = 8.0f;                // safe mode: rescale O only if the max grew by > 2^8
+constexpr float kGuardThreshold = 64.0f;              // fast mode: exponents beyond 2^64 hand the launch to the safe kernel
+constexpr int kDefaultPoly = 4;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
 
 constexpr uint32_t TMEM_S = 0;    // + 128 * tile
 constexpr uint32_t TMEM_O = 256;  // + 128 * tile
@@ -243,6 +245,31 @@ __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// 2^x for two packed values on the FMA/ALU pipes (no MUFU): x = n + f, n = round(x) taken from the
+// low mantissa bits of x + 1.5*2^23, f in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (max
+// relative error 7.5e-5, far below the bf16 rounding of P), 2^n by an integer multiply-add into the
+// exponent field.  Inputs are clamped at -126 (result ~ 0); callers guarantee x < 64.
+__device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& p0, float& p1)
+{
+    float x0, x1;
+    unpack_f32x2(x2, x0, x1);
+    x0 = fmaxf(x0, -126.f);
+    x1 = fmaxf(x1, -126.f);
+    const uint64_t xc = pack_f32x2(x0, x1);
+    const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);
+    const uint64_t xr = add_f32x2(xc, magic);                                   // integer part lands in the mantissa
+    const uint64_t n2 = add_f32x2(xr, pack_f32x2(-12582912.f, -12582912.f));    // round(x) as a float
+    const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.f, -1.f), xc);              // x - round(x)
+    uint64_t p = fma_f32x2(pack_f32x2(0.0551716685f, 0.0551716685f), f2, pack_f32x2(0.2426111251f, 0.2426111251f));
+    p = fma_f32x2(p, f2, pack_f32x2(0.6932609677f, 0.6932609677f));
+    p = fma_f32x2(p, f2, pack_f32x2(0.9999280572f, 0.9999280572f));
+    float q0, q1, r0, r1;
+    unpack_f32x2(p, q0, q1);
+    unpack_f32x2(xr, r0, r1);
+    p0 = __uint_as_float(__float_as_uint(r0) * 0x800000u + __float_as_uint(q0));   // += n << 23
+    p1 = __uint_as_float(__float_as_uint(r1) * 0x800000u + __float_as_uint(q1));
+}
+
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -311,15 +338,23 @@ struct KernelParams {
     int rows_capacity;
     double* out64;       // non-null (splits == 1): normalised fp64 output
     long long* trace;    // TRACE build only: clock64 stamps of CTA (0,0), [role][iteration][event]
+    unsigned int* guard; // fast mode writes `epoch` here when an exponent would overflow; the safe kernel runs iff *guard == epoch
+    unsigned int epoch;
 };
 
 constexpr int TRACE_ITERS = 24, TRACE_EVENTS = 8, TRACE_ROLES = 6;
 
-template <bool TRACE>
+// SAFE = the always-correct variant (row max agreed every tile, lazy rescale).  The default launch is
+// the fast variant (reference fixed after the first tile) followed by the SAFE variant, which exits
+// immediately unless the fast one raised the overflow guard.  POLY: see kDefaultPoly.
+template <bool TRACE, bool SAFE, int POLY>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
 {
+    if constexpr (SAFE) {
+        if (*prm.guard != prm.epoch) return;   // nothing overflowed in the fast pass: the whole grid leaves at once
+    }
     extern __shared__ uint8_t smem_raw[];
     SharedStorage& sm = *reinterpret_cast<SharedStorage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -511,12 +546,19 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 for (int c = 0; c < 16; c += 2) {
                     const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
                     const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
-                    float t0, t1;
-                    unpack_f32x2(t2, t0, t1);
-                    const float p0 = fast_exp2(t0);
-                    const float p1 = fast_exp2(t1);
+                    float p0, p1;
+                    // pairs 1 and 5 (POLY=4) or 1,3,5,7 (POLY=8) of the eight pairs use the polynomial
+                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
+                    if (poly) {
+                        exp2_poly_x2(t2, p0, p1);
+                    } else {
+                        float t0, t1;
+                        unpack_f32x2(t2, t0, t1);
+                        p0 = fast_exp2(t0);
+                        p1 = fast_exp2(t1);
+                    }
                     const uint64_t p2 = pack_f32x2(p0, p1);
-                    if (c & 2) acc1 = add_f32x2(acc1, p2);
+                    if (c & 4) acc1 = add_f32x2(acc1, p2);
                     else acc0 = add_f32x2(acc0, p2);
                     pr[c / 2] = pack_bf16x2(p0, p1);
                 }
@@ -529,8 +571,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             // 2^kLazyThreshold (or on the very first tile, reference = -inf) is the tile redone with the
             // new reference and O rescaled -- the lazy rescale, decided per warp with a vote.
             // MASKED = the last tile of the shard when n is not a multiple of 128.
-            auto tile_step = [&](int j, auto masked_tag) {
+            auto tile_step = [&](int j, auto masked_tag, auto first_tag) {
                 constexpr bool MASKED = decltype(masked_tag)::value;
+                constexpr bool AGREE = SAFE || decltype(first_tag)::value;   // exchange the row max on this tile?
                 mbar_wait(&sm.s_full[t], (uint32_t)j & 1u, 300 + t);
                 if (quad == 0) stamp(sw >> 2, j, 0);
                 tcgen05_fence_after();
@@ -567,8 +610,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 if (quad == 0) stamp(sw >> 2, j, 2);
 
-                // agree on the tile max with the thread that owns the other half of this row
                 const float my_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if constexpr (AGREE) {
+                // agree on the tile max with the thread that owns the other half of this row
                 sm.xchg[t][j & 1][half][row_in_tile] = my_max;
                 named_barrier_sync(bar_id, 64);
                 const float tile_max = fmaxf(my_max, sm.xchg[t][j & 1][half ^ 1][row_in_tile]);
@@ -601,6 +645,16 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
                     }
                 }
+                } else {
+                    // Fast mode after the first tile: the reference stays where the first tile put it
+                    // (any reference gives the same quotient o/lsum; fp32 has the range for 2^64 growth).
+                    // If a score outgrows it by more than 2^kGuardThreshold the launch is handed to the
+                    // SAFE kernel, which recomputes everything with per-tile agreement.
+                    if (quad == 0) stamp(sw >> 2, j, 3);
+                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
+                        if (lane == 0) atomicExch(prm.guard, prm.epoch);
+                    }
+                }
                 float a0, a1, a2, a3;
                 unpack_f32x2(acc0, a0, a1);
                 unpack_f32x2(acc1, a2, a3);
@@ -614,8 +668,12 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             };
             const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
             const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
-            for (int j = 0; j < full_tiles; ++j) tile_step(j, std::false_type{});
-            if (ragged) tile_step(num_tiles - 1, std::true_type{});
+            if (full_tiles > 0) tile_step(0, std::false_type{}, std::true_type{});
+            for (int j = 1; j < full_tiles; ++j) tile_step(j, std::false_type{}, std::false_type{});
+            if (ragged) {
+                if (num_tiles == 1) tile_step(0, std::true_type{}, std::true_type{});
+                else tile_step(num_tiles - 1, std::true_type{}, std::false_type{});
+            }
 
             // ---------------- epilogue: O_t, reference max, row sum ----------------
             sm.xchg[t][num_tiles & 1][half][row_in_tile] = lsum;
@@ -730,6 +788,8 @@ struct UmmaPlan {
     const void* q_base[2] = {nullptr, nullptr};
     int q_rows[2] = {0, 0};
     bool attr_set[64] = {};
+    unsigned int* guard = nullptr;   // device word for the overflow guard (on the plan's device)
+    unsigned int epoch = 0;
 };
 
 sdpa_status umma_plan_create(UmmaPlan** plan)
@@ -737,7 +797,11 @@ sdpa_status umma_plan_create(UmmaPlan** plan)
     *plan = new UmmaPlan();
     return SDPA_OK;
 }
-void umma_plan_destroy(UmmaPlan* plan) { delete plan; }
+void umma_plan_destroy(UmmaPlan* plan)
+{
+    if (plan && plan->guard) cudaFree(plan->guard);
+    delete plan;
+}
 
 bool attn_umma_supported(int dk, int dv) { return dk == HEAD && dv == HEAD; }
 
@@ -811,9 +875,24 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     const size_t smem_bytes = sizeof(SharedStorage) + 1024;
     int dev = 0;
     SDPA_CUDA_TRY(cudaGetDevice(&dev));
+    // developer knobs: SDPA_UMMA_POLY=0|4|8 exponentials of every 16 on the FMA pipe; SDPA_UMMA_SAFE=1 forces the safe kernel
+    const char* env_poly = getenv("SDPA_UMMA_POLY");
+    int poly = env_poly ? atoi(env_poly) : kDefaultPoly;
+    if (poly != 0 && poly != 4 && poly != 8) poly = kDefaultPoly;
+    const char* env_safe = getenv("SDPA_UMMA_SAFE");
+    const bool force_safe = env_safe && *env_safe == '1';
     if (dev < 64 && !plan->attr_set[dev]) {
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        const int sb = (int)smem_bytes;
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true, false, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         plan->attr_set[dev] = true;
+    }
+    if (!plan->guard) {
+        SDPA_CUDA_TRY(cudaMalloc(&plan->guard, sizeof(unsigned int)));
+        SDPA_CUDA_TRY(cudaMemset(plan->guard, 0, sizeof(unsigned int)));
     }
     KernelParams prm;
     prm.rows = rows;
@@ -827,6 +906,9 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.rows_capacity = part.rows_capacity;
     prm.out64 = out64;
     prm.trace = nullptr;
+    prm.guard = plan->guard;
+    prm.epoch = ++plan->epoch;
+    if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
     dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);
     const char* trace_path = getenv("SDPA_UMMA_TRACE");   // developer aid: dump a clock64 timeline of CTA (0,0)
     if (trace_path && *trace_path) {
@@ -835,8 +917,7 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
         SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
         prm.trace = dtrace;
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attn_umma_kernel<true><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
         std::vector<long long> host(count);
         SDPA_CUDA_TRY(cudaMemcpyAsync(host.data(), dtrace, count * sizeof(long long), cudaMemcpyDeviceToHost, stream));
@@ -851,9 +932,18 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
                             fprintf(f, "%d %d %d %lld\n", r, j, e, host[(r * TRACE_ITERS + j) * TRACE_EVENTS + e]);
             fclose(f);
         }
-        return SDPA_OK;
+        prm.trace = nullptr;
+    } else if (force_safe) {
+        SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
+        prm.epoch = 0xffffffffu;
+    } else {
+        if (poly == 0) attn_umma_kernel<false, false, 0><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (poly == 8) attn_umma_kernel<false, false, 8><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else attn_umma_kernel<false, false, 4><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        count_launch();
     }
-    attn_umma_kernel<false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+    // the safe variant: leaves immediately unless the guard was raised for this epoch
+    attn_umma_kernel<false, true, 0><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

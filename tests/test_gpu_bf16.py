@@ -93,3 +93,33 @@ def test_bf16_full_size_c3_row_subset(sdpa, oracle):
         ctx.load_kv_host_full(K[perm], V[perm])
         got_p = ctx.attention_host(Q)
         np.testing.assert_allclose(got_p, got, rtol=0, atol=2e-3)
+
+
+def test_bf16_overflow_guard_hands_over_to_safe_kernel(sdpa, oracle):
+    """Fast mode fixes the softmax reference after the first key tile; scores that outgrow it by more
+    than 2^64 raise the guard and the SAFE kernel (per-tile agreement + lazy rescale) recomputes the
+    launch.  First 128 keys tiny, the rest enormous: without the hand-over the result would be inf/NaN."""
+    Q, K, V = oracle.make_inputs(300, 1500, 128, 128, seed=11)
+    Q = Q * 3.0
+    K[:128] *= 0.01
+    K[128:] *= 30.0
+    Qb, Kb, Vb = (oracle.bf16_round(a).astype(np.float64) for a in (Q, K, V))
+    ref_b = oracle.attention_f64_numpy(Qb, Kb, Vb)
+    for splits in (1, 0):
+        with sdpa.Context(precision="bf16", kv_splits=splits) as ctx:
+            ctx.load_kv_host_full(K, V)
+            got = ctx.attention_host(Q)
+        assert np.isfinite(got).all()
+        np.testing.assert_allclose(got, ref_b, rtol=0, atol=2e-2)
+
+
+@pytest.mark.parametrize("env", [{"SDPA_UMMA_SAFE": "1"}, {"SDPA_UMMA_POLY": "0"}, {"SDPA_UMMA_POLY": "8"}])
+def test_bf16_kernel_variants(sdpa, oracle, monkeypatch, env):
+    """The safe kernel alone, and the fast kernel with 0 / 8 of every 16 exponentials on the FMA pipe."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    Q, K, V, got = _run(sdpa, oracle, 600, 2500, seed=21)
+    ref = oracle.attention_f64_numpy(Q, K, V)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=BF16_ATOL)
+    Qb, Kb, Vb = (oracle.bf16_round(a).astype(np.float64) for a in (Q, K, V))
+    np.testing.assert_allclose(got, oracle.attention_f64_numpy(Qb, Kb, Vb), rtol=0, atol=BF16_KERNEL_ATOL)
