@@ -1,0 +1,104 @@
+"""Multi-GPU parity (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
+K/V rows sharded with owner_count/owner_disp (attention-mpi.c:19-27), merged with the
+reference's three collectives over NCCL (attention-mpi.c:342,354,380) or the fused peer-memory
+merge; one process driving several GPUs, and one process per GPU (torchrun model)."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def _need_gpus(sdpa, n):
+    if sdpa.device_count() < n:
+        pytest.skip(f"needs {n} GPUs, {sdpa.device_count()} visible")
+
+
+@pytest.mark.parametrize("merge", ["nccl", "peer"])
+@pytest.mark.parametrize("prec,m,n,d,atol", [("f32", 300, 1001, 64, 1e-5), ("f32", 129, 3, 80, 1e-5),
+                                             ("bf16", 700, 5000, 128, 1e-2), ("bf16", 9000, 4100, 128, 1e-2)])
+def test_single_process_two_gpus(sdpa, oracle, merge, prec, m, n, d, atol):
+    _need_gpus(sdpa, 2)
+    Q, K, V = oracle.make_inputs(m, n, d, d, seed=m + n)
+    ref = oracle.attention_f64_numpy(Q, K, V)
+    with sdpa.Context(precision=prec, num_local=2, merge=merge) as ctx:
+        ctx.load_kv_host_full(K, V)       # n=3 with 2 shards: ragged; n < shards elsewhere -> empty shard
+        got = ctx.attention_host(Q)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=atol)
+    assert oracle.verify_rule(got, ref)
+
+
+def test_single_process_empty_shard(sdpa, oracle):
+    _need_gpus(sdpa, 2)
+    Q, K, V = oracle.make_inputs(50, 1, 32, 32, seed=5)   # n=1 < 2 shards: GPU 1 owns nothing (lmax=-inf, mpi.c:172)
+    ref = oracle.attention_f64(Q, K, V)
+    for merge in ("nccl", "peer"):
+        with sdpa.Context(precision="f32", num_local=2, merge=merge) as ctx:
+            ctx.load_kv_host_full(K, V)
+            got = ctx.attention_host(Q)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-5)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_worker(rank, world, port, out_dir, id_file):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import sdpa_b200
+    from sdpa_b200 import parallel
+    from oracle import oracle as o
+
+    m, n, d = 1500, 6001, 128
+    Q, K, V = o.make_inputs(m, n, d, d, seed=77)
+    ref = o.attention_f64_numpy(Q, K, V) if rank == 0 else None
+    first, count = parallel.shard_rows(n, world, rank)
+    for prec, atol in (("f32", 1e-5), ("bf16", 1e-2)):
+        # (1) pre-sharded inputs, one context per rank (bench.py's model)
+        ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank)
+        ctx.load_kv_host([K[first:first + count]], [V[first:first + count]])
+        got = ctx.attention_host(Q)
+        if rank == 0:
+            np.testing.assert_allclose(got, ref, rtol=0, atol=atol)
+        else:
+            assert got is None
+        # (2) the reference's calling convention: data on rank 0 only (mpi.c:508-517)
+        got2 = ctx.scatter_attention(Q, K, V) if rank == 0 else ctx.scatter_attention()
+        if rank == 0:
+            np.testing.assert_allclose(got2, ref, rtol=0, atol=atol)
+        ctx.close()
+    # (3) the drop-in entry point attention(..., mpi_rank, mpi_size) with the file rendezvous
+    os.environ["SDPA_NCCL_ID_FILE"] = id_file
+    os.environ["SDPA_PRECISION"] = "f32"
+    got3 = sdpa_b200.attention(Q, K, V, mpi_rank=rank, mpi_size=world) if rank == 0 else \
+        sdpa_b200.attention(None, None, None, mpi_rank=rank, mpi_size=world)
+    if rank == 0:
+        np.testing.assert_allclose(got3, ref, rtol=0, atol=1e-5)
+    sdpa_b200.runtime_shutdown()
+    dist.barrier()
+    Path(out_dir, f"ok{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_one_process_per_gpu(sdpa, oracle, tmp_path):
+    _need_gpus(sdpa, 2)
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_rank_worker, args=(world, _free_port(), str(tmp_path), str(tmp_path / "nccl_id")), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
