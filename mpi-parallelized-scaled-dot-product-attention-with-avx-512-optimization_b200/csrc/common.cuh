@@ -89,6 +89,9 @@ sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, 
 sdpa_status launch_rescale_to_gmax(float* contrib, float* lsum, const float* tmax, const float* gmax,
                                    int rows, int dv, cudaStream_t stream);
 sdpa_status launch_normalize(float* contrib, const float* gsum, int rows, int dv, cudaStream_t stream);
+// out64[row][d] = reduced[row][d] / gsum[row]  (gsum == 0 -> 0): normalise + fp32->fp64 after the single SUM reduce
+sdpa_status launch_finalize_reduced(double* out64, const float* reduced, const float* gsum, int rows, int dv,
+                                    cudaStream_t stream);
 // Fused device-side exchange: root reads every shard's (contrib,tmax,lsum) through peer pointers.
 sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
                                const float* const* lsum_ptrs, int shards, int rows, int dv,

@@ -87,7 +87,7 @@ sdpa_ctx* get_ctx(int mpi_rank, int mpi_size)
     cfg.q_batch = env_int("SDPA_Q_BATCH", 0);
     cfg.kv_splits = env_int("SDPA_KV_SPLITS", 0);
     const char* mg = getenv("SDPA_MERGE");
-    cfg.merge = (mg && !strcmp(mg, "peer")) ? SDPA_MERGE_PEER : SDPA_MERGE_NCCL;
+    cfg.merge = (mg && !strcmp(mg, "peer")) ? SDPA_MERGE_PEER : (mg && !strcmp(mg, "nccl3")) ? SDPA_MERGE_NCCL : SDPA_MERGE_NCCL2;
     if (mpi_size <= 1) {
         cfg.num_local = env_int("SDPA_NGPUS", 1);
         cfg.first_device = env_int("SDPA_FIRST_DEVICE", 0);

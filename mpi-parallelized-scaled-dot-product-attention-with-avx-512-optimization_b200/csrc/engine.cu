@@ -350,6 +350,8 @@ static int pick_q_batch(const sdpa_ctx* ctx, int m)
         // On NVLink the per-batch exchange is ~tens of microseconds, so batches are made as large
         // as the buffers allow (8192 rows); the ping-pong overlap matters once m exceeds one batch (c4, c5).
         B = 8192;
+        // sharded: at least two batches so the exchange of batch i hides behind the kernel of batch i+1
+        if (ctx->world > 1 && m >= 2048 && m <= B) B = ((m + 1) / 2 + 127) & ~127;
     }
     if (B > m) B = m;
     if (B < 1) B = 1;
@@ -364,13 +366,13 @@ static sdpa_status reserve_batch_buffers(sdpa_ctx* ctx, Shard& s, int B, int spl
     for (int b = 0; b < 2; ++b) {
         SDPA_TRY(s.q64[b].reserve((size_t)B * dk * sizeof(double)));
         SDPA_TRY(s.qc[b].reserve((size_t)(Bpad + 128) * dk * esz));
-        SDPA_TRY(s.contrib[b].reserve((size_t)B * dv * sizeof(float)));
+        SDPA_TRY(s.contrib[b].reserve(((size_t)B * dv + B) * sizeof(float)));   // + lsum tail for the 2-collective merge
         SDPA_TRY(s.tmax[b].reserve((size_t)B * sizeof(float)));
         SDPA_TRY(s.lsum[b].reserve((size_t)B * sizeof(float)));
         SDPA_TRY(s.gmax[b].reserve((size_t)B * sizeof(float)));
         SDPA_TRY(s.gsum[b].reserve((size_t)B * sizeof(float)));
         if (root) {
-            SDPA_TRY(s.out32[b].reserve((size_t)B * dv * sizeof(float)));
+            SDPA_TRY(s.out32[b].reserve(((size_t)B * dv + B) * sizeof(float)));
             SDPA_TRY(s.out64[b].reserve((size_t)B * dv * sizeof(double)));
         }
     }
@@ -415,6 +417,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     const int L = (int)ctx->shards.size();
     const NcclApi* api = nullptr;
     const bool use_peer = world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && ctx->peer_ok && world == L;
+    const bool two_coll = ctx->cfg.merge != SDPA_MERGE_NCCL;   // NCCL2 (default) unless the reference's 3-collective form is asked for
     if ((world > 1 && !use_peer) || q_from_root) {
         api = nccl_api();
         if (!api) return SDPA_ERR_NCCL;
@@ -506,8 +509,9 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 if (single) {
                     SDPA_TRY(launch_merge_splits(part, bs, dv, final_dst, nullptr, nullptr, nullptr, false, s.s_compute));
                 } else {
+                    float* lsum_dst = (two_coll && !use_peer) ? s.contrib[b].as<float>() + (size_t)bs * dv : s.lsum[b].as<float>();
                     SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, s.contrib[b].as<float>(), s.tmax[b].as<float>(),
-                                                 s.lsum[b].as<float>(), false, s.s_compute));
+                                                 lsum_dst, false, s.s_compute));
                 }
                 SDPA_TRY(time_end(s, 2, s.s_compute));
                 ++all_launches;
@@ -543,25 +547,55 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
             }
         } else if (world > 1) {
-            // the reference's three collectives (mpi.c:342,354,380), one NCCL group per step
             for (int i = 0; i < L; ++i) {
                 Shard& s = ctx->shards[i];
                 SDPA_CUDA_TRY(cudaSetDevice(s.dev));
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
                 SDPA_TRY(time_begin(s, 2, s.s_comm));
             }
+            // (1) global max (mpi.c:342)
             SDPA_NCCL_TRY(api->GroupStart());
             for (int i = 0; i < L; ++i) {
                 Shard& s = ctx->shards[i];
                 SDPA_NCCL_TRY(api->AllReduce(s.tmax[b].p, s.gmax[b].p, (size_t)bs, ncclFloat32, ncclMax, s.comm, s.s_comm));
             }
             SDPA_NCCL_TRY(api->GroupEnd());
+            if (two_coll) {
+                // (2) scale contrib and lsum to the global max (mpi.c:346-351); lsum lives right behind contrib,
+                // so ONE reduce(SUM) carries both (mpi.c:354 + mpi.c:380); normalisation (mpi.c:358-362) and the
+                // fp64 cast (mpi.c:373) run once on the root after it.
+                for (int i = 0; i < L; ++i) {
+                    Shard& s = ctx->shards[i];
+                    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+                    float* lsum_tail = s.contrib[b].as<float>() + (size_t)bs * dv;
+                    SDPA_TRY(launch_rescale_to_gmax(s.contrib[b].as<float>(), lsum_tail, s.tmax[b].as<float>(),
+                                                    s.gmax[b].as<float>(), bs, dv, s.s_comm));
+                }
+                SDPA_NCCL_TRY(api->GroupStart());
+                for (int i = 0; i < L; ++i) {
+                    Shard& s = ctx->shards[i];
+                    void* recv = s.grank == 0 ? s.out32[b].p : nullptr;
+                    SDPA_NCCL_TRY(api->Reduce(s.contrib[b].p, recv, (size_t)bs * dv + bs, ncclFloat32, ncclSum, 0, s.comm, s.s_comm));
+                }
+                SDPA_NCCL_TRY(api->GroupEnd());
+                for (int i = 0; i < L; ++i) {
+                    Shard& s = ctx->shards[i];
+                    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+                    if (s.grank == 0) {
+                        double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+                        SDPA_TRY(launch_finalize_reduced(dst, s.out32[b].as<float>(), s.out32[b].as<float>() + (size_t)bs * dv, bs, dv, s.s_comm));
+                    }
+                    SDPA_TRY(time_end(s, 2, s.s_comm));
+                    SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
+                    if (s.grank != 0) SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+                }
+            } else {
+            // the reference's three collectives (mpi.c:342,354,380), one NCCL group per step
             for (int i = 0; i < L; ++i) {
                 Shard& s = ctx->shards[i];
                 SDPA_CUDA_TRY(cudaSetDevice(s.dev));
                 SDPA_TRY(launch_rescale_to_gmax(s.contrib[b].as<float>(), s.lsum[b].as<float>(), s.tmax[b].as<float>(),
                                                 s.gmax[b].as<float>(), bs, dv, s.s_comm));
-                ++all_launches;
             }
             SDPA_NCCL_TRY(api->GroupStart());
             for (int i = 0; i < L; ++i) {
@@ -573,7 +607,6 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 Shard& s = ctx->shards[i];
                 SDPA_CUDA_TRY(cudaSetDevice(s.dev));
                 SDPA_TRY(launch_normalize(s.contrib[b].as<float>(), s.gsum[b].as<float>(), bs, dv, s.s_comm));
-                ++all_launches;
             }
             SDPA_NCCL_TRY(api->GroupStart());
             for (int i = 0; i < L; ++i) {
@@ -588,11 +621,11 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 if (s.grank == 0) {
                     double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
                     SDPA_TRY(launch_cvt_f2d(dst, s.out32[b].as<float>(), (size_t)bs * dv, s.s_comm));  // mpi.c:373
-                    ++all_launches;
                 }
                 SDPA_TRY(time_end(s, 2, s.s_comm));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
                 if (s.grank != 0) SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+            }
             }
         }
 
@@ -798,7 +831,7 @@ void sdpa_config_init(sdpa_config* cfg)
     if (!cfg) return;
     memset(cfg, 0, sizeof(*cfg));
     cfg->precision = SDPA_PREC_AUTO;
-    cfg->merge = SDPA_MERGE_NCCL;
+    cfg->merge = SDPA_MERGE_NCCL2;
     cfg->num_local = 1;
 }
 

@@ -119,7 +119,31 @@ normalize_kernel(float* __restrict__ contrib, const float* __restrict__ gsum, in
     for (int d = lane; d < dv; d += 32) contrib[(size_t)row * dv + d] *= inv;
 }
 
+// out64 = reduced / gsum  (mpi.c:358-362 applied after the reduce instead of before it, plus cvt_f2d mpi.c:373)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+finalize_reduced_kernel(double* __restrict__ out64, const float* __restrict__ reduced, const float* __restrict__ gsum,
+                        int rows, int dv)
+{
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    if (row >= rows) return;
+    const float g = gsum[row];
+    const float inv = (g == 0.f) ? 0.f : 1.f / g;
+    for (int d = lane; d < dv; d += 32) out64[(size_t)row * dv + d] = (double)(reduced[(size_t)row * dv + d] * inv);
+}
+
 }  // namespace
+
+sdpa_status launch_finalize_reduced(double* out64, const float* reduced, const float* gsum, int rows, int dv,
+                                    cudaStream_t stream)
+{
+    if (rows <= 0) return SDPA_OK;
+    finalize_reduced_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(out64, reduced, gsum, rows, dv);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
 
 sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, float* contrib,
                                 float* tmax_out, float* lsum_out, bool natural_log_max,

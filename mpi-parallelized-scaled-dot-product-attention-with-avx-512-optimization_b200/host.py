@@ -29,7 +29,8 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libsdpa_b200.so"
 
 PREC_AUTO, PREC_F32, PREC_BF16 = 0, 1, 2
-MERGE_NCCL, MERGE_PEER = 0, 1
+MERGE_NCCL, MERGE_PEER, MERGE_NCCL2 = 0, 1, 2
+_MERGE = {"nccl": MERGE_NCCL2, "nccl2": MERGE_NCCL2, "nccl3": MERGE_NCCL, "peer": MERGE_PEER}
 _PREC = {"auto": PREC_AUTO, "f32": PREC_F32, "fp32": PREC_F32, "bf16": PREC_BF16}
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -203,7 +204,7 @@ def set_bootstrap_id(uid: bytes | None) -> None:
 class Context:
     """One process' share of the K/V shards (``num_local`` GPUs out of ``world_size``)."""
 
-    def __init__(self, precision: str | int = "auto", q_batch: int = 0, kv_splits: int = 0, merge: str = "nccl",
+    def __init__(self, precision: str | int = "auto", q_batch: int = 0, kv_splits: int = 0, merge: str = "nccl2",
                  num_local: int = 1, first_device: int = 0, world_size: int = 0, rank_base: int = 0,
                  nccl_id: bytes | None = None):
         L = lib()
@@ -211,7 +212,7 @@ class Context:
         L.sdpa_config_init(ctypes.byref(cfg))
         cfg.precision = _PREC[precision] if isinstance(precision, str) else int(precision)
         cfg.q_batch, cfg.kv_splits = int(q_batch), int(kv_splits)
-        cfg.merge = MERGE_PEER if merge == "peer" else MERGE_NCCL
+        cfg.merge = _MERGE[merge]
         cfg.num_local, cfg.first_device = int(num_local), int(first_device)
         cfg.world_size, cfg.rank_base = int(world_size), int(rank_base)
         self.num_local = int(num_local)

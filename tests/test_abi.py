@@ -29,7 +29,7 @@ def test_config_struct_layout(sdpa):
     assert ctypes.sizeof(sdpa.Config) == 16 * 4
     cfg = sdpa.Config()
     sdpa.lib().sdpa_config_init(ctypes.byref(cfg))
-    assert cfg.precision == sdpa.PREC_AUTO and cfg.num_local == 1 and cfg.merge == sdpa.MERGE_NCCL
+    assert cfg.precision == sdpa.PREC_AUTO and cfg.num_local == 1 and cfg.merge == sdpa.MERGE_NCCL2
 
 
 def test_owner_map_matches_reference_formula(sdpa, oracle):

@@ -19,7 +19,7 @@ def _need_gpus(sdpa, n):
         pytest.skip(f"needs {n} GPUs, {sdpa.device_count()} visible")
 
 
-@pytest.mark.parametrize("merge", ["nccl", "peer"])
+@pytest.mark.parametrize("merge", ["nccl2", "nccl3", "peer"])
 @pytest.mark.parametrize("prec,m,n,d,atol", [("f32", 300, 1001, 64, 1e-5), ("f32", 129, 3, 80, 1e-5),
                                              ("bf16", 700, 5000, 128, 1e-2), ("bf16", 9000, 4100, 128, 1e-2)])
 def test_single_process_two_gpus(sdpa, oracle, merge, prec, m, n, d, atol):
@@ -37,7 +37,7 @@ def test_single_process_empty_shard(sdpa, oracle):
     _need_gpus(sdpa, 2)
     Q, K, V = oracle.make_inputs(50, 1, 32, 32, seed=5)   # n=1 < 2 shards: GPU 1 owns nothing (lmax=-inf, mpi.c:172)
     ref = oracle.attention_f64(Q, K, V)
-    for merge in ("nccl", "peer"):
+    for merge in ("nccl2", "nccl3", "peer"):
         with sdpa.Context(precision="f32", num_local=2, merge=merge) as ctx:
             ctx.load_kv_host_full(K, V)
             got = ctx.attention_host(Q)
