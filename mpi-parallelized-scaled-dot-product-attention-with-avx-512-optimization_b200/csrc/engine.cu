@@ -350,8 +350,9 @@ static int pick_q_batch(const sdpa_ctx* ctx, int m)
         // On NVLink the per-batch exchange is ~tens of microseconds, so batches are made as large
         // as the buffers allow (8192 rows); the ping-pong overlap matters once m exceeds one batch (c4, c5).
         B = 8192;
-        // sharded: at least two batches so the exchange of batch i hides behind the kernel of batch i+1
-        if (ctx->world > 1 && m >= 2048 && m <= B) B = ((m + 1) / 2 + 127) & ~127;
+        // (Measured on 2 GPUs: halving the batch to overlap the exchange with the next kernel does not pay --
+        // the fused kernel holds every SM, so the NCCL kernels queue behind it anyway, and two half-size
+        // launches lose more in the tail than the overlap wins.  m > 8192 still ping-pongs, as c4/c5 do.)
     }
     if (B > m) B = m;
     if (B < 1) B = 1;
