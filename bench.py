@@ -259,7 +259,8 @@ def run_ours(args) -> None:
     Rd = torch.zeros(m, DV, dtype=torch.float64, device="cuda") if rank == 0 else None
 
     if world > 1:
-        ctx = parallel.bootstrap_context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, local_rank=local_rank)
+        ctx = parallel.bootstrap_context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, local_rank=local_rank,
+                                         merge=args.merge)
     else:
         ctx = sdpa_b200.Context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, first_device=local_rank)
 
@@ -360,7 +361,9 @@ def run_ours(args) -> None:
             "q_rows_per_s": m * K / (ms_dev * 1e-3),
             "config": {"workload": desc, "m": m, "n": n, "n_per_gpu": n_local, "dk": DK, "dv": DV,
                        "parallelism": f"kv-shard x{world} (owner_count/owner_disp), Q replicated",
-                       "merge": "none" if world == 1 else "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)",
+                       "merge": "none" if world == 1 else {"peer": "device-side exchange: root merge kernel reads shard states over NVLink (CUDA IPC) behind epoch flags",
+                                                           "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
+                                                           "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],
                        "l2": "inputs_larger_than_l2 (fp64 Q+K+V per GPU = %d MiB)" % ((n_local * (DK + DV) + m * DK) * 8 >> 20),
                        "kernel": kernel_name},
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -404,6 +407,8 @@ def main() -> None:
     ap.add_argument("--n-per-gpu", type=int, default=0)
     ap.add_argument("--q-batch", type=int, default=0)
     ap.add_argument("--kv-splits", type=int, default=0)
+    ap.add_argument("--merge", choices=["peer", "nccl2", "nccl3"], default="peer",
+                    help="cross-GPU merge: peer = device-side exchange over CUDA-IPC peer memory (default); nccl2/nccl3 = NCCL collectives")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -97,4 +97,20 @@ sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* co
                                const float* const* lsum_ptrs, int shards, int rows, int dv,
                                double* out64, cudaStream_t stream);
 
+
+// ---- device-side exchange across processes (CUDA IPC peer memory + flags in device memory) ----------
+// A flag holds the epoch (global batch counter) of the last completed step.
+sdpa_status launch_signal_flag(unsigned int* flag, unsigned int epoch, cudaStream_t stream);       // release-store after prior work
+sdpa_status launch_wait_flag(const unsigned int* flag, unsigned int epoch, cudaStream_t stream);   // spin until *flag >= epoch
+struct PeerSync {
+    const unsigned int* ready[64];   // per shard: its "state of epoch e is complete" flag (local or IPC-mapped)
+    unsigned int* consumed;          // root-local: set to epoch once every block has merged (peers poll it before reuse)
+    unsigned int* block_counter;     // root-local scratch
+    unsigned int epoch;
+};
+// Root GPU: wait for every shard's flag, merge their (contrib,tmax,lsum) read through peer pointers, write fp64.
+sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
+                                      const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
+                                      const PeerSync& sync, cudaStream_t stream);
+
 }  // namespace sdpa

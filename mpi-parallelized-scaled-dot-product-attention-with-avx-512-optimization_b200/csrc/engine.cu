@@ -77,6 +77,7 @@ const NcclApi* nccl_api()
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
     api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
     api.Send = (decltype(api.Send))sym("ncclSend");
     api.Recv = (decltype(api.Recv))sym("ncclRecv");
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
@@ -176,6 +177,19 @@ struct sdpa_ctx {
     bool peer_ok = false;
     float last_timing[6] = {0, 0, 0, 0, 0, 0};
     const char* last_kernel = "none";
+    // device-side exchange across processes (one GPU per process): state buffers + flags shared through CUDA IPC
+    struct Ipc {
+        bool ready = false;
+        int cap_rows = 0, dv = 0;
+        DevBuf xbuf[2];                 // [contrib rows*dv | tmax rows | lsum rows], one per ping-pong slot
+        DevBuf flags;                   // uint32: ready[2], consumed[2], block_counter[2]
+        std::vector<void*> peer_x[2];   // root: every shard's xbuf (own pointer for itself)
+        std::vector<unsigned int*> peer_flags;  // root: every shard's flag block
+        unsigned int* root_flags = nullptr;     // non-root: the root's flag block
+        std::vector<void*> opened;      // IPC mappings to close
+        unsigned int epoch = 0;         // global batch counter, identical on every rank
+        unsigned int slot_epoch[2] = {0, 0};
+    } ipc;
     bool has_root() const { return rank_base == 0; }
 };
 
@@ -393,6 +407,97 @@ static sdpa_status run_fused(sdpa_ctx* ctx, Shard& s, int slot, int rows, int sp
                            ctx->dv, splits, part, direct_out, s.s_compute);
 }
 
+// ---------------------------------------------------------------------------
+// Device-side exchange for one process per GPU: every rank exports its per-slot state buffer and flag
+// block with cudaIpcGetMemHandle; the handles are all-gathered over the (already bootstrapped) NCCL
+// communicator; the root maps everybody's buffers, the others map the root's flags.  After this no
+// collective runs on the data path: shards publish an epoch flag, the root's merge kernel polls the
+// flags and reads the states over NVLink, and publishes "consumed" for buffer reuse.
+// ---------------------------------------------------------------------------
+static void ipc_close(sdpa_ctx* ctx)
+{
+    for (void* p : ctx->ipc.opened) cudaIpcCloseMemHandle(p);
+    ctx->ipc.opened.clear();
+    ctx->ipc.peer_x[0].clear();
+    ctx->ipc.peer_x[1].clear();
+    ctx->ipc.peer_flags.clear();
+    ctx->ipc.root_flags = nullptr;
+    ctx->ipc.ready = false;
+}
+
+static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
+{
+    sdpa_ctx::Ipc& x = ctx->ipc;
+    if (x.ready && x.cap_rows >= rows_cap && x.dv == dv) return SDPA_OK;
+    const NcclApi* api = nccl_api();
+    if (!api) return SDPA_ERR_NCCL;
+    Shard& s = ctx->shards[0];
+    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    SDPA_CUDA_TRY(cudaDeviceSynchronize());
+    ipc_close(ctx);
+    // every rank re-allocates together (the decision depends only on arguments all ranks share)
+    const size_t xbytes = ((size_t)rows_cap * dv + 2 * (size_t)rows_cap) * sizeof(float);
+    for (int b = 0; b < 2; ++b) {
+        x.xbuf[b].release();
+        SDPA_TRY(x.xbuf[b].reserve(xbytes));
+    }
+    if (!x.flags.p) {
+        SDPA_TRY(x.flags.reserve(256));
+        SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 256));
+        x.epoch = 0;
+        x.slot_epoch[0] = x.slot_epoch[1] = 0;
+    }
+    struct Handles { cudaIpcMemHandle_t x0, x1, fl; };
+    Handles mine;
+    SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.x0, x.xbuf[0].p));
+    SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.x1, x.xbuf[1].p));
+    SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.fl, x.flags.p));
+    const int world = ctx->world;
+    DevBuf dsend, drecv;
+    SDPA_TRY(dsend.reserve(sizeof(Handles)));
+    SDPA_TRY(drecv.reserve(sizeof(Handles) * world));
+    SDPA_CUDA_TRY(cudaMemcpyAsync(dsend.p, &mine, sizeof(Handles), cudaMemcpyHostToDevice, s.s_comm));
+    SDPA_NCCL_TRY(api->AllGather(dsend.p, drecv.p, sizeof(Handles), ncclUint8, s.comm, s.s_comm));
+    std::vector<Handles> all(world);
+    SDPA_CUDA_TRY(cudaMemcpyAsync(all.data(), drecv.p, sizeof(Handles) * world, cudaMemcpyDeviceToHost, s.s_comm));
+    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_comm));
+    dsend.release();
+    drecv.release();
+    auto open = [&](const cudaIpcMemHandle_t& h, void** out) -> sdpa_status {
+        SDPA_CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+        x.opened.push_back(*out);
+        return SDPA_OK;
+    };
+    if (s.grank == 0) {
+        x.peer_x[0].assign(world, nullptr);
+        x.peer_x[1].assign(world, nullptr);
+        x.peer_flags.assign(world, nullptr);
+        for (int r = 0; r < world; ++r) {
+            if (r == 0) {
+                x.peer_x[0][r] = x.xbuf[0].p;
+                x.peer_x[1][r] = x.xbuf[1].p;
+                x.peer_flags[r] = x.flags.as<unsigned int>();
+                continue;
+            }
+            void* p = nullptr;
+            SDPA_TRY(open(all[r].x0, &p));
+            x.peer_x[0][r] = p;
+            SDPA_TRY(open(all[r].x1, &p));
+            x.peer_x[1][r] = p;
+            SDPA_TRY(open(all[r].fl, &p));
+            x.peer_flags[r] = reinterpret_cast<unsigned int*>(p);
+        }
+    } else {
+        void* p = nullptr;
+        SDPA_TRY(open(all[0].fl, &p));
+        x.root_flags = reinterpret_cast<unsigned int*>(p);
+    }
+    x.cap_rows = rows_cap;
+    x.dv = dv;
+    x.ready = true;
+    return SDPA_OK;
+}
+
 static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const double* const* Q_dev,
                                   double* result, bool result_on_device, int m, bool q_from_root = false)
 {
@@ -418,8 +523,9 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     const int L = (int)ctx->shards.size();
     const NcclApi* api = nullptr;
     const bool use_peer = world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && ctx->peer_ok && world == L;
+    const bool use_ipc = world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && L == 1 && world > L;   // one GPU per process
     const bool two_coll = ctx->cfg.merge != SDPA_MERGE_NCCL;   // NCCL2 (default) unless the reference's 3-collective form is asked for
-    if ((world > 1 && !use_peer) || q_from_root) {
+    if ((world > 1 && !use_peer && !use_ipc) || q_from_root) {
         api = nccl_api();
         if (!api) return SDPA_ERR_NCCL;
     }
@@ -454,6 +560,8 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_begin, 0));
         SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, s.ev_begin, 0));
     }
+
+    if (use_ipc) SDPA_TRY(ipc_setup(ctx, std::max(B, 8192), dv));
 
     int fused_launches = 0, all_launches = 0;
     const unsigned long long launches_before = launch_count();
@@ -510,9 +618,23 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 if (single) {
                     SDPA_TRY(launch_merge_splits(part, bs, dv, final_dst, nullptr, nullptr, nullptr, false, s.s_compute));
                 } else {
+                    if (use_ipc) {
+                        // publish this shard's state in its IPC-shared slot, then raise the epoch flag
+                        sdpa_ctx::Ipc& x = ctx->ipc;
+                        float* xc = x.xbuf[b].as<float>();
+                        float* xt = xc + (size_t)x.cap_rows * dv;
+                        float* xl = xt + x.cap_rows;
+                        if (i == 0) ++x.epoch;
+                        if (s.grank != 0 && x.slot_epoch[b] != 0)   // the root must have consumed the slot's previous content
+                            SDPA_TRY(launch_wait_flag(x.root_flags + 2 + b, x.slot_epoch[b], s.s_compute));
+                        SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, xc, xt, xl, false, s.s_compute));
+                        SDPA_TRY(launch_signal_flag(x.flags.as<unsigned int>() + b, x.epoch, s.s_compute));
+                        x.slot_epoch[b] = x.epoch;
+                    } else {
                     float* lsum_dst = (two_coll && !use_peer) ? s.contrib[b].as<float>() + (size_t)bs * dv : s.lsum[b].as<float>();
                     SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, s.contrib[b].as<float>(), s.tmax[b].as<float>(),
                                                  lsum_dst, false, s.s_compute));
+                    }
                 }
                 SDPA_TRY(time_end(s, 2, s.s_compute));
                 ++all_launches;
@@ -521,7 +643,37 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         }
 
         // ---- cross-shard merge ----------------------------------------------------------------
-        if (world > 1 && use_peer) {
+        if (use_ipc) {
+            Shard& s = ctx->shards[0];
+            sdpa_ctx::Ipc& x = ctx->ipc;
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            if (s.grank == 0) {
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
+                const float* cp[64];
+                const float* tp[64];
+                const float* lp[64];
+                PeerSync sync;
+                for (int r = 0; r < world; ++r) {
+                    const float* base = reinterpret_cast<const float*>(x.peer_x[b][r]);
+                    cp[r] = base;
+                    tp[r] = base + (size_t)x.cap_rows * dv;
+                    lp[r] = tp[r] + x.cap_rows;
+                    sync.ready[r] = x.peer_flags[r] + b;
+                }
+                sync.consumed = x.flags.as<unsigned int>() + 2 + b;
+                sync.block_counter = x.flags.as<unsigned int>() + 4 + b;
+                sync.epoch = x.epoch;
+                double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+                SDPA_TRY(time_begin(s, 2, s.s_comm));
+                SDPA_TRY(launch_merge_peers_synced(cp, tp, lp, world, bs, dv, dst, sync, s.s_comm));
+                SDPA_TRY(time_end(s, 2, s.s_comm));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
+            } else {
+                // nothing to wait for on the host: slot reuse is guarded on the device by the root's "consumed" flag
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_compute));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_compute));
+            }
+        } else if (world > 1 && use_peer) {
             // fused device-side exchange: the root GPU reads every shard's state over NVLink
             Shard& r = ctx->shards[0];
             SDPA_CUDA_TRY(cudaSetDevice(r.dev));
@@ -642,6 +794,15 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                               cudaMemcpyDeviceToHost, s.s_out));
             SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_out));
         }
+    }
+
+    if (use_ipc && ctx->shards[0].grank != 0) {
+        // do not return (and possibly free or overwrite the slots) before the root has read them
+        Shard& s = ctx->shards[0];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        for (int b = 0; b < 2; ++b)
+            if (ctx->ipc.slot_epoch[b] != 0)
+                SDPA_TRY(launch_wait_flag(ctx->ipc.root_flags + 2 + b, ctx->ipc.slot_epoch[b], s.s_compute));
     }
 
     // ---- join: every stream back into the compute stream, then wait ----------------------------
@@ -945,6 +1106,14 @@ sdpa_status sdpa_ctx_destroy(sdpa_ctx* ctx)
     const NcclApi* api = nullptr;
     for (Shard& s : ctx->shards)
         if (s.comm) api = nccl_api();
+    if (!ctx->shards.empty()) {
+        cudaSetDevice(ctx->shards[0].dev);
+        cudaDeviceSynchronize();
+        ipc_close(ctx);
+        ctx->ipc.xbuf[0].release();
+        ctx->ipc.xbuf[1].release();
+        ctx->ipc.flags.release();
+    }
     for (Shard& s : ctx->shards) shard_destroy(s, api);
     delete ctx;
     return SDPA_OK;

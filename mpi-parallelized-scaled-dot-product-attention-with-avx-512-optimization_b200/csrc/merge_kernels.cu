@@ -26,11 +26,78 @@ struct StatePtrs {
     const float* lsum[64];
 };
 
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Bounded spin (a protocol bug traps instead of hanging the GPU).  Epochs only grow; the signed
+// difference tolerates wrap-around.
+__device__ __forceinline__ void spin_until(const unsigned int* flag, unsigned int epoch, int tag)
+{
+    const long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+        __nanosleep(200);
+        if (clock64() - t0 > 8000000000LL) {
+            printf("sdpa_b200: peer flag timeout tag=%d block=%d want=%u have=%u\n", tag, blockIdx.x, epoch, ld_acquire_sys(flag));
+            __trap();
+        }
+    }
+}
+
+__global__ void signal_flag_kernel(unsigned int* flag, unsigned int epoch)
+{
+    __threadfence_system();   // everything this GPU wrote before (earlier kernels on the stream) is visible system-wide
+    st_release_sys(flag, epoch);
+}
+__global__ void wait_flag_kernel(const unsigned int* flag, unsigned int epoch) { spin_until(flag, epoch, 1); }
+
+template <bool FINAL>
+__device__ __forceinline__ void merge_rows(const struct StatePtrs& st, int count, int rows, int dv, double* __restrict__ out64,
+                                           float* __restrict__ contrib, float* __restrict__ tmax_out,
+                                           float* __restrict__ lsum_out, float max_unit, bool vec_ok);
+
+struct SyncArgs {
+    const unsigned int* ready[64];
+    unsigned int* consumed;
+    unsigned int* block_counter;
+    unsigned int epoch;
+    int enabled;
+};
+
 template <bool FINAL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict__ out64,
                     float* __restrict__ contrib, float* __restrict__ tmax_out,
-                    float* __restrict__ lsum_out, float max_unit, bool vec_ok)
+                    float* __restrict__ lsum_out, float max_unit, bool vec_ok, const SyncArgs sync)
+{
+    if (sync.enabled) {
+        // fused exchange: the states live on other GPUs; wait until each of them has published this epoch
+        if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.epoch, 2);
+        __syncthreads();
+    }
+    merge_rows<FINAL>(st, count, rows, dv, out64, contrib, tmax_out, lsum_out, max_unit, vec_ok);
+    if (sync.enabled) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(sync.block_counter, 1u) == gridDim.x - 1) {
+                *sync.block_counter = 0;
+                st_release_sys(sync.consumed, sync.epoch);   // every block has read the peers' buffers: they may be reused
+            }
+        }
+    }
+}
+
+template <bool FINAL>
+__device__ __forceinline__ void merge_rows(const StatePtrs& st, int count, int rows, int dv, double* __restrict__ out64,
+                                           float* __restrict__ contrib, float* __restrict__ tmax_out,
+                                           float* __restrict__ lsum_out, float max_unit, bool vec_ok)
 {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -165,10 +232,10 @@ sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, 
     for (int s = 0; s < part.splits; ++s) vec_ok = vec_ok && al16(st.o[s]);
     if (out64 != nullptr)
         merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-            st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f, vec_ok);
+            st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f, vec_ok, SyncArgs{});
     else
         merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-            st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, natural_log_max ? kLn2 : 1.f, vec_ok);
+            st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, natural_log_max ? kLn2 : 1.f, vec_ok, SyncArgs{});
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
@@ -193,7 +260,54 @@ sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* co
     bool vec_ok = al16(out64);
     for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
     merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr,
-                                                                         nullptr, nullptr, 1.f, vec_ok);
+                                                                         nullptr, nullptr, 1.f, vec_ok, SyncArgs{});
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
+                                      const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
+                                      const PeerSync& sync, cudaStream_t stream)
+{
+    if (rows <= 0) return SDPA_OK;
+    if (shards < 1 || shards > 64) {
+        set_error("peer merge supports 1..64 shards (got %d)", shards);
+        return SDPA_ERR_INVALID;
+    }
+    StatePtrs st;
+    SyncArgs sa{};
+    for (int s = 0; s < shards; ++s) {
+        st.o[s] = contrib_ptrs[s];
+        st.tmax[s] = tmax_ptrs[s];
+        st.lsum[s] = lsum_ptrs[s];
+        sa.ready[s] = sync.ready[s];
+    }
+    sa.consumed = sync.consumed;
+    sa.block_counter = sync.block_counter;
+    sa.epoch = sync.epoch;
+    sa.enabled = 1;
+    const int blocks = ceil_div(rows, kWarpsPerBlock);
+    bool vec_ok = al16(out64);
+    for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
+    merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
+                                                                         nullptr, 1.f, vec_ok, sa);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_signal_flag(unsigned int* flag, unsigned int epoch, cudaStream_t stream)
+{
+    signal_flag_kernel<<<1, 1, 0, stream>>>(flag, epoch);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_wait_flag(const unsigned int* flag, unsigned int epoch, cudaStream_t stream)
+{
+    wait_flag_kernel<<<1, 1, 0, stream>>>(flag, epoch);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

@@ -32,7 +32,8 @@ def shard_rows(n: int, world: int, rank: int) -> tuple[int, int]:
     return host.owner_disp(n, world, rank), host.owner_count(n, world, rank)
 
 
-def bootstrap_context(precision="auto", q_batch: int = 0, kv_splits: int = 0, local_rank: int | None = None, group=None):
+def bootstrap_context(precision="auto", q_batch: int = 0, kv_splits: int = 0, local_rank: int | None = None, group=None,
+                      merge: str = "nccl2"):
     """Create the per-rank :class:`~host.Context` of a one-GPU-per-process job: rank 0 draws a
     ncclUniqueId, torch.distributed broadcasts it, every rank builds its communicator."""
     import os
@@ -44,7 +45,7 @@ def bootstrap_context(precision="auto", q_batch: int = 0, kv_splits: int = 0, lo
     if world > 1:
         uid = broadcast_bytes(host.get_unique_id() if rank == 0 else None, 128, src=0, group=group)
     return host.Context(precision=precision, q_batch=q_batch, kv_splits=kv_splits, num_local=1, first_device=local_rank,
-                        world_size=world, rank_base=rank, nccl_id=uid)
+                        world_size=world, rank_base=rank, nccl_id=uid, merge=merge)
 
 
 def max_over_ranks(value: float, group=None) -> float:
