@@ -347,7 +347,7 @@ constexpr int TRACE_ITERS = 24, TRACE_EVENTS = 8, TRACE_ROLES = 6;
 // SAFE = the always-correct variant (row max agreed every tile, lazy rescale).  The default launch is
 // the fast variant (reference fixed after the first tile) followed by the SAFE variant, which exits
 // immediately unless the fast one raised the overflow guard.  POLY: see kDefaultPoly.
-template <bool TRACE, bool SAFE, int POLY>
+template <bool TRACE, bool SAFE, int POLY, bool CHUNKED = true>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                  const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
@@ -585,6 +585,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 int keys_left = 64;
                 if constexpr (MASKED) keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;   // valid keys in my half
 
+                if constexpr (CHUNKED) {
                 SDPA_TMEM_LD16(s_addr, sr);
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
@@ -607,6 +608,31 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                     uint32_t pr[8];
                     exp_chunk(sv, neg_ref2, acc0, acc1, pr);
                     SDPA_TMEM_ST8(p_addr + 8 * ch, pr);   // columns [8ch, 8ch+8) of my region: S values already in registers
+                }
+                } else {
+                    // whole half row at once: one wait, no scheduling barriers between the 16-key groups
+                    SDPA_TMEM_LD32(s_addr, sr);
+                    SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
+                    tmem_wait_ld();
+                    if (quad == 0) stamp(sw >> 2, j, 1);
+                    if constexpr (MASKED) {
+#pragma unroll
+                        for (int c = 0; c < 64; ++c)
+                            if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
+                    }
+#pragma unroll
+                    for (int c = 0; c < 64; c += 8) {
+                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1])));
+                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
+                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
+                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
+                    }
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t pr[8];
+                        exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr);
+                        SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
+                    }
                 }
                 if (quad == 0) stamp(sw >> 2, j, 2);
 
@@ -879,6 +905,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     const char* env_poly = getenv("SDPA_UMMA_POLY");
     int poly = env_poly ? atoi(env_poly) : kDefaultPoly;
     if (poly != 0 && poly != 4 && poly != 8) poly = kDefaultPoly;
+    const char* env_chunk = getenv("SDPA_UMMA_CHUNK");
+    const bool chunked = !(env_chunk && *env_chunk == '0');
     const char* env_safe = getenv("SDPA_UMMA_SAFE");
     const bool force_safe = env_safe && *env_safe == '1';
     if (dev < 64 && !plan->attr_set[dev]) {
@@ -887,6 +915,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true, false, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         plan->attr_set[dev] = true;
     }
@@ -937,7 +967,9 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
         prm.epoch = 0xffffffffu;
     } else {
-        if (poly == 0) attn_umma_kernel<false, false, 0><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        if (!chunked && poly == 0) attn_umma_kernel<false, false, 0, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (!chunked) attn_umma_kernel<false, false, 4, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (poly == 0) attn_umma_kernel<false, false, 0><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else if (poly == 8) attn_umma_kernel<false, false, 8><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else attn_umma_kernel<false, false, 4><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
