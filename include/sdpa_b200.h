@@ -115,7 +115,8 @@ sdpa_status sdpa_set_bootstrap_id(const void* id128);
 /* K/V shard upload + cast (mpi.c:213-266: cvt_d2f of K,V then Bcast/Scatterv).
  * K_shards[i] / V_shards[i] are the rows owned by local GPU i
  * (n_local[i] x dk, n_local[i] x dv, fp64 row-major).  *_host: host memory
- * (pinned or pageable); *_device: already resident on that GPU. */
+ * (pinned or pageable), blocking; *_device: already resident on that GPU, and stream-ordered: the
+ * casts are queued and the arrays must stay untouched until the next sdpa_attention_* call returns. */
 sdpa_status sdpa_load_kv_host(sdpa_ctx* ctx, const double* const* K_shards,
                               const double* const* V_shards, const int* n_local, int dk, int dv);
 sdpa_status sdpa_load_kv_device(sdpa_ctx* ctx, const double* const* K_shards,

@@ -349,10 +349,14 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
             SDPA_TRY(umma_plan_bind_kv(s.plan, s.Kc.as<__nv_bfloat16>(), s.Vc.as<__nv_bfloat16>(), s.n_local, dk, dv));
         }
     }
-    for (Shard& s : ctx->shards) {
-        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
-        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
-    }
+    // Host sources: block until the uploads have been consumed (the caller may reuse its arrays).
+    // Device sources: stream-ordered -- the casts are queued on the compute stream that the next
+    // sdpa_attention_* call uses, so no host round trip is spent here (see include/sdpa_b200.h).
+    if (!on_device)
+        for (Shard& s : ctx->shards) {
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+        }
     return SDPA_OK;
 }
 
