@@ -55,7 +55,9 @@ def load_peaks():
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (one persistent
+    `nvidia-smi -lms 20` process; a 20-step region lasts only a few milliseconds, so bench.py keeps
+    the same load running under the sampler for about a second more and says so in `clocks.window`)."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
@@ -63,48 +65,57 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
-        self._stop = threading.Event()
+        self.proc = None
         self._thr = None
 
-    def _loop(self):
-        exe = shutil.which("nvidia-smi")
-        if not exe:
-            return
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run([exe, f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+    def _reader(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
 
     def __enter__(self):
-        self._thr = threading.Thread(target=self._loop, daemon=True)
-        self._thr.start()
+        exe = shutil.which("nvidia-smi")
+        if exe:
+            try:
+                self.proc = subprocess.Popen([exe, f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                              "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self._thr = threading.Thread(target=self._reader, daemon=True)
+                self._thr.start()
+            except Exception:
+                self.proc = None
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         if self._thr:
-            self._thr.join(timeout=6)
+            self._thr.join(timeout=5)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm, mx, power, reasons = [], 0, [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
+                clk, pw = float(r[0]), float(r[2])
                 mx = max(mx, float(r[1]))
             except Exception:
                 continue
+            if pw < 300.0:      # idle sample (before the first launch / after the last): not "under load"
+                continue
+            sm.append(clk)
+            power.append(pw)
             for name, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(power) if power else None,
+                "window": "timed region + ~1 s of the same steps (samples with power draw >= 300 W)"}
 
 
 # --------------------------------------------------------------------------- reference / CPU baseline
@@ -305,8 +316,8 @@ def run_ours(args) -> None:
     launches0 = sdpa_b200.launch_count()
     with ClockSampler(local_rank) as clk:
         ms_dev = timed(step_device, K, collect)
-        # keep the sampler alive for at least a few samples on very short runs
-        t_end = time.time() + max(0.0, 0.35 - ms_dev / 1e3)
+        # the timed region is a few milliseconds: keep the identical load running so the sampler sees it
+        t_end = time.time() + 1.0
         while time.time() < t_end:
             step_device()
     launches = sdpa_b200.launch_count() - launches0

@@ -19,6 +19,8 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
+
 namespace sdpa {
 
 namespace {
@@ -290,15 +292,24 @@ bool attn_f32_supported(int dk, int dv) { return dk >= 1 && dv >= 1 && dk <= 256
 
 int attn_f32_pick_splits(int rows, int n, int sm_count)
 {
-    // Aim for >= 2 CTAs per SM over the whole grid, but keep >= 4 key tiles per split.
+    // Fewest splits (>= 4 key tiles each, <= 64) whose grid row_blocks x splits fills whole waves of
+    // 2 resident CTAs per SM best; every extra split costs rows*dv*8 bytes of partial traffic.
     const int row_blocks = ceil_div(rows, BM);
     const int tiles = ceil_div(n, BN);
-    int splits = ceil_div(2 * sm_count, row_blocks > 0 ? row_blocks : 1);
-    const int max_by_work = tiles / 4 > 0 ? tiles / 4 : 1;
-    if (splits > max_by_work) splits = max_by_work;
-    if (splits < 1) splits = 1;
-    if (splits > 64) splits = 64;
-    return splits;
+    if (row_blocks <= 0 || tiles <= 1) return 1;
+    const int slots = 2 * sm_count;
+    const int max_splits = std::min(64, std::max(1, tiles / 4));
+    auto efficiency = [&](int s) {
+        const int ctas = row_blocks * s;
+        const int waves = ceil_div(ctas, slots);
+        const int tiles_per = ceil_div(tiles, s);
+        return (double)row_blocks * tiles / ((double)waves * slots * tiles_per);
+    };
+    double best_eff = 0.0;
+    for (int s = 1; s <= max_splits; ++s) best_eff = std::max(best_eff, efficiency(s));
+    for (int s = 1; s <= max_splits; ++s)
+        if (efficiency(s) >= 0.96 * best_eff) return s;
+    return 1;
 }
 
 sdpa_status launch_attn_f32(const float* Q, const float* K, const float* V, int rows, int n, int dk,
