@@ -54,6 +54,7 @@ constexpr uint32_t TILE_BYTES = TILE * HEAD * 2;      // 32 KiB
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;       // one 64-column TMA box
 constexpr float kLazyThreshold = 8.0f;                // safe mode: rescale O only if the max grew by > 2^8
 constexpr float kGuardThreshold = 64.0f;              // fast mode: exponents beyond 2^64 hand the launch to the safe kernel
+constexpr bool kDefaultV6 = false;                    // flipped once v6 is validated on hardware
 constexpr int kDefaultPoly = 4;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
 
 constexpr uint32_t TMEM_S = 0;    // + 128 * tile
@@ -765,6 +766,375 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
 }
 
+// =====================================================================================
+// v6: cluster of two CTAs, ONE 128-row Q tile per CTA, chain-free pipeline.
+//
+// v5 (above) keeps two Q tiles per CTA; because P aliases S in TMEM, a tile's next S = Q K^T cannot be
+// issued before its P V has consumed P, so each tile is a serial chain softmax -> PV -> S and the
+// iteration period is their SUM (profiles/r01/timeline_trace_v5_cta00.txt).  Here one Q tile owns the
+// whole TMEM: S and P are double-buffered and separate (S0 S1 O P0 P1 = 128+128+128+64+64 columns), so
+//      tensor pipe :  S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...      (never waits for the softmax of its own S)
+//      softmax     :  tile 0 | tile 1 | tile 2 | ...                  (S(j+1) is ready before tile j ends)
+// and the period becomes the MAX of the two.  Halving the rows per CTA would double the L2->SM traffic of
+// K/V (beyond the ~6.3 KB/clk L2 limit), so the two CTAs of a cluster take neighbouring Q tiles and the
+// SAME key range: each TMA-loads one 64-column half of every K/V tile and multicasts it into both CTAs'
+// shared memory; a stage is recycled when both CTAs' MMAs have committed (tcgen05.commit multicast).
+// Only the fast variant exists here; the overflow guard hands the launch to the v5 SAFE kernel.
+// =====================================================================================
+constexpr int V6_THREADS = 384;
+constexpr int V6_KSTAGES = 3, V6_VSTAGES = 2;
+constexpr uint32_t V6_S = 0, V6_O = 256, V6_P = 384;
+
+struct __align__(1024) SharedV6 {
+    uint8_t q[TILE_BYTES];
+    uint8_t k[V6_KSTAGES][TILE_BYTES];
+    uint8_t v[V6_VSTAGES][TILE_BYTES];
+    uint64_t q_full;
+    uint64_t k_full[V6_KSTAGES], k_empty[V6_KSTAGES];
+    uint64_t v_full[V6_VSTAGES], v_empty[V6_VSTAGES];
+    uint64_t s_full[2], p_ready[2], pv_done[2], o_done;
+    uint32_t tmem_base;
+    float xchg[2][2][TILE];   // [parity][column half][row]
+};
+
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// arrive (once the MMAs issued so far complete) on the barrier at this offset in every CTA of the mask
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+template <bool TRACE, int POLY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V6_THREADS, 1)
+attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
+{
+    extern __shared__ uint8_t smem_raw[];
+    SharedV6& sm = *reinterpret_cast<SharedV6*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int row_block = blockIdx.x;             // 128 rows; blockIdx.x = 2*cluster + rank
+    const int split = blockIdx.y;
+    const uint32_t rank = cluster_cta_rank();      // 0 or 1: which 64-column half of every K/V tile this CTA loads
+
+    const int tq = prm.tiles_total / prm.splits, tr = prm.tiles_total % prm.splits;
+    const int tile_begin = split * tq + min(split, tr);
+    const int num_tiles = tq + (split < tr ? 1 : 0);   // identical in both CTAs of the cluster
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_q);
+        prefetch_tensormap(&map_k);
+        prefetch_tensormap(&map_v);
+        mbar_init(&sm.q_full, 1);
+        mbar_init(&sm.o_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.s_full[i], 1);
+            mbar_init(&sm.p_ready[i], 256);
+            mbar_init(&sm.pv_done[i], 1);
+        }
+        for (int i = 0; i < V6_KSTAGES; ++i) {
+            mbar_init(&sm.k_full[i], 1);
+            mbar_init(&sm.k_empty[i], 2);   // both CTAs of the cluster must have consumed the stage
+        }
+        for (int i = 0; i < V6_VSTAGES; ++i) {
+            mbar_init(&sm.v_full[i], 1);
+            mbar_init(&sm.v_empty[i], 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
+    tcgen05_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    auto stamp = [&](int role, int j, int ev) {
+        if constexpr (TRACE) {
+            if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < TRACE_ITERS)
+                prm.trace[(role * TRACE_ITERS + j) * TRACE_EVENTS + ev] = clock64();
+        }
+    };
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        if (num_tiles > 0) {
+            if (warp == 0) {
+                // ================================ TMA producer ================================
+                const int qrow = row_block * TILE;
+                const uint16_t both = 0x3;
+                for (int j = 0; j < num_tiles; ++j) {
+                    const int ks = j % V6_KSTAGES, vs = j % V6_VSTAGES;
+                    const uint32_t kph = (uint32_t)(j / V6_KSTAGES) & 1u, vph = (uint32_t)(j / V6_VSTAGES) & 1u;
+                    const int key0 = (tile_begin + j) * TILE;
+                    if (j == 0 && elect_one_sync()) {
+                        mbar_arrive_expect_tx(&sm.q_full, TILE_BYTES);
+                        tma_load_2d(sm.q, &map_q, &sm.q_full, 0, qrow);
+                        tma_load_2d(sm.q + HALF_BYTES, &map_q, &sm.q_full, 64, qrow);
+                    }
+                    mbar_wait(&sm.k_empty[ks], kph ^ 1u, 100 + ks);
+                    stamp(5, j, 0);
+                    if (elect_one_sync()) {
+                        // my barrier will see the whole tile: my half + the half the peer multicasts to me
+                        mbar_arrive_expect_tx(&sm.k_full[ks], TILE_BYTES);
+                        tma_load_2d_multicast(sm.k[ks] + rank * HALF_BYTES, &map_k, &sm.k_full[ks], 64 * (int)rank, key0, both);
+                    }
+                    mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
+                    stamp(5, j, 1);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
+                        tma_load_2d_multicast(sm.v[vs] + rank * HALF_BYTES, &map_v, &sm.v_full[vs], 64 * (int)rank, key0, both);
+                    }
+                    __syncwarp();
+                }
+            } else if (warp == 1) {
+                // ================================ MMA issuer ==================================
+                constexpr uint32_t idesc_qk = make_idesc(TILE, TILE, 0);
+                constexpr uint32_t idesc_pv = make_idesc(TILE, HEAD, 1);
+                const uint64_t dq = desc_kmajor(smem_u32(sm.q), 0);
+                const uint64_t dkk[V6_KSTAGES] = {desc_kmajor(smem_u32(sm.k[0]), 0), desc_kmajor(smem_u32(sm.k[1]), 0),
+                                                  desc_kmajor(smem_u32(sm.k[2]), 0)};
+                const uint64_t dvv[V6_VSTAGES] = {desc_mnmajor(smem_u32(sm.v[0]), 0), desc_mnmajor(smem_u32(sm.v[1]), 0)};
+                const uint16_t both = 0x3;
+
+                auto issue_s = [&](int j) {
+                    const int sb = j & 1, ks = j % V6_KSTAGES;
+                    mbar_wait(&sm.k_full[ks], (uint32_t)(j / V6_KSTAGES) & 1u, 200 + ks);
+                    tcgen05_fence_after();
+                    if (elect_one_sync()) {
+                        const uint64_t b0 = dkk[ks];
+                        const uint32_t d = tmem + V6_S + 128u * sb;
+#pragma unroll
+                        for (int kk = 0; kk < HEAD / 16; ++kk) {
+                            const uint64_t off = (uint64_t)(((kk >> 2) * HALF_BYTES + (kk & 3) * 32u) >> 4);
+                            umma_ss(d, dq + off, b0 + off, idesc_qk, kk > 0 ? 1u : 0u);
+                        }
+                        umma_commit(&sm.s_full[sb]);
+                        umma_commit_multicast(&sm.k_empty[ks], both);
+                    }
+                    __syncwarp();
+                };
+                auto issue_pv = [&](int j, bool last) {
+                    const int pb = j & 1, vs = j % V6_VSTAGES;
+                    mbar_wait(&sm.v_full[vs], (uint32_t)(j / V6_VSTAGES) & 1u, 210 + vs);
+                    mbar_wait(&sm.p_ready[pb], (uint32_t)(j >> 1) & 1u, 212 + pb);
+                    stamp(4, j, 1);
+                    tcgen05_fence_after();
+                    if (elect_one_sync()) {
+                        const uint64_t b0 = dvv[vs];
+                        const uint32_t d = tmem + V6_O;
+                        const uint32_t a = tmem + V6_P + 64u * pb;
+#pragma unroll
+                        for (int kk = 0; kk < TILE / 16; ++kk)
+                            umma_ts(d, a + 8u * kk, b0 + (uint64_t)((kk * 2048u) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit(&sm.pv_done[pb]);
+                        umma_commit_multicast(&sm.v_empty[vs], both);
+                        if (last) umma_commit(&sm.o_done);
+                    }
+                    __syncwarp();
+                };
+
+                mbar_wait(&sm.q_full, 0, 201);
+                issue_s(0);
+                if (num_tiles > 1) issue_s(1);
+                for (int j = 0; j < num_tiles; ++j) {
+                    stamp(4, j, 0);
+                    issue_pv(j, j + 1 == num_tiles);
+                    stamp(4, j, 2);
+                    if (j + 2 < num_tiles) issue_s(j + 2);
+                    stamp(4, j, 3);
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        const int sw = warp - 4;                       // 0..7
+        const int half = sw >> 2;                      // which 64-key half of the row
+        const int quad = warp & 3;                     // TMEM lane quadrant of this warp
+        const int row_in_tile = quad * 32 + lane;
+        const int grow = row_block * TILE + row_in_tile;
+        if (num_tiles > 0) {
+            // ================================ softmax + epilogue ==========================
+            const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+            const uint32_t o_addr = tmem + lane_base + V6_O + 64u * half;
+            const float scale = prm.scale_log2;
+            const uint64_t scale2 = pack_f32x2(scale, scale);
+            const int bar_id = 1 + quad;               // pair barrier: the two warps that share these 32 rows
+
+            float m_ref = -CUDART_INF_F;
+            float lsum = 0.f;
+
+            auto exp_chunk = [&](const uint32_t* sv, uint64_t neg_ref2, uint64_t& acc0, uint64_t& acc1, uint32_t* pr) {
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+                    const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
+                    float p0, p1;
+                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
+                    if (poly) {
+                        exp2_poly_x2(t2, p0, p1);
+                    } else {
+                        float t0, t1;
+                        unpack_f32x2(t2, t0, t1);
+                        p0 = fast_exp2(t0);
+                        p1 = fast_exp2(t1);
+                    }
+                    const uint64_t p2 = pack_f32x2(p0, p1);
+                    if (c & 4) acc1 = add_f32x2(acc1, p2);
+                    else acc0 = add_f32x2(acc0, p2);
+                    pr[c / 2] = pack_bf16x2(p0, p1);
+                }
+            };
+
+            auto tile_step = [&](int j, auto masked_tag, auto first_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
+                constexpr bool FIRST = decltype(first_tag)::value;
+                const int sb = j & 1;
+                const uint32_t s_addr = tmem + lane_base + V6_S + 128u * sb + 64u * half;
+                const uint32_t p_addr = tmem + lane_base + V6_P + 64u * sb + 32u * half;
+                mbar_wait(&sm.s_full[sb], (uint32_t)(j >> 1) & 1u, 300 + sb);
+                if (quad == 0) stamp(half, j, 0);
+                tcgen05_fence_after();
+
+                uint32_t sr[64];
+                SDPA_TMEM_LD32(s_addr, sr);
+                SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
+                tmem_wait_ld();
+                if (quad == 0) stamp(half, j, 1);
+                if constexpr (MASKED) {
+                    const int keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;
+#pragma unroll
+                    for (int c = 0; c < 64; ++c)
+                        if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
+                }
+                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
+                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
+                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
+                }
+                const float my_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if constexpr (FIRST) {
+                    // the reference of the whole key range: the first tile's row max, agreed by the two halves
+                    sm.xchg[0][half][row_in_tile] = my_max;
+                    named_barrier_sync(bar_id, 64);
+                    m_ref = fmaxf(my_max, sm.xchg[0][half ^ 1][row_in_tile]);
+                } else {
+                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
+                        if (lane == 0) atomicExch(prm.guard, prm.epoch);   // hand the launch to the SAFE kernel
+                    }
+                }
+                if (j >= 2) mbar_wait(&sm.pv_done[sb], (uint32_t)((j >> 1) - 1) & 1u, 310 + sb);   // P buffer free again
+                if (quad == 0) stamp(half, j, 2);
+
+                const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
+                uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t pr[8];
+                    exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr);
+                    SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
+                }
+                float a0, a1, a2, a3;
+                unpack_f32x2(acc0, a0, a1);
+                unpack_f32x2(acc1, a2, a3);
+                lsum += (a0 + a1) + (a2 + a3);
+                if (quad == 0) stamp(half, j, 4);
+                tmem_wait_st();
+                tcgen05_fence_before();
+                mbar_arrive(&sm.p_ready[sb]);
+                if (quad == 0) stamp(half, j, 5);
+            };
+
+            const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
+            const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
+            if (full_tiles > 0) tile_step(0, std::false_type{}, std::true_type{});
+            for (int j = 1; j < full_tiles; ++j) tile_step(j, std::false_type{}, std::false_type{});
+            if (ragged) {
+                if (num_tiles == 1) tile_step(0, std::true_type{}, std::true_type{});
+                else tile_step(num_tiles - 1, std::true_type{}, std::false_type{});
+            }
+
+            // ---------------- epilogue ----------------
+            sm.xchg[1][half][row_in_tile] = lsum;
+            named_barrier_sync(bar_id, 64);
+            lsum += sm.xchg[1][half ^ 1][row_in_tile];
+            mbar_wait(&sm.o_done, 0, 320);
+            tcgen05_fence_after();
+            const bool valid = grow < prm.rows;
+            const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t orr[32];
+                SDPA_TMEM_LD32(o_addr + c0, orr);
+                tmem_wait_ld();
+                if (valid) {
+                    const int col = 64 * half + c0;
+                    if (prm.out64 != nullptr) {
+                        double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + col);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2)
+                            dst[c / 2] = make_double2((double)(__uint_as_float(orr[c]) * inv),
+                                                      (double)(__uint_as_float(orr[c + 1]) * inv));
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + col);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            dst[c / 4] = make_float4(__uint_as_float(orr[c]), __uint_as_float(orr[c + 1]),
+                                                     __uint_as_float(orr[c + 2]), __uint_as_float(orr[c + 3]));
+                    }
+                }
+            }
+            if (valid && half == 0 && prm.out64 == nullptr) {
+                prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = m_ref * scale;
+                prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = lsum;
+            }
+        } else if (grow < prm.rows) {
+            // empty key range: the neutral state (0, -inf, 0), mpi.c:172,188
+            if (prm.out64 != nullptr) {
+                for (int c = 0; c < 64; ++c) prm.out64[(size_t)grow * HEAD + 64 * half + c] = 0.0;
+            } else {
+                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + 64 * half;
+                for (int c = 0; c < 64; ++c) dst[c] = 0.f;
+                if (half == 0) {
+                    prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
+                    prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // neither CTA leaves while the other may still multicast into it or arrive on its barriers
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -858,9 +1228,16 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
     return SDPA_OK;
 }
 
+// Kernel generation: v6 (cluster of two 128-row CTAs, chain-free pipeline) unless SDPA_UMMA_V6=0 asks for v5.
+static bool use_v6()
+{
+    const char* e = getenv("SDPA_UMMA_V6");
+    return e ? (*e != '0') : kDefaultV6;
+}
+
 int attn_umma_pick_splits(int rows, int n, int sm_count)
 {
-    const int row_blocks = ceil_div(rows, BLOCK_ROWS);
+    const int row_blocks = use_v6() ? 2 * ceil_div(ceil_div(rows, TILE), 2) : ceil_div(rows, BLOCK_ROWS);
     const int tiles = ceil_div(n, TILE);
     if (row_blocks <= 0 || tiles <= 1) return 1;
     // choose the split count (<= 64, >= 4 key tiles each) with the best wave efficiency of the
@@ -918,6 +1295,11 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true, false, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
+        const int sb6 = (int)(sizeof(SharedV6) + 1024);
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
         plan->attr_set[dev] = true;
     }
     if (!plan->guard) {
@@ -939,7 +1321,10 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.guard = plan->guard;
     prm.epoch = ++plan->epoch;
     if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
-    dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);
+    dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);                      // v5 / SAFE: 256 rows per CTA
+    const bool v6 = use_v6();
+    dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v6: 128 rows per CTA, clusters of two along x
+    const size_t smem6 = sizeof(SharedV6) + 1024;
     const char* trace_path = getenv("SDPA_UMMA_TRACE");   // developer aid: dump a clock64 timeline of CTA (0,0)
     if (trace_path && *trace_path) {
         const size_t count = (size_t)TRACE_ROLES * TRACE_ITERS * TRACE_EVENTS;
@@ -947,7 +1332,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
         SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
         prm.trace = dtrace;
-        attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        if (v6) attn_umma_kernel_v6<true, kDefaultPoly><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
         std::vector<long long> host(count);
         SDPA_CUDA_TRY(cudaMemcpyAsync(host.data(), dtrace, count * sizeof(long long), cudaMemcpyDeviceToHost, stream));
@@ -966,6 +1352,11 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     } else if (force_safe) {
         SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
         prm.epoch = 0xffffffffu;
+    } else if (v6) {
+        if (poly == 0) attn_umma_kernel_v6<false, 0><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (poly == 8) attn_umma_kernel_v6<false, 8><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else attn_umma_kernel_v6<false, 4><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        count_launch();
     } else {
         if (!chunked && poly == 0) attn_umma_kernel<false, false, 0, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else if (!chunked) attn_umma_kernel<false, false, 4, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
