@@ -316,10 +316,13 @@ def run_ours(args) -> None:
     launches0 = sdpa_b200.launch_count()
     with ClockSampler(local_rank) as clk:
         ms_dev = timed(step_device, K, collect)
-        # the timed region is a few milliseconds: keep the identical load running so the sampler sees it
-        t_end = time.time() + 1.0
-        while time.time() < t_end:
+        # The timed region is a few milliseconds: keep the identical load running so the sampler sees it.
+        # Every step is collective across ranks, so the extra steps are a COUNT derived from the
+        # max-reduced time (identical on all ranks), never a per-rank wall-clock loop.
+        extra = int(min(20000, max(1, 1000.0 / max(ms_dev / K, 1e-3))))
+        for _ in range(extra):
             step_device()
+        barrier()
     launches = sdpa_b200.launch_count() - launches0
     clocks = clk.summary()
     kernel_name = ctx.last_kernel()
