@@ -54,6 +54,7 @@ constexpr uint32_t TILE_BYTES = TILE * HEAD * 2;      // 32 KiB
 constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;       // one 64-column TMA box
 constexpr float kLazyThreshold = 8.0f;                // safe mode: rescale O only if the max grew by > 2^8
 constexpr float kGuardThreshold = 64.0f;              // fast mode: exponents beyond 2^64 hand the launch to the safe kernel
+constexpr int kDefaultParts = 2;                      // v6: softmax warpgroups per tile
 constexpr bool kDefaultV6 = false;                    // flipped once v6 is validated on hardware
 constexpr int kDefaultPoly = 4;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
 
@@ -794,7 +795,7 @@ struct __align__(1024) SharedV6 {
     uint64_t v_full[V6_VSTAGES], v_empty[V6_VSTAGES];
     uint64_t s_full[2], p_ready[2], pv_done[2], o_done;
     uint32_t tmem_base;
-    float xchg[2][2][TILE];   // [parity][column half][row]
+    float xchg[2][4][TILE];   // [first-tile max | final sum][column part][row]
 };
 
 __device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -824,8 +825,9 @@ __device__ __forceinline__ uint32_t cluster_cta_rank()
     return r;
 }
 
-template <bool TRACE, int POLY>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V6_THREADS, 1)
+// NPARTS = softmax warpgroups per tile (2 or 4): a thread owns one row and 128/NPARTS of its keys.
+template <bool TRACE, int POLY, int NPARTS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * NPARTS, 1)
 attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
 {
@@ -850,7 +852,7 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         mbar_init(&sm.o_done, 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.s_full[i], 1);
-            mbar_init(&sm.p_ready[i], 256);
+            mbar_init(&sm.p_ready[i], 128 * NPARTS);
             mbar_init(&sm.pv_done[i], 1);
         }
         for (int i = 0; i < V6_KSTAGES; ++i) {
@@ -877,7 +879,8 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     };
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (num_tiles > 0) {
             if (warp == 0) {
                 // ================================ TMA producer ================================
@@ -967,16 +970,18 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        const int sw = warp - 4;                       // 0..7
-        const int half = sw >> 2;                      // which 64-key half of the row
+        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        constexpr int COLS = TILE / NPARTS;            // keys (S columns) per thread: 64 or 32
+        const int sw = warp - 4;
+        const int half = sw >> 2;                      // which COLS-wide part of the row (0..NPARTS-1)
         const int quad = warp & 3;                     // TMEM lane quadrant of this warp
         const int row_in_tile = quad * 32 + lane;
         const int grow = row_block * TILE + row_in_tile;
         if (num_tiles > 0) {
             // ================================ softmax + epilogue ==========================
             const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-            const uint32_t o_addr = tmem + lane_base + V6_O + 64u * half;
+            const uint32_t o_addr = tmem + lane_base + V6_O + (uint32_t)COLS * half;
             const float scale = prm.scale_log2;
             const uint64_t scale2 = pack_f32x2(scale, scale);
             const int bar_id = 1 + quad;               // pair barrier: the two warps that share these 32 rows
@@ -1010,26 +1015,26 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 constexpr bool MASKED = decltype(masked_tag)::value;
                 constexpr bool FIRST = decltype(first_tag)::value;
                 const int sb = j & 1;
-                const uint32_t s_addr = tmem + lane_base + V6_S + 128u * sb + 64u * half;
-                const uint32_t p_addr = tmem + lane_base + V6_P + 64u * sb + 32u * half;
+                const uint32_t s_addr = tmem + lane_base + V6_S + 128u * sb + (uint32_t)COLS * half;
+                const uint32_t p_addr = tmem + lane_base + V6_P + 64u * sb + (uint32_t)(COLS / 2) * half;
                 mbar_wait(&sm.s_full[sb], (uint32_t)(j >> 1) & 1u, 300 + sb);
-                if (quad == 0) stamp(half, j, 0);
+                if (quad == 0 && half < 2) stamp(half, j, 0);
                 tcgen05_fence_after();
 
-                uint32_t sr[64];
+                uint32_t sr[COLS];
                 SDPA_TMEM_LD32(s_addr, sr);
-                SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
+                if constexpr (COLS == 64) SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
                 tmem_wait_ld();
-                if (quad == 0) stamp(half, j, 1);
+                if (quad == 0 && half < 2) stamp(half, j, 1);
                 if constexpr (MASKED) {
-                    const int keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;
+                    const int keys_left = prm.n - (tile_begin + j) * TILE - COLS * half;
 #pragma unroll
-                    for (int c = 0; c < 64; ++c)
+                    for (int c = 0; c < COLS; ++c)
                         if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
                 }
                 float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
 #pragma unroll
-                for (int c = 0; c < 64; c += 8) {
+                for (int c = 0; c < COLS; c += 8) {
                     mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1])));
                     mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
                     mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
@@ -1039,20 +1044,19 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 if constexpr (FIRST) {
                     // the reference of the whole key range: the first tile's row max, agreed by the two halves
                     sm.xchg[0][half][row_in_tile] = my_max;
-                    named_barrier_sync(bar_id, 64);
-                    m_ref = fmaxf(my_max, sm.xchg[0][half ^ 1][row_in_tile]);
-                } else {
-                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
-                        if (lane == 0) atomicExch(prm.guard, prm.epoch);   // hand the launch to the SAFE kernel
-                    }
+                    named_barrier_sync(bar_id, 32 * NPARTS);
+                    m_ref = my_max;
+#pragma unroll
+                    for (int p = 0; p < NPARTS; ++p) m_ref = fmaxf(m_ref, sm.xchg[0][p][row_in_tile]);
                 }
-                if (j >= 2) mbar_wait(&sm.pv_done[sb], (uint32_t)((j >> 1) - 1) & 1u, 310 + sb);   // P buffer free again
-                if (quad == 0) stamp(half, j, 2);
+                // No wait is needed before overwriting P buffer sb: PV(j-2), its last reader, was issued before
+                // S(j), and the commit behind s_full(j) covers every MMA issued before it.
+                if (quad == 0 && half < 2) stamp(half, j, 2);
 
                 const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
                 uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch < COLS / 16; ++ch) {
                     uint32_t pr[8];
                     exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr);
                     SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
@@ -1061,11 +1065,17 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 unpack_f32x2(acc0, a0, a1);
                 unpack_f32x2(acc1, a2, a3);
                 lsum += (a0 + a1) + (a2 + a3);
-                if (quad == 0) stamp(half, j, 4);
+                if constexpr (!FIRST) {
+                    // overflow guard, off the critical path (the max chain overlaps the exponentials)
+                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
+                        if (lane == 0) atomicExch(prm.guard, prm.epoch);   // hand the launch to the SAFE kernel
+                    }
+                }
+                if (quad == 0 && half < 2) stamp(half, j, 4);
                 tmem_wait_st();
                 tcgen05_fence_before();
                 mbar_arrive(&sm.p_ready[sb]);
-                if (quad == 0) stamp(half, j, 5);
+                if (quad == 0 && half < 2) stamp(half, j, 5);
             };
 
             const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
@@ -1079,19 +1089,21 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 
             // ---------------- epilogue ----------------
             sm.xchg[1][half][row_in_tile] = lsum;
-            named_barrier_sync(bar_id, 64);
-            lsum += sm.xchg[1][half ^ 1][row_in_tile];
+            named_barrier_sync(bar_id, 32 * NPARTS);
+            lsum = 0.f;
+#pragma unroll
+            for (int p = 0; p < NPARTS; ++p) lsum += sm.xchg[1][p][row_in_tile];
             mbar_wait(&sm.o_done, 0, 320);
             tcgen05_fence_after();
             const bool valid = grow < prm.rows;
             const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
 #pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+            for (int c0 = 0; c0 < COLS; c0 += 32) {
                 uint32_t orr[32];
                 SDPA_TMEM_LD32(o_addr + c0, orr);
                 tmem_wait_ld();
                 if (valid) {
-                    const int col = 64 * half + c0;
+                    const int col = COLS * half + c0;
                     if (prm.out64 != nullptr) {
                         double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + col);
 #pragma unroll
@@ -1114,10 +1126,10 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         } else if (grow < prm.rows) {
             // empty key range: the neutral state (0, -inf, 0), mpi.c:172,188
             if (prm.out64 != nullptr) {
-                for (int c = 0; c < 64; ++c) prm.out64[(size_t)grow * HEAD + 64 * half + c] = 0.0;
+                for (int c = 0; c < COLS; ++c) prm.out64[(size_t)grow * HEAD + COLS * half + c] = 0.0;
             } else {
-                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + 64 * half;
-                for (int c = 0; c < 64; ++c) dst[c] = 0.f;
+                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + COLS * half;
+                for (int c = 0; c < COLS; ++c) dst[c] = 0.f;
                 if (half == 0) {
                     prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
                     prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
@@ -1296,10 +1308,14 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true, false, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         const int sb6 = (int)(sizeof(SharedV6) + 1024);
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
         plan->attr_set[dev] = true;
     }
     if (!plan->guard) {
@@ -1323,6 +1339,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
     dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);                      // v5 / SAFE: 256 rows per CTA
     const bool v6 = use_v6();
+    const char* env_parts = getenv("SDPA_UMMA_PARTS");   // v6: softmax warpgroups per tile (2 or 4)
+    const bool parts4 = env_parts ? (atoi(env_parts) == 4) : (kDefaultParts == 4);
     dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v6: 128 rows per CTA, clusters of two along x
     const size_t smem6 = sizeof(SharedV6) + 1024;
     const char* trace_path = getenv("SDPA_UMMA_TRACE");   // developer aid: dump a clock64 timeline of CTA (0,0)
@@ -1332,7 +1350,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
         SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
         prm.trace = dtrace;
-        if (v6) attn_umma_kernel_v6<true, kDefaultPoly><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        if (v6 && parts4) attn_umma_kernel_v6<true, kDefaultPoly, 4><<<grid6, 640, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (v6) attn_umma_kernel_v6<true, kDefaultPoly, 2><<<grid6, 384, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
         std::vector<long long> host(count);
@@ -1353,9 +1372,17 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
         prm.epoch = 0xffffffffu;
     } else if (v6) {
-        if (poly == 0) attn_umma_kernel_v6<false, 0><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (poly == 8) attn_umma_kernel_v6<false, 8><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else attn_umma_kernel_v6<false, 4><<<grid6, V6_THREADS, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+#define SDPA_LAUNCH_V6(P, N) attn_umma_kernel_v6<false, P, N><<<grid6, 128 + 128 * N, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
+        if (parts4) {
+            if (poly == 0) SDPA_LAUNCH_V6(0, 4);
+            else if (poly == 8) SDPA_LAUNCH_V6(8, 4);
+            else SDPA_LAUNCH_V6(4, 4);
+        } else {
+            if (poly == 0) SDPA_LAUNCH_V6(0, 2);
+            else if (poly == 8) SDPA_LAUNCH_V6(8, 2);
+            else SDPA_LAUNCH_V6(4, 2);
+        }
+#undef SDPA_LAUNCH_V6
         count_launch();
     } else {
         if (!chunked && poly == 0) attn_umma_kernel<false, false, 0, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
