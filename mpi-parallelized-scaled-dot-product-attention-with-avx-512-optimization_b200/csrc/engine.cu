@@ -21,6 +21,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <atomic>
@@ -212,6 +213,14 @@ static sdpa_status time_end(Shard& s, int which, cudaStream_t st)
     SDPA_CUDA_TRY(cudaEventRecord(s.tev[which][s.tev_used[which] + 1], st));
     s.tev_used[which] += 2;
     return SDPA_OK;
+}
+
+// Developer aid: SDPA_HOST_PROFILE=1 prints host-side timestamps (us) of one attention call's phases.
+static double host_now_us()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 
 static size_t elem_size(int prec) { return prec == SDPA_PREC_BF16 ? 2 : 4; }
@@ -537,6 +546,8 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     for (float& t : ctx->last_timing) t = 0.f;
     if (m == 0) return SDPA_OK;
 
+    static const bool host_prof = getenv("SDPA_HOST_PROFILE") != nullptr;
+    const double hp0 = host_prof ? host_now_us() : 0.0;
     const int B = pick_q_batch(ctx, m);
     const int num_iter = ceil_div(m, B);
 
@@ -809,6 +820,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_TRY(launch_wait_flag(ctx->ipc.root_flags + 2 + b, ctx->ipc.slot_epoch[b], s.s_compute));
     }
 
+    const double hp1 = host_prof ? host_now_us() : 0.0;
     // ---- join: every stream back into the compute stream, then wait ----------------------------
     for (int i = 0; i < L; ++i) {
         Shard& s = ctx->shards[i];
@@ -826,6 +838,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
     }
 
+    const double hp2 = host_prof ? host_now_us() : 0.0;
     // ---- timings (max over local shards) --------------------------------------------------------
     for (int i = 0; i < L; ++i) {
         Shard& s = ctx->shards[i];
@@ -843,6 +856,11 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         ctx->last_timing[1] = std::max(ctx->last_timing[1], acc[0]);
         ctx->last_timing[2] = std::max(ctx->last_timing[2], acc[1]);
         ctx->last_timing[3] = std::max(ctx->last_timing[3], acc[2]);
+    }
+    if (host_prof) {
+        const double hp3 = host_now_us();
+        fprintf(stderr, "sdpa host profile: enqueue %.1f us, join+sync %.1f us, event queries %.1f us (device total %.1f us)\n",
+                hp1 - hp0, hp2 - hp1, hp3 - hp2, ctx->last_timing[0] * 1e3);
     }
     ctx->last_timing[4] = (float)fused_launches;
     (void)all_launches;
