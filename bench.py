@@ -275,9 +275,10 @@ def run_ours(args) -> None:
     else:
         ctx = sdpa_b200.Context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, first_device=local_rank)
 
+    kd, vd, qd, rd = [Kd.data_ptr()], [Vd.data_ptr()], [Qd.data_ptr()], (Rd.data_ptr() if Rd is not None else None)
+
     def step_device():
-        ctx.load_kv_device_ptrs([Kd.data_ptr()], [Vd.data_ptr()], [n_local], DK, DV)
-        ctx.attention_device_ptrs([Qd.data_ptr()], Rd.data_ptr() if Rd is not None else None, m)
+        ctx.attention_device_full(kd, vd, [n_local], DK, DV, qd, rd, m)
 
     def step_host():
         ctx.load_kv_host_ptrs([Kh.data_ptr()], [Vh.data_ptr()], [n_local], DK, DV)

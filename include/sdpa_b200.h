@@ -133,6 +133,11 @@ sdpa_status sdpa_load_kv_host_full(sdpa_ctx* ctx, const double* K, const double*
 sdpa_status sdpa_attention_host(sdpa_ctx* ctx, const double* Q, double* result, int m);
 sdpa_status sdpa_attention_device(sdpa_ctx* ctx, const double* const* Q_dev, double* result_dev, int m);
 
+/* load_kv_device + attention_device in one call (the whole attention() path on device-resident fp64). */
+sdpa_status sdpa_attention_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
+                                       const int* n_local, int dk, int dv, const double* const* Q_dev,
+                                       double* result_dev, int m);
+
 /* The reference's calling convention on a one-GPU-per-process context (world_size > 1):
  * dimensions and Q/K/V/result are valid on the process that owns shard 0 only; that process
  * scatters the K/V shards and broadcasts the Q batches over NCCL (mpi.c:196,213-266,305,327). */

@@ -782,7 +782,7 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // shared memory; a stage is recycled when both CTAs' MMAs have committed (tcgen05.commit multicast).
 // Only the fast variant exists here; the overflow guard hands the launch to the v5 SAFE kernel.
 // =====================================================================================
-constexpr int V6_THREADS = 384;
+
 constexpr int V6_KSTAGES = 3, V6_VSTAGES = 2;
 constexpr uint32_t V6_S = 0, V6_O = 256, V6_P = 384;
 
@@ -1194,6 +1194,8 @@ struct UmmaPlan {
     int n = 0;
     bool kv_bound = false, q_bound[2] = {false, false};
     const void* q_base[2] = {nullptr, nullptr};
+    const void* k_base = nullptr;
+    const void* v_base = nullptr;
     int q_rows[2] = {0, 0};
     bool attr_set[64] = {};
     unsigned int* guard = nullptr;   // device word for the overflow guard (on the plan's device)
@@ -1219,8 +1221,11 @@ sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv
         set_error("bf16 tensor-core kernel supports dk == dv == 128 (got dk=%d dv=%d)", dk, dv);
         return SDPA_ERR_UNSUPPORTED;
     }
+    if (plan->kv_bound && plan->k_base == K && plan->v_base == V && plan->n == n) return SDPA_OK;   // descriptors still valid
     SDPA_TRY(encode_map(&plan->map_k, K, n));
     SDPA_TRY(encode_map(&plan->map_v, V, n));
+    plan->k_base = K;
+    plan->v_base = V;
     plan->n = n;
     plan->kv_bound = true;
     return SDPA_OK;

@@ -1189,6 +1189,14 @@ sdpa_status sdpa_attention_device(sdpa_ctx* ctx, const double* const* Q_dev, dou
     return attention_impl(ctx, nullptr, Q_dev, result_dev, true, m);
 }
 
+/* attention() on device-resident fp64 arrays in one call: K/V shard cast + Q batches + merge. */
+sdpa_status sdpa_attention_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
+                                       const int* n_local, int dk, int dv, const double* const* Q_dev, double* result_dev, int m)
+{
+    SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true));
+    return sdpa_attention_device(ctx, Q_dev, result_dev, m);
+}
+
 sdpa_status sdpa_online_softmax_partials(sdpa_ctx* ctx, int local, const float* Qf_dev, int m, float* contrib_dev,
                                          float* lmax_dev, float* lsum_dev)
 {

@@ -75,6 +75,7 @@ ABI = {
     "sdpa_load_kv_host_full": (ctypes.c_int, [_V, _V, _V, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "sdpa_attention_host": (ctypes.c_int, [_V, _V, _V, ctypes.c_int]),
     "sdpa_attention_device": (ctypes.c_int, [_V, _dpp, _V, ctypes.c_int]),
+    "sdpa_attention_device_full": (ctypes.c_int, [_V, _dpp, _dpp, _ip, ctypes.c_int, ctypes.c_int, _dpp, _V, ctypes.c_int]),
     "sdpa_scatter_attention": (ctypes.c_int, [_V, _V, _V, _V, _V] + [ctypes.c_int] * 4),
     "sdpa_online_softmax_partials": (ctypes.c_int, [_V, ctypes.c_int, _V, ctypes.c_int, _V, _V, _V]),
     "sdpa_last_timings": (ctypes.c_int, [_V, _fp]),
@@ -295,6 +296,18 @@ class Context:
     def attention_device_ptrs(self, Q_ptrs, result_ptr: int | None, m: int) -> None:
         _check(lib().sdpa_attention_device(self._h, self._ptr_array(Q_ptrs), ctypes.c_void_p(result_ptr or 0), m),
                "sdpa_attention_device")
+
+    def attention_device_full(self, K_ptrs, V_ptrs, n_local, dk: int, dv: int, Q_ptrs, result_ptr: int | None, m: int) -> None:
+        """The whole path on device-resident fp64 arrays in one C call (K/V cast, Q batches, merge)."""
+        key = (tuple(K_ptrs), tuple(V_ptrs), tuple(n_local), tuple(Q_ptrs))
+        if getattr(self, "_full_key", None) != key:   # marshal the pointer arrays once per distinct argument set
+            counts = (ctypes.c_int * self.num_local)(*[int(c) for c in n_local])
+            self._full_args = (self._ptr_array(K_ptrs), self._ptr_array(V_ptrs), counts, self._ptr_array(Q_ptrs))
+            self._full_key = key
+        ka, va, counts, qa = self._full_args
+        _check(lib().sdpa_attention_device_full(self._h, ka, va, counts, dk, dv, qa, ctypes.c_void_p(result_ptr or 0), m),
+               "sdpa_attention_device_full")
+        self.dk, self.dv = dk, dv
 
     def scatter_attention(self, Q=None, K=None, V=None, result=None):
         """Reference calling convention across processes: data on the shard-0 process only."""
