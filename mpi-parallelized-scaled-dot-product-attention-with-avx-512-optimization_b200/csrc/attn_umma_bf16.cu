@@ -1147,6 +1147,416 @@ attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
 }
 
+// =====================================================================================
+// v7: v6 with the 2-CTA tensor-core instruction (tcgen05.mma.cta_group::2).  The two CTAs of a cluster
+// form ONE M=256 MMA: each holds its own 128-row Q tile (A) and its own accumulators/P in its TMEM, and
+// each keeps only HALF of every K tile (64 keys) and V tile (64 value columns) in shared memory -- the
+// B operand is split across the pair -- so per SM the shared-memory traffic per key tile drops from
+// 160 KB (v6) to 96 KB and no multicast is needed.  Only the leader CTA (cluster rank 0) issues MMAs;
+// its barriers collect both CTAs' TMA bytes (2-SM TMA form: the mbarrier address is mapped to the
+// leader) and both CTAs' softmax arrivals (remote mbarrier.arrive through mapa); tcgen05.commit
+// multicasts completions to both CTAs.
+// =====================================================================================
+constexpr int V7_KSTAGES = 4, V7_VSTAGES = 3;
+constexpr uint32_t HALF_TILE_BYTES = TILE_BYTES / 2;   // 64 keys x 128 (K half) or 128 keys x 64 columns (V half)
+
+struct __align__(1024) SharedV7 {
+    uint8_t q[TILE_BYTES];
+    uint8_t k[V7_KSTAGES][HALF_TILE_BYTES];
+    uint8_t v[V7_VSTAGES][HALF_TILE_BYTES];
+    uint64_t q_full;
+    uint64_t k_full[V7_KSTAGES], k_empty[V7_KSTAGES];
+    uint64_t v_full[V7_VSTAGES], v_empty[V7_VSTAGES];
+    uint64_t s_full[2], p_ready[2], o_done;
+    uint32_t tmem_base;
+    float xchg[2][4][TILE];
+};
+
+// 2-SM TMA load: data into THIS CTA's shared memory, completion bytes on the LEADER CTA's mbarrier
+// (bit 24 of the shared::cluster address selects the CTA of the pair; clearing it addresses rank 0).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t cta_rank)
+{
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(cta_rank));
+    return ra;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <bool TRACE, int POLY, int NPARTS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * NPARTS, 1)
+attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
+{
+    extern __shared__ uint8_t smem_raw[];
+    SharedV7& sm = *reinterpret_cast<SharedV7*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int row_block = blockIdx.x;             // 128 rows; blockIdx.x = 2*cluster + rank
+    const int split = blockIdx.y;
+    const uint32_t rank = cluster_cta_rank();      // 0 = leader (issues the MMAs); rank r keeps keys [64r,64r+64) of K and columns [64r,64r+64) of V
+    const bool leader = rank == 0;
+
+    const int tq = prm.tiles_total / prm.splits, tr = prm.tiles_total % prm.splits;
+    const int tile_begin = split * tq + min(split, tr);
+    const int num_tiles = tq + (split < tr ? 1 : 0);   // identical in both CTAs of the cluster
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_khalf);
+        prefetch_tensormap(&map_q);
+        prefetch_tensormap(&map_k);
+        prefetch_tensormap(&map_v);
+        mbar_init(&sm.q_full, 2);          // leader's copy is the one used: one arrival per CTA's producer + all bytes
+        mbar_init(&sm.o_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.s_full[i], 1);
+            mbar_init(&sm.p_ready[i], 2 * 4 * NPARTS);   // leader's copy: one arrival per softmax warp of BOTH CTAs
+        }
+        for (int i = 0; i < V7_KSTAGES; ++i) {
+            mbar_init(&sm.k_full[i], 2);
+            mbar_init(&sm.k_empty[i], 1);  // the leader's commit, multicast to both CTAs
+        }
+        for (int i = 0; i < V7_VSTAGES; ++i) {
+            mbar_init(&sm.v_full[i], 2);
+            mbar_init(&sm.v_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_2cta(&sm.tmem_base, 512);   // the same warp in both CTAs
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
+    tcgen05_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    auto stamp = [&](int role, int j, int ev) {
+        if constexpr (TRACE) {
+            if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < TRACE_ITERS)
+                prm.trace[(role * TRACE_ITERS + j) * TRACE_EVENTS + ev] = clock64();
+        }
+    };
+
+    if (warp < 4) {
+        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (num_tiles > 0) {
+            if (warp == 0) {
+                // ================================ TMA producer ================================
+                // every load lands in this CTA's shared memory and reports its bytes to the LEADER's barrier;
+                // the leader arms the barrier with the bytes of both CTAs, the peer adds its plain arrival.
+                const int qrow = row_block * TILE;
+                const uint32_t leader_qfull = map_to_cta(&sm.q_full, 0);
+                for (int j = 0; j < num_tiles; ++j) {
+                    const int ks = j % V7_KSTAGES, vs = j % V7_VSTAGES;
+                    const uint32_t kph = (uint32_t)(j / V7_KSTAGES) & 1u, vph = (uint32_t)(j / V7_VSTAGES) & 1u;
+                    const int key0 = (tile_begin + j) * TILE;
+                    if (j == 0 && elect_one_sync()) {
+                        if (leader) mbar_arrive_expect_tx(&sm.q_full, 2 * TILE_BYTES);
+                        else mbar_arrive_cluster(leader_qfull);
+                        tma_load_2d_2sm(sm.q, &map_q, &sm.q_full, 0, qrow);
+                        tma_load_2d_2sm(sm.q + HALF_BYTES, &map_q, &sm.q_full, 64, qrow);
+                    }
+                    mbar_wait(&sm.k_empty[ks], kph ^ 1u, 100 + ks);
+                    stamp(5, j, 0);
+                    if (elect_one_sync()) {
+                        if (leader) mbar_arrive_expect_tx(&sm.k_full[ks], TILE_BYTES);
+                        else mbar_arrive_cluster(map_to_cta(&sm.k_full[ks], 0));
+                        // my 64 keys of the tile: two boxes of 64 columns x 64 rows (8 KiB each)
+                        tma_load_2d_2sm(sm.k[ks], &map_khalf, &sm.k_full[ks], 0, key0 + 64 * (int)rank);
+                        tma_load_2d_2sm(sm.k[ks] + HALF_TILE_BYTES / 2, &map_khalf, &sm.k_full[ks], 64, key0 + 64 * (int)rank);
+                    }
+                    mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
+                    stamp(5, j, 1);
+                    if (elect_one_sync()) {
+                        if (leader) mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
+                        else mbar_arrive_cluster(map_to_cta(&sm.v_full[vs], 0));
+                        // my 64 value columns of the tile: one box of 64 columns x 128 keys (16 KiB)
+                        tma_load_2d_2sm(sm.v[vs], &map_v, &sm.v_full[vs], 64 * (int)rank, key0);
+                    }
+                    __syncwarp();
+                }
+            } else if (warp == 1) {
+                // ================================ MMA issuer (leader CTA only) ==================
+                if (leader) {
+                constexpr uint32_t idesc_qk = make_idesc(2 * TILE, TILE, 0);   // M = 256 over the CTA pair
+                constexpr uint32_t idesc_pv = make_idesc(2 * TILE, HEAD, 1);
+                const uint64_t dq = desc_kmajor(smem_u32(sm.q), 0);
+                uint64_t dkk[V7_KSTAGES], dvv[V7_VSTAGES];
+#pragma unroll
+                for (int i = 0; i < V7_KSTAGES; ++i) dkk[i] = make_desc(smem_u32(sm.k[i]), 16u, 1024u);
+#pragma unroll
+                for (int i = 0; i < V7_VSTAGES; ++i) dvv[i] = make_desc(smem_u32(sm.v[i]), HALF_TILE_BYTES, 1024u);
+                const uint16_t both = 0x3;
+
+                auto issue_s = [&](int j) {
+                    const int sb = j & 1, ks = j % V7_KSTAGES;
+                    mbar_wait(&sm.k_full[ks], (uint32_t)(j / V7_KSTAGES) & 1u, 200 + ks);
+                    tcgen05_fence_after();
+                    if (elect_one_sync()) {
+                        const uint64_t b0 = dkk[ks];
+                        const uint32_t d = tmem + V6_S + 128u * sb;
+#pragma unroll
+                        for (int kk = 0; kk < HEAD / 16; ++kk) {
+                            const uint64_t offa = (uint64_t)(((kk >> 2) * HALF_BYTES + (kk & 3) * 32u) >> 4);            // Q: boxes of 128 rows
+                            const uint64_t offb = (uint64_t)(((kk >> 2) * (HALF_TILE_BYTES / 2) + (kk & 3) * 32u) >> 4);   // K half: boxes of 64 rows
+                            umma_ss_2cta(d, dq + offa, b0 + offb, idesc_qk, kk > 0 ? 1u : 0u);
+                        }
+                        umma_commit_2cta(&sm.s_full[sb], both);
+                        umma_commit_2cta(&sm.k_empty[ks], both);
+                    }
+                    __syncwarp();
+                };
+                auto issue_pv = [&](int j, bool last) {
+                    const int pb = j & 1, vs = j % V7_VSTAGES;
+                    mbar_wait(&sm.v_full[vs], (uint32_t)(j / V7_VSTAGES) & 1u, 210 + vs);
+                    mbar_wait(&sm.p_ready[pb], (uint32_t)(j >> 1) & 1u, 212 + pb);
+                    stamp(4, j, 1);
+                    tcgen05_fence_after();
+                    if (elect_one_sync()) {
+                        const uint64_t b0 = dvv[vs];
+                        const uint32_t d = tmem + V6_O;
+                        const uint32_t a = tmem + V6_P + 64u * pb;
+#pragma unroll
+                        for (int kk = 0; kk < TILE / 16; ++kk)
+                            umma_ts_2cta(d, a + 8u * kk, b0 + (uint64_t)((kk * 2048u) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit_2cta(&sm.v_empty[vs], both);
+                        if (last) umma_commit_2cta(&sm.o_done, both);
+                    }
+                    __syncwarp();
+                };
+
+                mbar_wait(&sm.q_full, 0, 201);
+                issue_s(0);
+                if (num_tiles > 1) issue_s(1);
+                for (int j = 0; j < num_tiles; ++j) {
+                    stamp(4, j, 0);
+                    issue_pv(j, j + 1 == num_tiles);
+                    stamp(4, j, 2);
+                    if (j + 2 < num_tiles) issue_s(j + 2);
+                    stamp(4, j, 3);
+                }
+                }
+            }
+        }
+    } else {
+        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        constexpr int COLS = TILE / NPARTS;            // keys (S columns) per thread: 64 or 32
+        const int sw = warp - 4;
+        const int half = sw >> 2;                      // which COLS-wide part of the row (0..NPARTS-1)
+        const int quad = warp & 3;                     // TMEM lane quadrant of this warp
+        const int row_in_tile = quad * 32 + lane;
+        const int grow = row_block * TILE + row_in_tile;
+        if (num_tiles > 0) {
+            // ================================ softmax + epilogue ==========================
+            const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+            const uint32_t o_addr = tmem + lane_base + V6_O + (uint32_t)COLS * half;
+            const float scale = prm.scale_log2;
+            const uint64_t scale2 = pack_f32x2(scale, scale);
+            const int bar_id = 1 + quad;               // pair barrier: the two warps that share these 32 rows
+            const uint32_t leader_pready[2] = {map_to_cta(&sm.p_ready[0], 0), map_to_cta(&sm.p_ready[1], 0)};
+
+            float m_ref = -CUDART_INF_F;
+            float lsum = 0.f;
+
+            auto exp_chunk = [&](const uint32_t* sv, uint64_t neg_ref2, uint64_t& acc0, uint64_t& acc1, uint32_t* pr) {
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+                    const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
+                    float p0, p1;
+                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
+                    if (poly) {
+                        exp2_poly_x2(t2, p0, p1);
+                    } else {
+                        float t0, t1;
+                        unpack_f32x2(t2, t0, t1);
+                        p0 = fast_exp2(t0);
+                        p1 = fast_exp2(t1);
+                    }
+                    const uint64_t p2 = pack_f32x2(p0, p1);
+                    if (c & 4) acc1 = add_f32x2(acc1, p2);
+                    else acc0 = add_f32x2(acc0, p2);
+                    pr[c / 2] = pack_bf16x2(p0, p1);
+                }
+            };
+
+            auto tile_step = [&](int j, auto masked_tag, auto first_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
+                constexpr bool FIRST = decltype(first_tag)::value;
+                const int sb = j & 1;
+                const uint32_t s_addr = tmem + lane_base + V6_S + 128u * sb + (uint32_t)COLS * half;
+                const uint32_t p_addr = tmem + lane_base + V6_P + 64u * sb + (uint32_t)(COLS / 2) * half;
+                mbar_wait(&sm.s_full[sb], (uint32_t)(j >> 1) & 1u, 300 + sb);
+                if (quad == 0 && half < 2) stamp(half, j, 0);
+                tcgen05_fence_after();
+
+                uint32_t sr[COLS];
+                SDPA_TMEM_LD32(s_addr, sr);
+                if constexpr (COLS == 64) SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
+                tmem_wait_ld();
+                if (quad == 0 && half < 2) stamp(half, j, 1);
+                if constexpr (MASKED) {
+                    const int keys_left = prm.n - (tile_begin + j) * TILE - COLS * half;
+#pragma unroll
+                    for (int c = 0; c < COLS; ++c)
+                        if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
+                }
+                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+                for (int c = 0; c < COLS; c += 8) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
+                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
+                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
+                }
+                const float my_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if constexpr (FIRST) {
+                    // the reference of the whole key range: the first tile's row max, agreed by the two halves
+                    sm.xchg[0][half][row_in_tile] = my_max;
+                    named_barrier_sync(bar_id, 32 * NPARTS);
+                    m_ref = my_max;
+#pragma unroll
+                    for (int p = 0; p < NPARTS; ++p) m_ref = fmaxf(m_ref, sm.xchg[0][p][row_in_tile]);
+                }
+                // No wait is needed before overwriting P buffer sb: PV(j-2), its last reader, was issued before
+                // S(j), and the commit behind s_full(j) covers every MMA issued before it.
+                if (quad == 0 && half < 2) stamp(half, j, 2);
+
+                const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
+                uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+#pragma unroll
+                for (int ch = 0; ch < COLS / 16; ++ch) {
+                    uint32_t pr[8];
+                    exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr);
+                    SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
+                }
+                float a0, a1, a2, a3;
+                unpack_f32x2(acc0, a0, a1);
+                unpack_f32x2(acc1, a2, a3);
+                lsum += (a0 + a1) + (a2 + a3);
+                if constexpr (!FIRST) {
+                    // overflow guard, off the critical path (the max chain overlaps the exponentials)
+                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
+                        if (lane == 0) atomicExch(prm.guard, prm.epoch);   // hand the launch to the SAFE kernel
+                    }
+                }
+                if (quad == 0 && half < 2) stamp(half, j, 4);
+                tmem_wait_st();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_pready[sb]);   // one arrival per warp, on the leader's barrier
+                if (quad == 0 && half < 2) stamp(half, j, 5);
+            };
+
+            const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
+            const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
+            if (full_tiles > 0) tile_step(0, std::false_type{}, std::true_type{});
+            for (int j = 1; j < full_tiles; ++j) tile_step(j, std::false_type{}, std::false_type{});
+            if (ragged) {
+                if (num_tiles == 1) tile_step(0, std::true_type{}, std::true_type{});
+                else tile_step(num_tiles - 1, std::true_type{}, std::false_type{});
+            }
+
+            // ---------------- epilogue ----------------
+            sm.xchg[1][half][row_in_tile] = lsum;
+            named_barrier_sync(bar_id, 32 * NPARTS);
+            lsum = 0.f;
+#pragma unroll
+            for (int p = 0; p < NPARTS; ++p) lsum += sm.xchg[1][p][row_in_tile];
+            mbar_wait(&sm.o_done, 0, 320);
+            tcgen05_fence_after();
+            const bool valid = grow < prm.rows;
+            const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
+#pragma unroll
+            for (int c0 = 0; c0 < COLS; c0 += 32) {
+                uint32_t orr[32];
+                SDPA_TMEM_LD32(o_addr + c0, orr);
+                tmem_wait_ld();
+                if (valid) {
+                    const int col = COLS * half + c0;
+                    if (prm.out64 != nullptr) {
+                        double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + col);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 2)
+                            dst[c / 2] = make_double2((double)(__uint_as_float(orr[c]) * inv),
+                                                      (double)(__uint_as_float(orr[c + 1]) * inv));
+                    } else {
+                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + col);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            dst[c / 4] = make_float4(__uint_as_float(orr[c]), __uint_as_float(orr[c + 1]),
+                                                     __uint_as_float(orr[c + 2]), __uint_as_float(orr[c + 3]));
+                    }
+                }
+            }
+            if (valid && half == 0 && prm.out64 == nullptr) {
+                prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = m_ref * scale;
+                prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = lsum;
+            }
+        } else if (grow < prm.rows) {
+            // empty key range: the neutral state (0, -inf, 0), mpi.c:172,188
+            if (prm.out64 != nullptr) {
+                for (int c = 0; c < COLS; ++c) prm.out64[(size_t)grow * HEAD + COLS * half + c] = 0.0;
+            } else {
+                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + COLS * half;
+                for (int c = 0; c < COLS; ++c) dst[c] = 0.f;
+                if (half == 0) {
+                    prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
+                    prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // neither CTA leaves while the other may still multicast into it or arrive on its barriers
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_2cta(tmem, 512);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1166,7 +1576,7 @@ PFN_encodeTiled get_encode()
 }
 
 // 2-D bf16 row-major [rows][128] tensor, box = 64 columns x 128 rows, 128-byte swizzle, OOB rows -> 0.
-sdpa_status encode_map(CUtensorMap* map, const void* base, int rows)
+sdpa_status encode_map(CUtensorMap* map, const void* base, int rows, int box_rows = TILE)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -1175,7 +1585,7 @@ sdpa_status encode_map(CUtensorMap* map, const void* base, int rows)
     }
     const cuuint64_t dims[2] = {(cuuint64_t)HEAD, (cuuint64_t)(rows > 0 ? rows : 1)};
     const cuuint64_t strides[1] = {(cuuint64_t)HEAD * 2};
-    const cuuint32_t box[2] = {64, (cuuint32_t)TILE};
+    const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1191,6 +1601,7 @@ sdpa_status encode_map(CUtensorMap* map, const void* base, int rows)
 
 struct UmmaPlan {
     CUtensorMap map_k, map_v, map_q[2];
+    CUtensorMap map_khalf;   // K with 64-row boxes (v7: each CTA of a pair keeps 64 keys of a tile)
     int n = 0;
     bool kv_bound = false, q_bound[2] = {false, false};
     const void* q_base[2] = {nullptr, nullptr};
@@ -1224,6 +1635,7 @@ sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv
     if (plan->kv_bound && plan->k_base == K && plan->v_base == V && plan->n == n) return SDPA_OK;   // descriptors still valid
     SDPA_TRY(encode_map(&plan->map_k, K, n));
     SDPA_TRY(encode_map(&plan->map_v, V, n));
+    SDPA_TRY(encode_map(&plan->map_khalf, K, n, 64));
     plan->k_base = K;
     plan->v_base = V;
     plan->n = n;
@@ -1248,6 +1660,8 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
 // Kernel generation: v6 (cluster of two 128-row CTAs, chain-free pipeline) unless SDPA_UMMA_V6=0 asks for v5.
 static bool use_v6()
 {
+    const char* e7 = getenv("SDPA_UMMA_V7");
+    if (e7 && *e7 == '1') return true;   // v7 shares v6's grid shape (128-row CTAs in clusters of two)
     const char* e = getenv("SDPA_UMMA_V6");
     return e ? (*e != '0') : kDefaultV6;
 }
@@ -1321,6 +1735,11 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
+        const int sb7 = (int)(sizeof(SharedV7) + 1024);
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
         plan->attr_set[dev] = true;
     }
     if (!plan->guard) {
@@ -1343,7 +1762,10 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.epoch = ++plan->epoch;
     if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
     dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);                      // v5 / SAFE: 256 rows per CTA
-    const bool v6 = use_v6();
+    const char* env_v7 = getenv("SDPA_UMMA_V7");   // experimental: 2-CTA MMA variant of v6
+    const bool v7 = env_v7 && *env_v7 == '1';
+    const bool v6 = use_v6() || v7;
+    const size_t smem7 = sizeof(SharedV7) + 1024;
     const char* env_parts = getenv("SDPA_UMMA_PARTS");   // v6: softmax warpgroups per tile (2 or 4)
     const bool parts4 = env_parts ? (atoi(env_parts) == 4) : (kDefaultParts == 4);
     dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v6: 128 rows per CTA, clusters of two along x
@@ -1355,7 +1777,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
         SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
         prm.trace = dtrace;
-        if (v6 && parts4) attn_umma_kernel_v6<true, kDefaultPoly, 4><<<grid6, 640, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        if (v7) attn_umma_kernel_v7<true, 4, 2><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (v6 && parts4) attn_umma_kernel_v6<true, kDefaultPoly, 4><<<grid6, 640, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else if (v6) attn_umma_kernel_v6<true, kDefaultPoly, 2><<<grid6, 384, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
@@ -1376,6 +1799,11 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     } else if (force_safe) {
         SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
         prm.epoch = 0xffffffffu;
+    } else if (v7) {
+        if (parts4) attn_umma_kernel_v7<false, 4, 4><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (poly == 8) attn_umma_kernel_v7<false, 8, 2><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else attn_umma_kernel_v7<false, 4, 2><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        count_launch();
     } else if (v6) {
 #define SDPA_LAUNCH_V6(P, N) attn_umma_kernel_v6<false, P, N><<<grid6, 128 + 128 * N, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
         if (parts4) {
