@@ -1187,9 +1187,12 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t cta_r
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(cta_rank));
     return ra;
 }
+// Remote arrive with the default (CTA-scope release) semantics.  The data handed over is in TMEM / is
+// TMA traffic, ordered by tcgen05.fence / complete_tx; an explicit .release.cluster here costs ~1100
+// cycles per arrive (measured, profiles/r01/timeline_trace_v7_first.txt).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
