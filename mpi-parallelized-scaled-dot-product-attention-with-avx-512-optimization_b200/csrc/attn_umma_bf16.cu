@@ -1169,7 +1169,8 @@ struct __align__(1024) SharedV7 {
     uint64_t v_full[V7_VSTAGES], v_empty[V7_VSTAGES];
     uint64_t s_full[2], p_ready[2], o_done;
     uint32_t tmem_base;
-    float xchg[2][4][TILE];
+    float xchg[2][4][TILE];   // [first-tile max | final sum][group*NPARTS + part][row]
+    float mref[TILE];         // the agreed reference, handed from softmax group 0 to the others
 };
 
 // 2-SM TMA load: data into THIS CTA's shared memory, completion bytes on the LEADER CTA's mbarrier
@@ -1225,8 +1226,12 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-template <bool TRACE, int POLY, int NPARTS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * NPARTS, 1)
+// GROUPS = softmax groups ping-ponged over alternating key tiles (group g owns tiles j = g mod GROUPS and the
+// S/P buffers g): with the reference fixed by the first tile the tiles are independent, so while one
+// group sits in its fixed latencies (barrier wake-up, TMEM store drain, remote arrive) the other keeps the
+// MUFU / FMA pipes busy.  The groups' row sums are added in the epilogue.
+template <bool TRACE, int POLY, int NPARTS, int GROUPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * NPARTS * GROUPS, 1)
 attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
 {
@@ -1279,7 +1284,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
     };
 
     if (warp < 4) {
-        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        if constexpr (NPARTS * GROUPS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (num_tiles > 0) {
             if (warp == 0) {
@@ -1381,21 +1386,25 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
             }
         }
     } else {
-        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        if constexpr (NPARTS * GROUPS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         constexpr int COLS = TILE / NPARTS;            // keys (S columns) per thread: 64 or 32
+        constexpr int OCOLS = HEAD / (NPARTS * GROUPS); // output columns per thread in the epilogue
         const int sw = warp - 4;
-        const int half = sw >> 2;                      // which COLS-wide part of the row (0..NPARTS-1)
+        const int group = sw / (4 * NPARTS);           // which softmax group (owns tiles j = group mod GROUPS)
+        const int half = (sw % (4 * NPARTS)) >> 2;     // which COLS-wide part of the row (0..NPARTS-1)
+        const int gp = group * NPARTS + half;          // 0 .. NPARTS*GROUPS-1
         const int quad = warp & 3;                     // TMEM lane quadrant of this warp
         const int row_in_tile = quad * 32 + lane;
         const int grow = row_block * TILE + row_in_tile;
         if (num_tiles > 0) {
             // ================================ softmax + epilogue ==========================
             const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-            const uint32_t o_addr = tmem + lane_base + V6_O + (uint32_t)COLS * half;
+            const uint32_t o_addr = tmem + lane_base + V6_O + (uint32_t)OCOLS * gp;
             const float scale = prm.scale_log2;
             const uint64_t scale2 = pack_f32x2(scale, scale);
-            const int bar_id = 1 + quad;               // pair barrier: the two warps that share these 32 rows
+            const int bar_id = 1 + quad;               // the warps of ONE group that share these 32 rows
+            const int bar_all = 5 + quad;              // the warps of ALL groups that share these 32 rows
             const uint32_t leader_pready[2] = {map_to_cta(&sm.p_ready[0], 0), map_to_cta(&sm.p_ready[1], 0)};
 
             float m_ref = -CUDART_INF_F;
@@ -1430,14 +1439,14 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 const uint32_t s_addr = tmem + lane_base + V6_S + 128u * sb + (uint32_t)COLS * half;
                 const uint32_t p_addr = tmem + lane_base + V6_P + 64u * sb + (uint32_t)(COLS / 2) * half;
                 mbar_wait(&sm.s_full[sb], (uint32_t)(j >> 1) & 1u, 300 + sb);
-                if (quad == 0 && half < 2) stamp(half, j, 0);
+                if (quad == 0 && half == 0) stamp(group, j, 0);
                 tcgen05_fence_after();
 
                 uint32_t sr[COLS];
                 SDPA_TMEM_LD32(s_addr, sr);
                 if constexpr (COLS == 64) SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
                 tmem_wait_ld();
-                if (quad == 0 && half < 2) stamp(half, j, 1);
+                if (quad == 0 && half == 0) stamp(group, j, 1);
                 if constexpr (MASKED) {
                     const int keys_left = prm.n - (tile_begin + j) * TILE - COLS * half;
 #pragma unroll
@@ -1460,10 +1469,14 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                     m_ref = my_max;
 #pragma unroll
                     for (int p = 0; p < NPARTS; ++p) m_ref = fmaxf(m_ref, sm.xchg[0][p][row_in_tile]);
+                    if constexpr (GROUPS > 1) {
+                        if (half == 0) sm.mref[row_in_tile] = m_ref;
+                        named_barrier_sync(bar_all, 32 * NPARTS * GROUPS);   // the other groups pick the reference up
+                    }
                 }
                 // No wait is needed before overwriting P buffer sb: PV(j-2), its last reader, was issued before
                 // S(j), and the commit behind s_full(j) covers every MMA issued before it.
-                if (quad == 0 && half < 2) stamp(half, j, 2);
+                if (quad == 0 && half == 0) stamp(group, j, 2);
 
                 const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
                 uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
@@ -1483,40 +1496,44 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                         if (lane == 0) atomicExch(prm.guard, prm.epoch);   // hand the launch to the SAFE kernel
                     }
                 }
-                if (quad == 0 && half < 2) stamp(half, j, 4);
+                if (quad == 0 && half == 0) stamp(group, j, 4);
                 tmem_wait_st();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(leader_pready[sb]);   // one arrival per warp, on the leader's barrier
-                if (quad == 0 && half < 2) stamp(half, j, 5);
+                if (quad == 0 && half == 0) stamp(group, j, 5);
             };
 
             const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
-            const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
-            if (full_tiles > 0) tile_step(0, std::false_type{}, std::true_type{});
-            for (int j = 1; j < full_tiles; ++j) tile_step(j, std::false_type{}, std::false_type{});
-            if (ragged) {
-                if (num_tiles == 1) tile_step(0, std::true_type{}, std::true_type{});
-                else tile_step(num_tiles - 1, std::true_type{}, std::false_type{});
+            if (group == 0) {
+                if (ragged && num_tiles == 1) tile_step(0, std::true_type{}, std::true_type{});
+                else tile_step(0, std::false_type{}, std::true_type{});
+            } else {
+                named_barrier_sync(bar_all, 32 * NPARTS * GROUPS);   // wait for group 0's reference
+                m_ref = sm.mref[row_in_tile];
+            }
+            for (int j = (group == 0 ? GROUPS : group); j < num_tiles; j += GROUPS) {
+                if (ragged && j == num_tiles - 1) tile_step(j, std::true_type{}, std::false_type{});
+                else tile_step(j, std::false_type{}, std::false_type{});
             }
 
             // ---------------- epilogue ----------------
-            sm.xchg[1][half][row_in_tile] = lsum;
-            named_barrier_sync(bar_id, 32 * NPARTS);
+            sm.xchg[1][gp][row_in_tile] = lsum;
+            named_barrier_sync(bar_all, 32 * NPARTS * GROUPS);
             lsum = 0.f;
 #pragma unroll
-            for (int p = 0; p < NPARTS; ++p) lsum += sm.xchg[1][p][row_in_tile];
+            for (int p = 0; p < NPARTS * GROUPS; ++p) lsum += sm.xchg[1][p][row_in_tile];
             mbar_wait(&sm.o_done, 0, 320);
             tcgen05_fence_after();
             const bool valid = grow < prm.rows;
             const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
 #pragma unroll
-            for (int c0 = 0; c0 < COLS; c0 += 32) {
+            for (int c0 = 0; c0 < OCOLS; c0 += 32) {
                 uint32_t orr[32];
                 SDPA_TMEM_LD32(o_addr + c0, orr);
                 tmem_wait_ld();
                 if (valid) {
-                    const int col = COLS * half + c0;
+                    const int col = OCOLS * gp + c0;
                     if (prm.out64 != nullptr) {
                         double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + col);
 #pragma unroll
@@ -1532,18 +1549,18 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                     }
                 }
             }
-            if (valid && half == 0 && prm.out64 == nullptr) {
+            if (valid && gp == 0 && prm.out64 == nullptr) {
                 prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = m_ref * scale;
                 prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = lsum;
             }
         } else if (grow < prm.rows) {
             // empty key range: the neutral state (0, -inf, 0), mpi.c:172,188
             if (prm.out64 != nullptr) {
-                for (int c = 0; c < COLS; ++c) prm.out64[(size_t)grow * HEAD + COLS * half + c] = 0.0;
+                for (int c = 0; c < OCOLS; ++c) prm.out64[(size_t)grow * HEAD + OCOLS * gp + c] = 0.0;
             } else {
-                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + COLS * half;
-                for (int c = 0; c < COLS; ++c) dst[c] = 0.f;
-                if (half == 0) {
+                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + OCOLS * gp;
+                for (int c = 0; c < OCOLS; ++c) dst[c] = 0.f;
+                if (gp == 0) {
                     prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
                     prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
                 }
@@ -1739,10 +1756,12 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
         const int sb7 = (int)(sizeof(SharedV7) + 1024);
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 8, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
         plan->attr_set[dev] = true;
     }
     if (!plan->guard) {
@@ -1767,6 +1786,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);                      // v5 / SAFE: 256 rows per CTA
     const char* env_v7 = getenv("SDPA_UMMA_V7");   // experimental: 2-CTA MMA variant of v6
     const bool v7 = env_v7 && *env_v7 == '1';
+    const char* env_groups = getenv("SDPA_UMMA_GROUPS");   // v7: softmax groups ping-ponged over key tiles (1 or 2)
+    const bool groups2 = env_groups ? (atoi(env_groups) == 2) : true;
     const bool v6 = use_v6() || v7;
     const size_t smem7 = sizeof(SharedV7) + 1024;
     const char* env_parts = getenv("SDPA_UMMA_PARTS");   // v6: softmax warpgroups per tile (2 or 4)
@@ -1780,7 +1801,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
         SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
         prm.trace = dtrace;
-        if (v7) attn_umma_kernel_v7<true, 4, 2><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        if (v7 && groups2) attn_umma_kernel_v7<true, 4, 2, 2><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else if (v7) attn_umma_kernel_v7<true, 4, 2, 1><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else if (v6 && parts4) attn_umma_kernel_v6<true, kDefaultPoly, 4><<<grid6, 640, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else if (v6) attn_umma_kernel_v6<true, kDefaultPoly, 2><<<grid6, 384, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
@@ -1803,9 +1825,12 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
         prm.epoch = 0xffffffffu;
     } else if (v7) {
-        if (parts4) attn_umma_kernel_v7<false, 4, 4><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (poly == 8) attn_umma_kernel_v7<false, 8, 2><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else attn_umma_kernel_v7<false, 4, 2><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+#define SDPA_LAUNCH_V7(P, G) attn_umma_kernel_v7<false, P, 2, G><<<grid6, 128 + 256 * G, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
+        if (!groups2) SDPA_LAUNCH_V7(4, 1);
+        else if (poly == 0) SDPA_LAUNCH_V7(0, 2);
+        else if (poly == 8) SDPA_LAUNCH_V7(8, 2);
+        else SDPA_LAUNCH_V7(4, 2);
+#undef SDPA_LAUNCH_V7
         count_launch();
     } else if (v6) {
 #define SDPA_LAUNCH_V6(P, N) attn_umma_kernel_v6<false, P, N><<<grid6, 128 + 128 * N, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
