@@ -1167,7 +1167,7 @@ struct __align__(1024) SharedV7 {
     uint64_t q_full;
     uint64_t k_full[V7_KSTAGES], k_empty[V7_KSTAGES];
     uint64_t v_full[V7_VSTAGES], v_empty[V7_VSTAGES];
-    uint64_t s_full[2], p_ready[2], o_done;
+    uint64_t s_full[2], p_ready[2], s_free[2], pv_done[2], o_done;
     uint32_t tmem_base;
     float xchg[2][4][TILE];   // [first-tile max | final sum][group*NPARTS + part][row]
     float mref[TILE];         // the agreed reference, handed from softmax group 0 to the others
@@ -1259,6 +1259,8 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
         for (int i = 0; i < 2; ++i) {
             mbar_init(&sm.s_full[i], 1);
             mbar_init(&sm.p_ready[i], 2 * 4 * NPARTS);   // leader's copy: one arrival per softmax warp of BOTH CTAs
+            mbar_init(&sm.s_free[i], 2 * 4 * NPARTS);    // leader's copy: S buffer i has been read into registers
+            mbar_init(&sm.pv_done[i], 1);                // both CTAs: P buffer i may be overwritten
         }
         for (int i = 0; i < V7_KSTAGES; ++i) {
             mbar_init(&sm.k_full[i], 2);
@@ -1366,6 +1368,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
 #pragma unroll
                         for (int kk = 0; kk < TILE / 16; ++kk)
                             umma_ts_2cta(d, a + 8u * kk, b0 + (uint64_t)((kk * 2048u) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit_2cta(&sm.pv_done[pb], both);
                         umma_commit_2cta(&sm.v_empty[vs], both);
                         if (last) umma_commit_2cta(&sm.o_done, both);
                     }
@@ -1377,9 +1380,14 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 if (num_tiles > 1) issue_s(1);
                 for (int j = 0; j < num_tiles; ++j) {
                     stamp(4, j, 0);
-                    issue_pv(j, j + 1 == num_tiles);
+                    if (j + 2 < num_tiles) {
+                        // S(j+2) reuses the buffer of S(j): it only needs S(j) to be in the softmax registers
+                        // (s_free), NOT P(j) -- issuing it before PV(j) is what breaks the per-tile chain.
+                        mbar_wait(&sm.s_free[j & 1], (uint32_t)(j >> 1) & 1u, 214 + (j & 1));
+                        issue_s(j + 2);
+                    }
                     stamp(4, j, 2);
-                    if (j + 2 < num_tiles) issue_s(j + 2);
+                    issue_pv(j, j + 1 == num_tiles);
                     stamp(4, j, 3);
                 }
                 }
@@ -1406,6 +1414,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
             const int bar_id = 1 + quad;               // the warps of ONE group that share these 32 rows
             const int bar_all = 5 + quad;              // the warps of ALL groups that share these 32 rows
             const uint32_t leader_pready[2] = {map_to_cta(&sm.p_ready[0], 0), map_to_cta(&sm.p_ready[1], 0)};
+            const uint32_t leader_sfree[2] = {map_to_cta(&sm.s_free[0], 0), map_to_cta(&sm.s_free[1], 0)};
 
             float m_ref = -CUDART_INF_F;
             float lsum = 0.f;
@@ -1446,6 +1455,9 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 SDPA_TMEM_LD32(s_addr, sr);
                 if constexpr (COLS == 64) SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
                 tmem_wait_ld();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_sfree[sb]);   // S buffer sb may be overwritten by S(j+2)
                 if (quad == 0 && half == 0) stamp(group, j, 1);
                 if constexpr (MASKED) {
                     const int keys_left = prm.n - (tile_begin + j) * TILE - COLS * half;
@@ -1480,12 +1492,13 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
 
                 const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
                 uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+                uint32_t pr[COLS / 2];   // the packed bf16 P of the whole part; stored at the end, once PV(j-2) has left the buffer
 #pragma unroll
-                for (int ch = 0; ch < COLS / 16; ++ch) {
-                    uint32_t pr[8];
-                    exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr);
-                    SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
-                }
+                for (int ch = 0; ch < COLS / 16; ++ch) exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr + 8 * ch);
+                if (j >= 2) mbar_wait(&sm.pv_done[sb], (uint32_t)((j >> 1) - 1) & 1u, 310 + sb);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < COLS / 16; ++ch) SDPA_TMEM_ST8(p_addr + 8 * ch, (pr + 8 * ch));
                 float a0, a1, a2, a3;
                 unpack_f32x2(acc0, a0, a1);
                 unpack_f32x2(acc1, a2, a3);
