@@ -1339,7 +1339,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
 
                 auto issue_s = [&](int j) {
                     const int sb = j & 1, ks = j % V7_KSTAGES;
-                    mbar_wait(&sm.k_full[ks], (uint32_t)(j / V7_KSTAGES) & 1u, 200 + ks);
+                    mbar_wait(&sm.k_full[ks], (uint32_t)(j / V7_KSTAGES) & 1u, 200 + ks);   // (already tested by the scheduler below)
                     tcgen05_fence_after();
                     if (elect_one_sync()) {
                         const uint64_t b0 = dkk[ks];
@@ -1378,17 +1378,39 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 mbar_wait(&sm.q_full, 0, 201);
                 issue_s(0);
                 if (num_tiles > 1) issue_s(1);
-                for (int j = 0; j < num_tiles; ++j) {
-                    stamp(4, j, 0);
-                    if (j + 2 < num_tiles) {
-                        // S(j+2) reuses the buffer of S(j): it only needs S(j) to be in the softmax registers
-                        // (s_free), NOT P(j) -- issuing it before PV(j) is what breaks the per-tile chain.
-                        mbar_wait(&sm.s_free[j & 1], (uint32_t)(j >> 1) & 1u, 214 + (j & 1));
-                        issue_s(j + 2);
+                // Two independent in-order streams share this thread: S(js) needs {s_free(js-2), K(js)}, PV(jp) needs
+                // {p_ready(jp), V(jp)}.  Whichever is ready is issued, so a group still busy with tile jp never delays
+                // the other group's next S (a fixed S,PV,S,PV order would).
+                int js = 2, jp = 0;
+                const long long t_start = clock64();
+                while (jp < num_tiles) {
+                    bool progressed = false;
+                    if (js < num_tiles) {
+                        bool ok = mbar_try_wait(&sm.s_free[js & 1], (uint32_t)((js - 2) >> 1) & 1u) &&
+                                  mbar_try_wait(&sm.k_full[js % V7_KSTAGES], (uint32_t)(js / V7_KSTAGES) & 1u);
+                        ok = __all_sync(0xffffffffu, ok);
+                        if (ok) {
+                            stamp(4, js - 2, 2);
+                            issue_s(js);
+                            ++js;
+                            progressed = true;
+                        }
                     }
-                    stamp(4, j, 2);
-                    issue_pv(j, j + 1 == num_tiles);
-                    stamp(4, j, 3);
+                    {
+                        bool ok = mbar_try_wait(&sm.p_ready[jp & 1], (uint32_t)(jp >> 1) & 1u) &&
+                                  mbar_try_wait(&sm.v_full[jp % V7_VSTAGES], (uint32_t)(jp / V7_VSTAGES) & 1u);
+                        ok = __all_sync(0xffffffffu, ok);
+                        if (ok) {
+                            issue_pv(jp, jp + 1 == num_tiles);
+                            stamp(4, jp, 3);
+                            ++jp;
+                            progressed = true;
+                        }
+                    }
+                    if (!progressed && clock64() - t_start > 40000000000LL) {
+                        if (lane == 0) printf("sdpa_b200: v7 MMA scheduler timeout block=(%d,%d) js=%d jp=%d\n", blockIdx.x, blockIdx.y, js, jp);
+                        __trap();
+                    }
                 }
                 }
             }
