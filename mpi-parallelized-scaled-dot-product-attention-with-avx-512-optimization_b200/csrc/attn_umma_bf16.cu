@@ -100,6 +100,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a hardware time slice before reporting failure,
+// which a scheduler polling several barriers cannot afford).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag)
 {
@@ -1386,8 +1400,8 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 while (jp < num_tiles) {
                     bool progressed = false;
                     if (js < num_tiles) {
-                        bool ok = mbar_try_wait(&sm.s_free[js & 1], (uint32_t)((js - 2) >> 1) & 1u) &&
-                                  mbar_try_wait(&sm.k_full[js % V7_KSTAGES], (uint32_t)(js / V7_KSTAGES) & 1u);
+                        bool ok = mbar_test_wait(&sm.s_free[js & 1], (uint32_t)((js - 2) >> 1) & 1u) &&
+                                  mbar_test_wait(&sm.k_full[js % V7_KSTAGES], (uint32_t)(js / V7_KSTAGES) & 1u);
                         ok = __all_sync(0xffffffffu, ok);
                         if (ok) {
                             stamp(4, js - 2, 2);
@@ -1397,8 +1411,8 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                         }
                     }
                     {
-                        bool ok = mbar_try_wait(&sm.p_ready[jp & 1], (uint32_t)(jp >> 1) & 1u) &&
-                                  mbar_try_wait(&sm.v_full[jp % V7_VSTAGES], (uint32_t)(jp / V7_VSTAGES) & 1u);
+                        bool ok = mbar_test_wait(&sm.p_ready[jp & 1], (uint32_t)(jp >> 1) & 1u) &&
+                                  mbar_test_wait(&sm.v_full[jp % V7_VSTAGES], (uint32_t)(jp / V7_VSTAGES) & 1u);
                         ok = __all_sync(0xffffffffu, ok);
                         if (ok) {
                             issue_pv(jp, jp + 1 == num_tiles);
