@@ -56,7 +56,7 @@ constexpr float kLazyThreshold = 8.0f;                // safe mode: rescale O on
 constexpr float kGuardThreshold = 64.0f;              // fast mode: exponents beyond 2^64 hand the launch to the safe kernel
 constexpr int kDefaultParts = 2;                      // v6: softmax warpgroups per tile
 constexpr bool kDefaultV6 = false;                    // flipped once v6 is validated on hardware
-constexpr int kDefaultPoly = 4;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
+constexpr int kDefaultPoly = 0;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
 
 constexpr uint32_t TMEM_S = 0;    // + 128 * tile
 constexpr uint32_t TMEM_O = 256;  // + 128 * tile
@@ -94,20 +94,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Non-blocking probe (try_wait may suspend the thread for a hardware time slice before reporting failure,
-// which a scheduler polling several barriers cannot afford).
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
@@ -1392,39 +1378,18 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 mbar_wait(&sm.q_full, 0, 201);
                 issue_s(0);
                 if (num_tiles > 1) issue_s(1);
-                // Two independent in-order streams share this thread: S(js) needs {s_free(js-2), K(js)}, PV(jp) needs
-                // {p_ready(jp), V(jp)}.  Whichever is ready is issued, so a group still busy with tile jp never delays
-                // the other group's next S (a fixed S,PV,S,PV order would).
-                int js = 2, jp = 0;
-                const long long t_start = clock64();
-                while (jp < num_tiles) {
-                    bool progressed = false;
-                    if (js < num_tiles) {
-                        bool ok = mbar_test_wait(&sm.s_free[js & 1], (uint32_t)((js - 2) >> 1) & 1u) &&
-                                  mbar_test_wait(&sm.k_full[js % V7_KSTAGES], (uint32_t)(js / V7_KSTAGES) & 1u);
-                        ok = __all_sync(0xffffffffu, ok);
-                        if (ok) {
-                            stamp(4, js - 2, 2);
-                            issue_s(js);
-                            ++js;
-                            progressed = true;
-                        }
+                // Fixed order per tile: S(j+2) as soon as S(j) sits in the softmax registers (s_free), then PV(j) once
+                // P(j) is ready.  (A scheduler issuing "whichever stream is ready" was measured slower -- polling two
+                // barriers costs more than the occasional head-of-line wait: profiles/r01/sweep_v7_3_testwait_scheduler.txt.)
+                for (int j = 0; j < num_tiles; ++j) {
+                    stamp(4, j, 0);
+                    if (j + 2 < num_tiles) {
+                        mbar_wait(&sm.s_free[j & 1], (uint32_t)(j >> 1) & 1u, 214 + (j & 1));
+                        issue_s(j + 2);
                     }
-                    {
-                        bool ok = mbar_test_wait(&sm.p_ready[jp & 1], (uint32_t)(jp >> 1) & 1u) &&
-                                  mbar_test_wait(&sm.v_full[jp % V7_VSTAGES], (uint32_t)(jp / V7_VSTAGES) & 1u);
-                        ok = __all_sync(0xffffffffu, ok);
-                        if (ok) {
-                            issue_pv(jp, jp + 1 == num_tiles);
-                            stamp(4, jp, 3);
-                            ++jp;
-                            progressed = true;
-                        }
-                    }
-                    if (!progressed && clock64() - t_start > 40000000000LL) {
-                        if (lane == 0) printf("sdpa_b200: v7 MMA scheduler timeout block=(%d,%d) js=%d jp=%d\n", blockIdx.x, blockIdx.y, js, jp);
-                        __trap();
-                    }
+                    stamp(4, j, 2);
+                    issue_pv(j, j + 1 == num_tiles);
+                    stamp(4, j, 3);
                 }
                 }
             }
@@ -1730,8 +1695,8 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
 static bool use_v6()
 {
     const char* e7 = getenv("SDPA_UMMA_V7");
-    if (e7 && *e7 == '1') return true;   // v7 shares v6's grid shape (128-row CTAs in clusters of two)
     const char* e = getenv("SDPA_UMMA_V6");
+    if (e7 ? (*e7 == '1') : (e == nullptr)) return true;   // v7 (default) shares v6's grid shape (128-row CTAs in clusters of two)
     return e ? (*e != '0') : kDefaultV6;
 }
 
@@ -1833,8 +1798,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.epoch = ++plan->epoch;
     if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
     dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);                      // v5 / SAFE: 256 rows per CTA
-    const char* env_v7 = getenv("SDPA_UMMA_V7");   // experimental: 2-CTA MMA variant of v6
-    const bool v7 = env_v7 && *env_v7 == '1';
+    const char* env_v7 = getenv("SDPA_UMMA_V7");   // the 2-CTA kernel is the default; SDPA_UMMA_V7=0 selects v5 (or v6 with SDPA_UMMA_V6=1)
+    const bool v7 = env_v7 ? (*env_v7 == '1') : (getenv("SDPA_UMMA_V6") == nullptr);
     const char* env_groups = getenv("SDPA_UMMA_GROUPS");   // v7: softmax groups ping-ponged over key tiles (1 or 2)
     const bool groups2 = env_groups ? (atoi(env_groups) == 2) : true;
     const bool v6 = use_v6() || v7;

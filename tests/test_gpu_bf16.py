@@ -113,9 +113,12 @@ def test_bf16_overflow_guard_hands_over_to_safe_kernel(sdpa, oracle):
         np.testing.assert_allclose(got, ref_b, rtol=0, atol=2e-2)
 
 
-@pytest.mark.parametrize("env", [{"SDPA_UMMA_SAFE": "1"}, {"SDPA_UMMA_POLY": "0"}, {"SDPA_UMMA_POLY": "8"}])
+@pytest.mark.parametrize("env", [{"SDPA_UMMA_SAFE": "1"}, {"SDPA_UMMA_POLY": "4"}, {"SDPA_UMMA_POLY": "8"}, {"SDPA_UMMA_GROUPS": "1"},
+                                 {"SDPA_UMMA_V7": "0"}, {"SDPA_UMMA_V7": "0", "SDPA_UMMA_POLY": "4"}, {"SDPA_UMMA_V7": "0", "SDPA_UMMA_CHUNK": "0"},
+                                 {"SDPA_UMMA_V6": "1"}, {"SDPA_UMMA_V6": "1", "SDPA_UMMA_PARTS": "4"}])
 def test_bf16_kernel_variants(sdpa, oracle, monkeypatch, env):
-    """The safe kernel alone, and the fast kernel with 0 / 8 of every 16 exponentials on the FMA pipe."""
+    """Every kernel generation behind the same contract: the default is v7 (2-CTA MMA, two softmax groups);
+    v5 (SDPA_UMMA_V7=0), v6 (SDPA_UMMA_V6=1), the SAFE kernel alone, and the exp2-polynomial variants."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     Q, K, V, got = _run(sdpa, oracle, 600, 2500, seed=21)
