@@ -1,6 +1,16 @@
 // attn_umma_bf16.cu -- fused QK^T -> online softmax -> .V on the 5th-generation tensor cores
 // (tcgen05.mma, accumulators in TMEM, operands staged by TMA), bf16 operands / fp32 accumulate.
 //
+// Three kernel generations live here behind one launcher (launch_attn_umma); all produce the same
+// partial softmax state and pass the same parity tests:
+//   attn_umma_kernel_v7  DEFAULT.  Cluster of two CTAs forming one M=256 tcgen05.mma.cta_group::2 (each CTA keeps
+//                        half of every K/V tile), S and P double-buffered in TMEM (no MMA waits for the softmax of
+//                        its own S), two softmax groups ping-ponged over alternating key tiles.  See its banner.
+//   attn_umma_kernel     v5 (SDPA_UMMA_V7=0): one CTA, two Q tiles ping-ponged, P aliases S.  Its SAFE variant is
+//                        the overflow-guard fallback of every generation.  Described right below.
+//   attn_umma_kernel_v6  (SDPA_UMMA_V6=1) v7's pipeline without the 2-CTA MMA (K/V multicast instead); kept as the
+//                        measured stepping stone (profiles/README.md).
+//
 // The B200 counterpart of online_softmax_attention (attention-mpi.c:168-189): where the
 // reference does one AVX-512 dot (dot_avx512, :103-121) and one axpy (axpy_avx512, :123-140)
 // per (query, key) pair, this kernel does two 128x128x128 tensor-core GEMMs per
