@@ -291,14 +291,16 @@ def run_ours(args) -> None:
 
     def timed(fn, steps, collect=None):
         barrier()
+        if collect is not None:
+            ctx.accumulated_timings(reset=True)   # stage events are queried once, after the loop
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
-            if collect is not None:
-                collect(ctx.last_timings())
         e1.record()
         barrier()
+        if collect is not None:
+            collect(ctx.accumulated_timings(reset=True))
         return parallel.max_over_ranks(e0.elapsed_time(e1))  # ms, max over ranks
 
     W, K = max(3, args.warmup), max(1, args.steps)
@@ -317,6 +319,7 @@ def run_ours(args) -> None:
     launches0 = sdpa_b200.launch_count()
     with ClockSampler(local_rank) as clk:
         ms_dev = timed(step_device, K, collect)
+        launches = sdpa_b200.launch_count() - launches0   # kernels launched inside the timed region only
         # The timed region is a few milliseconds: keep the identical load running so the sampler sees it.
         # Every step is collective across ranks, so the extra steps are a COUNT derived from the
         # max-reduced time (identical on all ranks), never a per-rank wall-clock loop.
@@ -324,7 +327,6 @@ def run_ours(args) -> None:
         for _ in range(extra):
             step_device()
         barrier()
-    launches = sdpa_b200.launch_count() - launches0
     clocks = clk.summary()
     kernel_name = ctx.last_kernel()
 

@@ -155,6 +155,9 @@ sdpa_status sdpa_online_softmax_partials(sdpa_ctx* ctx, int local, const float* 
  * local GPUs: [0] total, [1] casts, [2] fused attention kernel(s),
  * [3] merge + collectives, [4] fused-kernel launches, [5] all kernel launches. */
 sdpa_status sdpa_last_timings(sdpa_ctx* ctx, float* out6);
+/* The same stage times summed over every sdpa_attention_* call since the last reset; the event queries happen
+ * here, not inside the calls.  out6: [0] total, [1] casts, [2] fused, [3] merge (ms), [4] fused launches, [5] calls. */
+sdpa_status sdpa_accumulated_timings(sdpa_ctx* ctx, double* out6, int reset);
 /* Which kernel the last call used: "f32_simt" | "bf16_umma". */
 const char* sdpa_last_kernel(sdpa_ctx* ctx);
 

@@ -157,8 +157,12 @@ struct Shard {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
     // timing event pool: pairs around casts [0], fused kernel [1], merge+collectives [2]
-    std::vector<cudaEvent_t> tev[3];
-    size_t tev_used[3] = {0, 0, 0};
+    // [3] = the whole call.  Pairs are appended call after call and only turned into numbers when somebody asks
+    // (sdpa_last_timings / sdpa_accumulated_timings): querying ~8 events costs ~11 us of host time per call.
+    std::vector<cudaEvent_t> tev[4];
+    size_t tev_used[4] = {0, 0, 0, 0};
+    size_t tev_last[4] = {0, 0, 0, 0};      // where the last call's pairs start
+    double acc_ms[4] = {0, 0, 0, 0};        // folded (already queried) time since the last reset
     UmmaPlan* plan = nullptr;
     int sm_count = 148;
 };
@@ -177,6 +181,8 @@ struct sdpa_ctx {
     int q_batch = 0;
     bool peer_ok = false;
     float last_timing[6] = {0, 0, 0, 0, 0, 0};
+    bool last_timing_valid = true;          // false: last_timing[0..3] still have to be computed from the event pairs
+    double acc_fused_launches = 0, acc_calls = 0;
     const char* last_kernel = "none";
     // device-side exchange across processes (one GPU per process): state buffers + flags shared through CUDA IPC
     struct Ipc {
@@ -221,6 +227,32 @@ static double host_now_us()
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+// Turn the pending event pairs [from, used) of category w into milliseconds.
+static sdpa_status sum_pairs(Shard& s, int w, size_t from, double* out)
+{
+    double acc = 0.0;
+    for (size_t k = from; k + 1 < s.tev_used[w]; k += 2) {
+        float ms = 0.f;
+        SDPA_CUDA_TRY(cudaEventElapsedTime(&ms, s.tev[w][k], s.tev[w][k + 1]));
+        acc += ms;
+    }
+    *out = acc;
+    return SDPA_OK;
+}
+// Fold everything recorded so far into acc_ms and recycle the events (all recorded work must be complete).
+static sdpa_status fold_timings(Shard& s)
+{
+    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    for (int w = 0; w < 4; ++w) {
+        double ms = 0.0;
+        SDPA_TRY(sum_pairs(s, w, 0, &ms));
+        s.acc_ms[w] += ms;
+        s.tev_used[w] = 0;
+        s.tev_last[w] = 0;
+    }
+    return SDPA_OK;
 }
 
 static size_t elem_size(int prec) { return prec == SDPA_PREC_BF16 ? 2 : 4; }
@@ -282,7 +314,7 @@ static void shard_destroy(Shard& s, const NcclApi* api)
                          s.ev_join[0], s.ev_join[1], s.ev_join[2]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
-    for (int w = 0; w < 3; ++w)
+    for (int w = 0; w < 4; ++w)
         for (cudaEvent_t e : s.tev[w]) cudaEventDestroy(e);
     cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out};
     for (cudaStream_t st : sts)
@@ -544,7 +576,10 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     }
     ctx->last_kernel = ctx->prec == SDPA_PREC_BF16 ? "bf16_umma" : "f32_simt";
     for (float& t : ctx->last_timing) t = 0.f;
-    if (m == 0) return SDPA_OK;
+    if (m == 0) {
+        ctx->last_timing_valid = true;   // nothing ran: all-zero stage times
+        return SDPA_OK;
+    }
 
     static const bool host_prof = getenv("SDPA_HOST_PROFILE") != nullptr;
     const double hp0 = host_prof ? host_now_us() : 0.0;
@@ -565,10 +600,15 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         Shard& s = ctx->shards[i];
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         SDPA_TRY(reserve_batch_buffers(ctx, s, B, splits, s.grank == 0));
-        for (int w = 0; w < 3; ++w) s.tev_used[w] = 0;
+        if (s.tev_used[1] > 1024) {   // long unmeasured loops: keep the pools bounded (previous calls are complete)
+            if (!ctx->last_timing_valid) ctx->last_timing_valid = true;   // the last call's detail is dropped with the fold
+            SDPA_TRY(fold_timings(s));
+        }
+        for (int w = 0; w < 4; ++w) s.tev_last[w] = s.tev_used[w];
         if (ctx->prec == SDPA_PREC_BF16)
             for (int b = 0; b < 2; ++b)
                 SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk));
+        SDPA_TRY(time_begin(s, 3, s.s_compute));
         SDPA_CUDA_TRY(cudaEventRecord(s.ev_begin, s.s_compute));
         // the other streams start after ev_begin so that "total" brackets everything
         SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_begin, 0));
@@ -830,7 +870,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             SDPA_CUDA_TRY(cudaEventRecord(s.ev_join[j], side[j]));
             SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_join[j], 0));
         }
-        SDPA_CUDA_TRY(cudaEventRecord(s.ev_end, s.s_compute));
+        SDPA_TRY(time_end(s, 3, s.s_compute));
     }
     for (int i = 0; i < L; ++i) {
         Shard& s = ctx->shards[i];
@@ -839,28 +879,13 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     }
 
     const double hp2 = host_prof ? host_now_us() : 0.0;
-    // ---- timings (max over local shards) --------------------------------------------------------
-    for (int i = 0; i < L; ++i) {
-        Shard& s = ctx->shards[i];
-        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
-        float total = 0.f;
-        SDPA_CUDA_TRY(cudaEventElapsedTime(&total, s.ev_begin, s.ev_end));
-        float acc[3] = {0.f, 0.f, 0.f};
-        for (int w = 0; w < 3; ++w)
-            for (size_t k = 0; k + 1 < s.tev_used[w]; k += 2) {
-                float ms = 0.f;
-                SDPA_CUDA_TRY(cudaEventElapsedTime(&ms, s.tev[w][k], s.tev[w][k + 1]));
-                acc[w] += ms;
-            }
-        ctx->last_timing[0] = std::max(ctx->last_timing[0], total);
-        ctx->last_timing[1] = std::max(ctx->last_timing[1], acc[0]);
-        ctx->last_timing[2] = std::max(ctx->last_timing[2], acc[1]);
-        ctx->last_timing[3] = std::max(ctx->last_timing[3], acc[2]);
-    }
+    ctx->last_timing_valid = false;   // evaluated lazily by sdpa_last_timings / sdpa_accumulated_timings
+    ctx->acc_fused_launches += fused_launches;
+    ctx->acc_calls += 1;
     if (host_prof) {
         const double hp3 = host_now_us();
         fprintf(stderr, "sdpa host profile: enqueue %.1f us, join+sync %.1f us, event queries %.1f us (device total %.1f us)\n",
-                hp1 - hp0, hp2 - hp1, hp3 - hp2, ctx->last_timing[0] * 1e3);
+                hp1 - hp0, hp2 - hp1, hp3 - hp2, 0.0);
     }
     ctx->last_timing[4] = (float)fused_launches;
     (void)all_launches;
@@ -1236,7 +1261,43 @@ sdpa_status sdpa_last_timings(sdpa_ctx* ctx, float* out6)
         set_error("sdpa_last_timings: bad arguments");
         return SDPA_ERR_INVALID;
     }
+    if (!ctx->last_timing_valid) {
+        for (int k = 0; k < 4; ++k) ctx->last_timing[k] = 0.f;
+        for (Shard& s : ctx->shards) {
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            const int slot[4] = {3, 0, 1, 2};   // out[0] total, [1] casts, [2] fused, [3] merge
+            for (int k = 0; k < 4; ++k) {
+                double ms = 0.0;
+                SDPA_TRY(sum_pairs(s, slot[k], s.tev_last[slot[k]], &ms));
+                ctx->last_timing[k] = std::max(ctx->last_timing[k], (float)ms);
+            }
+        }
+        ctx->last_timing_valid = true;
+    }
     memcpy(out6, ctx->last_timing, sizeof(ctx->last_timing));
+    return SDPA_OK;
+}
+
+/* Device time summed over every sdpa_attention_* call since the last reset, evaluated now (no host work is spent
+ * on timing inside the calls): out[0] total, [1] casts, [2] fused kernel(s), [3] merge, [4] fused launches, [5] calls. */
+sdpa_status sdpa_accumulated_timings(sdpa_ctx* ctx, double* out6, int reset)
+{
+    if (!ctx || !out6) {
+        set_error("sdpa_accumulated_timings: bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    float last[6];
+    SDPA_TRY(sdpa_last_timings(ctx, last));   // keep the last call's detail before the events are recycled
+    for (int k = 0; k < 6; ++k) out6[k] = 0.0;
+    for (Shard& s : ctx->shards) {
+        SDPA_TRY(fold_timings(s));
+        const int slot[4] = {3, 0, 1, 2};
+        for (int k = 0; k < 4; ++k) out6[k] = std::max(out6[k], s.acc_ms[slot[k]]);
+        if (reset) for (int w = 0; w < 4; ++w) s.acc_ms[w] = 0.0;
+    }
+    out6[4] = ctx->acc_fused_launches;
+    out6[5] = ctx->acc_calls;
+    if (reset) ctx->acc_fused_launches = ctx->acc_calls = 0;
     return SDPA_OK;
 }
 

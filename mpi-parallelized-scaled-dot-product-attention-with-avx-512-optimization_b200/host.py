@@ -79,6 +79,7 @@ ABI = {
     "sdpa_scatter_attention": (ctypes.c_int, [_V, _V, _V, _V, _V] + [ctypes.c_int] * 4),
     "sdpa_online_softmax_partials": (ctypes.c_int, [_V, ctypes.c_int, _V, ctypes.c_int, _V, _V, _V]),
     "sdpa_last_timings": (ctypes.c_int, [_V, _fp]),
+    "sdpa_accumulated_timings": (ctypes.c_int, [_V, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
     "sdpa_last_kernel": (ctypes.c_char_p, [_V]),
     "sdpa_cvt_d2f": (ctypes.c_int, [_V, _V, ctypes.c_size_t, _V]),
     "sdpa_cvt_f2d": (ctypes.c_int, [_V, _V, ctypes.c_size_t, _V]),
@@ -333,6 +334,13 @@ class Context:
         out = (ctypes.c_float * 6)()
         _check(lib().sdpa_last_timings(self._h, out), "sdpa_last_timings")
         keys = ("total_ms", "cast_ms", "fused_ms", "merge_ms", "fused_launches", "launches")
+        return dict(zip(keys, [float(x) for x in out]))
+
+    def accumulated_timings(self, reset: bool = False) -> dict:
+        """Stage times summed over all attention calls since the last reset (queried now, not inside the calls)."""
+        out = (ctypes.c_double * 6)()
+        _check(lib().sdpa_accumulated_timings(self._h, out, 1 if reset else 0), "sdpa_accumulated_timings")
+        keys = ("total_ms", "cast_ms", "fused_ms", "merge_ms", "fused_launches", "calls")
         return dict(zip(keys, [float(x) for x in out]))
 
     def last_kernel(self) -> str:

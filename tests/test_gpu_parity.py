@@ -156,6 +156,29 @@ def test_device_resident_api(sdpa, oracle, torch_cuda):
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=F32_ATOL)
 
 
+def test_accumulated_stage_timings(sdpa, oracle, torch_cuda):
+    """Stage times are recorded per call and only evaluated on demand; the accumulated view
+    sums every call since the last reset (bench.py reads it once after its timed loop)."""
+    Q, K, V = oracle.make_inputs(512, 2048, 128, 128, seed=5)
+    with sdpa.Context(precision="bf16") as ctx:
+        ctx.load_kv_host_full(K, V)
+        ctx.accumulated_timings(reset=True)
+        for _ in range(3):
+            ctx.attention_host(Q)
+        last = ctx.last_timings()
+        acc = ctx.accumulated_timings(reset=True)
+        assert acc["calls"] == 3 and acc["fused_launches"] == 3 * last["fused_launches"]
+        assert 0 < last["fused_ms"] <= last["total_ms"]
+        assert acc["fused_ms"] >= last["fused_ms"] and acc["total_ms"] >= acc["fused_ms"] > 0
+        again = ctx.accumulated_timings()
+        assert again["calls"] == 0 and again["total_ms"] == 0
+        # many calls without a query: the event pools are folded, totals stay consistent
+        for _ in range(700):
+            ctx.attention_host(Q[:128])
+        acc = ctx.accumulated_timings(reset=True)
+        assert acc["calls"] == 700 and acc["total_ms"] >= acc["fused_ms"] > 0
+
+
 def test_full_size_c2_properties(sdpa, oracle, torch_cuda):
     """BASELINE c2 (m=n=4096, d=128, fp32) at full size: a seeded row subset against the fp64
     oracle plus size-independent properties (rows are convex combinations of V rows; softmax
