@@ -55,38 +55,112 @@ def load_peaks():
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (one persistent
-    `nvidia-smi -lms 20` process; a 20-step region lasts only a few milliseconds, so bench.py keeps
-    the same load running under the sampler for about a second more and says so in `clocks.window`)."""
+    """Samples SM clock, power and clock-event reasons of this rank's GPU while the timed region runs.
+
+    NVML is read in-process (pynvml, the source nvidia-smi prints) from a thread every 10 ms; `start()` does
+    the NVML attach BEFORE the warm-up so that no driver initialisation overlaps the timed steps (eight
+    `nvidia-smi` processes attaching to an 8-GPU box during the timed region stretched the steps 3x).  A 20-step
+    region lasts a few milliseconds, so bench.py keeps the same load running under the sampler for about a
+    second more and says so in `clocks.window`.  Falls back to one `nvidia-smi -lms 100` on rank 0."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str | None = None, allow_subprocess: bool = True):
         self.gpu = gpu_index
-        self.rows = []
+        self.uuid = uuid
+        self.allow_subprocess = allow_subprocess
+        self.rows = []          # (sm_mhz, max_mhz, power_w, [reason names])
         self.proc = None
         self._thr = None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._nvml = None
+        self._handle = None
+        self.source = "none"
 
-    def _reader(self):
-        for line in self.proc.stdout:
-            parts = [x.strip() for x in line.strip().split(",")]
-            if len(parts) >= 7:
-                self.rows.append(parts)
-
-    def __enter__(self):
+    # -- setup (untimed) ----------------------------------------------------------------------
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in (self.uuid, "GPU-" + self.uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self._nvml, self._handle, self.source = pynvml, h, "nvml"
+            self._thr = threading.Thread(target=self._poll_nvml, daemon=True)
+            self._thr.start()
+            return self
+        except Exception:
+            self._nvml = None
         exe = shutil.which("nvidia-smi")
-        if exe:
+        if exe and self.allow_subprocess:
             try:
                 self.proc = subprocess.Popen([exe, f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                              "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-                self._thr = threading.Thread(target=self._reader, daemon=True)
+                                              "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+                self._thr = threading.Thread(target=self._read_smi, daemon=True)
                 self._thr.start()
+                t0 = time.time()
+                while not self.rows and time.time() - t0 < 15.0:   # wait for the attach to finish
+                    time.sleep(0.05)
             except Exception:
                 self.proc = None
         return self
 
+    def _poll_nvml(self):
+        nv, h = self._nvml, self._handle
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = 0.0
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    clk = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    self.rows.append((clk, mx, pw, [n for n, bit in names if mask & bit]))
+                except Exception:
+                    pass
+            self._stop.wait(0.010)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) >= 7:
+                try:
+                    row = (float(parts[0]), float(parts[1]), float(parts[2]),
+                           [n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active")])
+                except Exception:
+                    continue
+                if self._active.is_set() or not self.rows:
+                    self.rows.append(row)
+
+    # -- the sampled window -------------------------------------------------------------------
+    def __enter__(self):
+        if self._thr is None:
+            self.start()
+        self.rows = self.rows[:0] if self.source == "nvml" else self.rows[-1:]
+        self._active.set()
+        return self
+
     def __exit__(self, *exc):
+        self._active.clear()
+
+    def close(self):
+        self._stop.set()
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -95,26 +169,24 @@ class ClockSampler:
                 self.proc.kill()
         if self._thr:
             self._thr.join(timeout=5)
+        if self._nvml is not None:
+            try:
+                self._nvml.nvmlShutdown()
+            except Exception:
+                pass
 
     def summary(self):
         sm, mx, power, reasons = [], 0, [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                clk, pw = float(r[0]), float(r[2])
-                mx = max(mx, float(r[1]))
-            except Exception:
-                continue
+        for clk, cmax, pw, why in self.rows:
+            mx = max(mx, cmax)
             if pw < 300.0:      # idle sample (before the first launch / after the last): not "under load"
                 continue
             sm.append(clk)
             power.append(pw)
-            for name, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+            reasons.update(why)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None,
+                "samples": len(sm), "power_w_max": max(power) if power else None, "source": self.source,
                 "window": "timed region + ~1 s of the same steps (samples with power draw >= 300 W)"}
 
 
@@ -278,7 +350,8 @@ def run_ours(args) -> None:
     kd, vd, qd, rd = [Kd.data_ptr()], [Vd.data_ptr()], [Qd.data_ptr()], (Rd.data_ptr() if Rd is not None else None)
 
     def step_device():
-        ctx.attention_device_full(kd, vd, [n_local], DK, DV, qd, rd, m)
+        # queued pass (sdpa_enqueue_device_full): K steps run back to back in stream order, one wait at the end
+        ctx.attention_device_full(kd, vd, [n_local], DK, DV, qd, rd, m, blocking=False)
 
     def step_host():
         ctx.load_kv_host_ptrs([Kh.data_ptr()], [Vh.data_ptr()], [n_local], DK, DV)
@@ -297,15 +370,25 @@ def run_ours(args) -> None:
         e0.record()
         for _ in range(steps):
             fn()
+        ctx.synchronize()   # the library runs on its own streams: wait for them before the closing event
         e1.record()
         barrier()
         if collect is not None:
             collect(ctx.accumulated_timings(reset=True))
         return parallel.max_over_ranks(e0.elapsed_time(e1))  # ms, max over ranks
 
+    # NVML attach happens here, before the warm-up: nothing driver-side may start inside the timed region
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid, allow_subprocess=(rank == 0)).start()
+    barrier()
+
     W, K = max(3, args.warmup), max(1, args.steps)
     for _ in range(W):
         step_device()
+    ctx.synchronize()
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------
     fused = {"ms": 0.0, "launches": 0.0, "cast_ms": 0.0, "merge_ms": 0.0}
@@ -317,7 +400,7 @@ def run_ours(args) -> None:
         fused["merge_ms"] += t["merge_ms"]
 
     launches0 = sdpa_b200.launch_count()
-    with ClockSampler(local_rank) as clk:
+    with sampler as clk:
         ms_dev = timed(step_device, K, collect)
         launches = sdpa_b200.launch_count() - launches0   # kernels launched inside the timed region only
         # The timed region is a few milliseconds: keep the identical load running so the sampler sees it.
@@ -326,8 +409,21 @@ def run_ours(args) -> None:
         extra = int(min(20000, max(1, 1000.0 / max(ms_dev / K, 1e-3))))
         for _ in range(extra):
             step_device()
+        ctx.synchronize()
         barrier()
     clocks = clk.summary()
+    sampler.close()
+    if world > 1:   # every rank sampled its own GPU: report the slowest median clock and the union of the reasons
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, clocks)
+        meds = [c["sm_mhz"] for c in per_rank if c and c["sm_mhz"]]
+        clocks = dict(per_rank[0])
+        clocks["sm_mhz"] = min(meds) if meds else None
+        clocks["reasons"] = sorted({r for c in per_rank if c for r in c["reasons"]})
+        clocks["samples"] = sum(c["samples"] for c in per_rank if c)
+        pw = [c["power_w_max"] for c in per_rank if c and c["power_w_max"]]
+        clocks["power_w_max"] = max(pw) if pw else None
+        clocks["per_rank_sm_mhz"] = [c["sm_mhz"] if c else None for c in per_rank]
     kernel_name = ctx.last_kernel()
 
     # ---- e2e: pinned host buffers through the C ABI -------------------------------------------
@@ -381,6 +477,7 @@ def run_ours(args) -> None:
                        "merge": "none" if world == 1 else {"peer": "device-side exchange: root merge kernel reads shard states over NVLink (CUDA IPC) behind epoch flags",
                                                            "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
                                                            "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],
+                       "submission": "K passes queued back to back (sdpa_enqueue_device_full), one wait after the last; e2e uses the blocking host call",
                        "l2": "inputs_larger_than_l2 (fp64 Q+K+V per GPU = %d MiB)" % ((n_local * (DK + DV) + m * DK) * 8 >> 20),
                        "kernel": kernel_name},
             "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

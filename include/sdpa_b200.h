@@ -138,6 +138,16 @@ sdpa_status sdpa_attention_device_full(sdpa_ctx* ctx, const double* const* K_sha
                                        const int* n_local, int dk, int dv, const double* const* Q_dev,
                                        double* result_dev, int m);
 
+/* The same pass, queued instead of blocking: returns once the work is enqueued on the context's streams.  Consecutive
+ * passes run back to back in stream order (they share the context's buffers), which removes the host round trip
+ * between passes; every array must stay valid and unmodified until sdpa_synchronize() returns.  This is the form
+ * bench.py times for the HBM-resident metric -- the blocking calls above keep the reference's semantics
+ * (attention() returns with the result complete, attention-mpi.c:521-523). */
+sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
+                                     const int* n_local, int dk, int dv, const double* const* Q_dev,
+                                     double* result_dev, int m);
+sdpa_status sdpa_synchronize(sdpa_ctx* ctx);
+
 /* The reference's calling convention on a one-GPU-per-process context (world_size > 1):
  * dimensions and Q/K/V/result are valid on the process that owns shard 0 only; that process
  * scatters the K/V shards and broadcasts the Q batches over NCCL (mpi.c:196,213-266,305,327). */

@@ -129,6 +129,47 @@ cvt_d2bf16_scalar_kernel(__nv_bfloat16* __restrict__ dst, const double* __restri
         dst[i] = __float2bfloat16_rn(__double2float_rn(src[i]));
 }
 
+// Several fp64 -> compute-precision casts in ONE launch (the K shard, the V shard and the first Q batch of a
+// device-resident call): the segments form one virtual array of 2-element units, so the grid-stride loop has a
+// single tail instead of one per operand and two launch gaps disappear from the step.
+template <bool BF16>
+__global__ void __launch_bounds__(kCastThreads) cvt_in_batch_kernel(CastBatch cb)
+{
+    const size_t u0 = cb.units[0], u01 = u0 + cb.units[1], all = u01 + cb.units[2];
+    const size_t total = (size_t)gridDim.x * blockDim.x;
+    auto locate = [&](size_t g, const double2*& src, void*& dst, size_t& off) {
+        const int seg = g < u0 ? 0 : (g < u01 ? 1 : 2);
+        off = g - (seg == 0 ? 0 : (seg == 1 ? u0 : u01));
+        src = reinterpret_cast<const double2*>(cb.src[seg]);
+        dst = cb.dst[seg];
+    };
+    auto store = [&](void* dst, size_t off, double2 v) {
+        if (BF16) reinterpret_cast<uint32_t*>(dst)[off] = pack_bf16x2(__double2float_rn(v.x), __double2float_rn(v.y));
+        else reinterpret_cast<float2*>(dst)[off] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+    };
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * total < all; i += kUnroll * total) {
+        double2 v[kUnroll];
+        void* d[kUnroll];
+        size_t off[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const double2* src;
+            locate(i + u * total, src, d[u], off[u]);
+            v[u] = ld_stream_f64x2(src + off[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) store(d[u], off[u], v[u]);
+    }
+    for (; i < all; i += total) {
+        const double2* src;
+        void* d;
+        size_t off;
+        locate(i, src, d, off);
+        store(d, off, ld_stream_f64x2(src + off));
+    }
+}
+
 inline int cast_grid(size_t work_items)
 {
     // 148 SMs x 8 resident CTAs of 256 threads; never more CTAs than work.
@@ -195,6 +236,47 @@ sdpa_status launch_cvt_d2bf16(__nv_bfloat16* dst, const double* src, size_t coun
         cvt_d2bf16_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst, src, done, count);
         count_launch();
     }
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+// Up to three operands in one launch; falls back to one launch per operand when a pointer is not 16-byte aligned
+// or a count is odd (the batched kernel moves 2-element units only).
+sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, int nseg,
+                                cudaStream_t stream)
+{
+    if (nseg < 0 || nseg > 3) {
+        set_error("launch_cvt_in_batch: 0..3 segments");
+        return SDPA_ERR_INVALID;
+    }
+    bool vec_ok = true;
+    size_t units_total = 0;
+    CastBatch cb;
+    for (int k = 0; k < 3; ++k) {
+        cb.dst[k] = nullptr;
+        cb.src[k] = nullptr;
+        cb.units[k] = 0;
+    }
+    for (int k = 0; k < nseg; ++k) {
+        if (count[k] == 0) continue;
+        vec_ok = vec_ok && (count[k] % 2 == 0) && aligned(src[k], 16) && aligned(dst[k], 8);
+        cb.dst[k] = dst[k];
+        cb.src[k] = src[k];
+        cb.units[k] = count[k] / 2;
+        units_total += cb.units[k];
+    }
+    if (units_total == 0 && vec_ok) return SDPA_OK;
+    if (!vec_ok) {
+        for (int k = 0; k < nseg; ++k) {
+            if (prec == SDPA_PREC_BF16) SDPA_TRY(launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst[k]), src[k], count[k], stream));
+            else SDPA_TRY(launch_cvt_d2f(reinterpret_cast<float*>(dst[k]), src[k], count[k], stream));
+        }
+        return SDPA_OK;
+    }
+    const int grid = cast_grid(units_total / kUnroll);
+    if (prec == SDPA_PREC_BF16) cvt_in_batch_kernel<true><<<grid, kCastThreads, 0, stream>>>(cb);
+    else cvt_in_batch_kernel<false><<<grid, kCastThreads, 0, stream>>>(cb);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }

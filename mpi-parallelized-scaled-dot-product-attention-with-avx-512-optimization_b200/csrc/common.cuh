@@ -57,6 +57,13 @@ struct Partials {
 sdpa_status launch_cvt_d2f(float* dst, const double* src, size_t count, cudaStream_t stream);
 sdpa_status launch_cvt_f2d(double* dst, const float* src, size_t count, cudaStream_t stream);
 sdpa_status launch_cvt_d2bf16(__nv_bfloat16* dst, const double* src, size_t count, cudaStream_t stream);
+struct CastBatch {
+    void* dst[3];
+    const double* src[3];
+    size_t units[3];   // 2-element units per segment
+};
+sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, int nseg,
+                                cudaStream_t stream);
 
 // fp32 CUDA-core fused attention.  Q [rows x dk], K [n x dk], V [n x dv] fp32 row-major.
 // If out64 != nullptr (requires splits == 1) the normalised result is written as fp64

@@ -155,13 +155,22 @@ struct Shard {
     cudaEvent_t ev_compute_done[2] = {nullptr, nullptr}, ev_slot_free[2] = {nullptr, nullptr};
     cudaEvent_t ev_comm_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // K/V casts of a device-resident call that wait for the first Q batch so that all three share one launch
+    void* pend_dst[2] = {nullptr, nullptr};
+    const double* pend_src[2] = {nullptr, nullptr};
+    size_t pend_cnt[2] = {0, 0};
+    int npend = 0;
     cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
-    // timing event pool: pairs around casts [0], fused kernel [1], merge+collectives [2]
-    // [3] = the whole call.  Pairs are appended call after call and only turned into numbers when somebody asks
-    // (sdpa_last_timings / sdpa_accumulated_timings): querying ~8 events costs ~11 us of host time per call.
-    std::vector<cudaEvent_t> tev[4];
-    size_t tev_used[4] = {0, 0, 0, 0};
-    size_t tev_last[4] = {0, 0, 0, 0};      // where the last call's pairs start
+    // Stage timing: one pool of timestamp events ("marks"); each category -- casts [0], fused kernel [1],
+    // merge + collectives [2], the whole call [3] -- keeps (begin, end) indices into it.  Adjacent stages on the
+    // compute stream share a mark (the end of the cast IS the begin of the fused kernel), so a device-resident
+    // single-GPU pass records 4 events, not 11.  Pairs accumulate call after call and are only turned into
+    // numbers on demand (sdpa_last_timings / sdpa_accumulated_timings): the queries cost ~11 us of host time.
+    std::vector<cudaEvent_t> marks;
+    size_t marks_used = 0;
+    int open_mark = -1;                      // last mark on s_compute with nothing enqueued behind it, or -1
+    std::vector<int> tpair[4];               // begin, end, begin, end, ...
+    size_t tpair_last[4] = {0, 0, 0, 0};     // where the last call's pairs start
     double acc_ms[4] = {0, 0, 0, 0};        // folded (already queried) time since the last reset
     UmmaPlan* plan = nullptr;
     int sm_count = 148;
@@ -202,22 +211,37 @@ struct sdpa_ctx {
 
 namespace sdpa {
 
-static sdpa_status time_begin(Shard& s, int which, cudaStream_t st)
+static sdpa_status new_mark(Shard& s, cudaStream_t st, int* idx)
 {
-    if (s.tev_used[which] + 2 > s.tev[which].size()) {
-        for (int i = 0; i < 2; ++i) {
-            cudaEvent_t e;
-            SDPA_CUDA_TRY(cudaEventCreate(&e));
-            s.tev[which].push_back(e);
-        }
+    if (s.marks_used == s.marks.size()) {
+        cudaEvent_t e;
+        SDPA_CUDA_TRY(cudaEventCreate(&e));
+        s.marks.push_back(e);
     }
-    SDPA_CUDA_TRY(cudaEventRecord(s.tev[which][s.tev_used[which]], st));
+    SDPA_CUDA_TRY(cudaEventRecord(s.marks[s.marks_used], st));
+    *idx = (int)s.marks_used++;
     return SDPA_OK;
 }
-static sdpa_status time_end(Shard& s, int which, cudaStream_t st)
+// Work enqueued on the compute stream outside a timed stage (event waits, flag kernels) must call this:
+// the next stage may then not reuse the previous stage's end mark as its begin.
+static inline void compute_stream_touched(Shard& s) { s.open_mark = -1; }
+
+static sdpa_status time_begin(Shard& s, int which, cudaStream_t st)
 {
-    SDPA_CUDA_TRY(cudaEventRecord(s.tev[which][s.tev_used[which] + 1], st));
-    s.tev_used[which] += 2;
+    int idx = -1;
+    if (st == s.s_compute && s.open_mark >= 0) idx = s.open_mark;
+    else SDPA_TRY(new_mark(s, st, &idx));
+    if (st == s.s_compute) s.open_mark = idx;   // still nothing behind it until the stage's work is enqueued
+    s.tpair[which].push_back(idx);
+    return SDPA_OK;
+}
+static sdpa_status time_end(Shard& s, int which, cudaStream_t st, bool may_share = false)
+{
+    int idx = -1;
+    if (may_share && st == s.s_compute && s.open_mark >= 0) idx = s.open_mark;   // nothing ran since the last end mark
+    else SDPA_TRY(new_mark(s, st, &idx));
+    if (st == s.s_compute) s.open_mark = idx;
+    s.tpair[which].push_back(idx);
     return SDPA_OK;
 }
 
@@ -229,29 +253,33 @@ static double host_now_us()
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 
-// Turn the pending event pairs [from, used) of category w into milliseconds.
+// Turn the pending pairs [from, end) of category w into milliseconds (the recorded work must be complete).
 static sdpa_status sum_pairs(Shard& s, int w, size_t from, double* out)
 {
     double acc = 0.0;
-    for (size_t k = from; k + 1 < s.tev_used[w]; k += 2) {
+    const std::vector<int>& p = s.tpair[w];
+    for (size_t k = from; k + 1 < p.size(); k += 2) {
         float ms = 0.f;
-        SDPA_CUDA_TRY(cudaEventElapsedTime(&ms, s.tev[w][k], s.tev[w][k + 1]));
+        if (p[k] != p[k + 1]) SDPA_CUDA_TRY(cudaEventElapsedTime(&ms, s.marks[p[k]], s.marks[p[k + 1]]));
         acc += ms;
     }
     *out = acc;
     return SDPA_OK;
 }
-// Fold everything recorded so far into acc_ms and recycle the events (all recorded work must be complete).
+// Fold everything recorded so far into acc_ms and recycle the marks.
 static sdpa_status fold_timings(Shard& s)
 {
     SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));   // queued passes (sdpa_enqueue_*) must have finished
     for (int w = 0; w < 4; ++w) {
         double ms = 0.0;
         SDPA_TRY(sum_pairs(s, w, 0, &ms));
         s.acc_ms[w] += ms;
-        s.tev_used[w] = 0;
-        s.tev_last[w] = 0;
+        s.tpair[w].clear();
+        s.tpair_last[w] = 0;
     }
+    s.marks_used = 0;
+    s.open_mark = -1;
     return SDPA_OK;
 }
 
@@ -314,8 +342,7 @@ static void shard_destroy(Shard& s, const NcclApi* api)
                          s.ev_join[0], s.ev_join[1], s.ev_join[2]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
-    for (int w = 0; w < 4; ++w)
-        for (cudaEvent_t e : s.tev[w]) cudaEventDestroy(e);
+    for (cudaEvent_t e : s.marks) cudaEventDestroy(e);
     cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out};
     for (cudaStream_t st : sts)
         if (st) cudaStreamDestroy(st);
@@ -351,7 +378,7 @@ static sdpa_status upload_cast(Shard& s, int prec, void* dst, const double* src,
 }
 
 static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
-                           const int* n_local, int dk, int dv, bool on_device)
+                           const int* n_local, int dk, int dv, bool on_device, bool defer_casts = false)
 {
     if (!ctx || !n_local || dk < 1 || dv < 1) {
         set_error("load_kv: bad arguments");
@@ -381,7 +408,13 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
         // +128 rows of slack so TMA boxes / vector loads past the last row stay in bounds
         SDPA_TRY(s.Kc.reserve(((size_t)s.n_local + 128) * dk * esz));
         SDPA_TRY(s.Vc.reserve(((size_t)s.n_local + 128) * dv * esz));
-        if (s.n_local > 0) {
+        s.npend = 0;
+        if (s.n_local > 0 && on_device && defer_casts) {
+            // sdpa_attention_device_full: the sources stay valid for the whole call, so the casts ride with Q's
+            s.pend_dst[0] = s.Kc.p, s.pend_src[0] = K_shards[i], s.pend_cnt[0] = (size_t)s.n_local * dk;
+            s.pend_dst[1] = s.Vc.p, s.pend_src[1] = V_shards[i], s.pend_cnt[1] = (size_t)s.n_local * dv;
+            s.npend = 2;
+        } else if (s.n_local > 0) {
             SDPA_TRY(upload_cast(s, prec, s.Kc.p, K_shards[i], (size_t)s.n_local * dk, on_device));
             SDPA_TRY(upload_cast(s, prec, s.Vc.p, V_shards[i], (size_t)s.n_local * dv, on_device));
         }
@@ -544,7 +577,8 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
 }
 
 static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const double* const* Q_dev,
-                                  double* result, bool result_on_device, int m, bool q_from_root = false)
+                                  double* result, bool result_on_device, int m, bool q_from_root = false,
+                                  bool blocking = true)
 {
     if (!ctx || m < 0) {
         set_error("attention: bad arguments");
@@ -578,6 +612,12 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     for (float& t : ctx->last_timing) t = 0.f;
     if (m == 0) {
         ctx->last_timing_valid = true;   // nothing ran: all-zero stage times
+        for (Shard& s : ctx->shards) {   // K/V casts deferred by sdpa_attention_device_full still have to happen
+            if (s.npend == 0) continue;
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            SDPA_TRY(launch_cvt_in_batch(ctx->prec, s.pend_dst, s.pend_src, s.pend_cnt, 2, s.s_compute));
+            s.npend = 0;
+        }
         return SDPA_OK;
     }
 
@@ -596,24 +636,30 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     }
     splits = std::max(1, std::min(splits, 64));
 
+    // which side streams this call touches (the others are neither forked nor joined: every stream operation
+    // between two kernels costs front-end time on the GPU)
+    const bool use_in = !on_device;                                  // H2D of the Q batches
+    const bool use_comm = world > 1;                                 // collectives / peer merge
+    const bool use_out = world > 1 || !result_on_device;             // D2H of the result, slot recycling
     for (int i = 0; i < L; ++i) {
         Shard& s = ctx->shards[i];
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         SDPA_TRY(reserve_batch_buffers(ctx, s, B, splits, s.grank == 0));
-        if (s.tev_used[1] > 1024) {   // long unmeasured loops: keep the pools bounded (previous calls are complete)
-            if (!ctx->last_timing_valid) ctx->last_timing_valid = true;   // the last call's detail is dropped with the fold
+        if (s.marks_used > 2048) {   // long unmeasured loops: keep the pool bounded
+            ctx->last_timing_valid = true;   // the last call's detail is dropped with the fold
             SDPA_TRY(fold_timings(s));
         }
-        for (int w = 0; w < 4; ++w) s.tev_last[w] = s.tev_used[w];
+        for (int w = 0; w < 4; ++w) s.tpair_last[w] = s.tpair[w].size();
+        compute_stream_touched(s);   // whatever ran before this call is not part of it
         if (ctx->prec == SDPA_PREC_BF16)
             for (int b = 0; b < 2; ++b)
                 SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk));
         SDPA_TRY(time_begin(s, 3, s.s_compute));
-        SDPA_CUDA_TRY(cudaEventRecord(s.ev_begin, s.s_compute));
-        // the other streams start after ev_begin so that "total" brackets everything
-        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_begin, 0));
-        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_begin, 0));
-        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, s.ev_begin, 0));
+        // the side streams this call uses start after the begin mark, so that "total" brackets everything
+        cudaEvent_t begun = s.marks[s.tpair[3].back()];
+        if (use_in) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, begun, 0));
+        if (use_comm) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, begun, 0));
+        if (use_out) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, begun, 0));
     }
 
     if (use_ipc) SDPA_TRY(ipc_setup(ctx, std::max(B, 8192), dv));
@@ -642,13 +688,24 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                               cudaMemcpyHostToDevice, s.s_in));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_ready[b], s.s_in));
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_q_ready[b], 0));
+                compute_stream_touched(s);
                 q_src_dev = s.q64[b].as<double>();
             }
             // slot b (contrib/out buffers) must have been drained by batch ii-2's collectives / D2H
-            if (ii >= 2) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_slot_free[b], 0));
+            if (ii >= 2 && use_out) {
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_slot_free[b], 0));
+                compute_stream_touched(s);
+            }
 
             SDPA_TRY(time_begin(s, 0, s.s_compute));
-            if (have_q) {
+            if (s.npend > 0) {
+                void* cd[3] = {s.pend_dst[0], s.pend_dst[1], s.qc[b].p};
+                const double* cs[3] = {s.pend_src[0], s.pend_src[1], q_src_dev};
+                const size_t cc[3] = {s.pend_cnt[0], s.pend_cnt[1], (size_t)bs * dk};
+                SDPA_TRY(launch_cvt_in_batch(ctx->prec, cd, cs, cc, have_q ? 3 : 2, s.s_compute));
+                s.npend = 0;
+                ++all_launches;
+            } else if (have_q) {
                 SDPA_TRY(cast_in(ctx->prec, s.qc[b].p, q_src_dev, (size_t)bs * dk, s.s_compute));
                 ++all_launches;
             }
@@ -694,7 +751,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_TRY(time_end(s, 2, s.s_compute));
                 ++all_launches;
             }
-            SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
+            if (use_comm || use_out) SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
         }
 
         // ---- cross-shard merge ----------------------------------------------------------------
@@ -840,7 +897,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         // ---- root: fp64 rows of this batch back to the host ------------------------------------
         for (int i = 0; i < L; ++i) {
             Shard& s = ctx->shards[i];
-            if (s.grank != 0) continue;
+            if (s.grank != 0 || !use_out) continue;   // single GPU writing to device memory: all on the compute stream
             SDPA_CUDA_TRY(cudaSetDevice(s.dev));
             cudaEvent_t ready = world > 1 ? s.ev_comm_done[b] : s.ev_compute_done[b];
             SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, ready, 0));
@@ -858,6 +915,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         for (int b = 0; b < 2; ++b)
             if (ctx->ipc.slot_epoch[b] != 0)
                 SDPA_TRY(launch_wait_flag(ctx->ipc.root_flags + 2 + b, ctx->ipc.slot_epoch[b], s.s_compute));
+        compute_stream_touched(s);
     }
 
     const double hp1 = host_prof ? host_now_us() : 0.0;
@@ -866,13 +924,16 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         Shard& s = ctx->shards[i];
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         cudaStream_t side[3] = {s.s_in, s.s_comm, s.s_out};
+        const bool used[3] = {use_in, use_comm, use_out};
         for (int j = 0; j < 3; ++j) {
+            if (!used[j]) continue;
             SDPA_CUDA_TRY(cudaEventRecord(s.ev_join[j], side[j]));
             SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_join[j], 0));
+            compute_stream_touched(s);
         }
-        SDPA_TRY(time_end(s, 3, s.s_compute));
+        SDPA_TRY(time_end(s, 3, s.s_compute, true));
     }
-    for (int i = 0; i < L; ++i) {
+    for (int i = 0; i < L && blocking; ++i) {
         Shard& s = ctx->shards[i];
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
@@ -1218,8 +1279,38 @@ sdpa_status sdpa_attention_device(sdpa_ctx* ctx, const double* const* Q_dev, dou
 sdpa_status sdpa_attention_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
                                        const int* n_local, int dk, int dv, const double* const* Q_dev, double* result_dev, int m)
 {
-    SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true));
-    return sdpa_attention_device(ctx, Q_dev, result_dev, m);
+    if (m > 0 && !Q_dev) {
+        set_error("sdpa_attention_device_full: Q_dev is NULL");
+        return SDPA_ERR_INVALID;
+    }
+    SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true));
+    return attention_impl(ctx, nullptr, Q_dev, result_dev, true, m);
+}
+
+/* The same pass, queued: returns as soon as the work is enqueued (stream order keeps consecutive passes and their
+ * shared buffers in sequence); sdpa_synchronize() waits.  All arrays must stay valid until then. */
+sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
+                                     const int* n_local, int dk, int dv, const double* const* Q_dev, double* result_dev, int m)
+{
+    if (m > 0 && !Q_dev) {
+        set_error("sdpa_enqueue_device_full: Q_dev is NULL");
+        return SDPA_ERR_INVALID;
+    }
+    SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true));
+    return attention_impl(ctx, nullptr, Q_dev, result_dev, true, m, false, false);
+}
+
+sdpa_status sdpa_synchronize(sdpa_ctx* ctx)
+{
+    if (!ctx) {
+        set_error("sdpa_synchronize: ctx is NULL");
+        return SDPA_ERR_INVALID;
+    }
+    for (Shard& s : ctx->shards) {
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+    }
+    return SDPA_OK;
 }
 
 sdpa_status sdpa_online_softmax_partials(sdpa_ctx* ctx, int local, const float* Qf_dev, int m, float* contrib_dev,
@@ -1265,10 +1356,11 @@ sdpa_status sdpa_last_timings(sdpa_ctx* ctx, float* out6)
         for (int k = 0; k < 4; ++k) ctx->last_timing[k] = 0.f;
         for (Shard& s : ctx->shards) {
             SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));   // queued passes (sdpa_enqueue_*) must have finished
             const int slot[4] = {3, 0, 1, 2};   // out[0] total, [1] casts, [2] fused, [3] merge
             for (int k = 0; k < 4; ++k) {
                 double ms = 0.0;
-                SDPA_TRY(sum_pairs(s, slot[k], s.tev_last[slot[k]], &ms));
+                SDPA_TRY(sum_pairs(s, slot[k], s.tpair_last[slot[k]], &ms));
                 ctx->last_timing[k] = std::max(ctx->last_timing[k], (float)ms);
             }
         }

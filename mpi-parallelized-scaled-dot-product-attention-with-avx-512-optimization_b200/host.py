@@ -76,6 +76,8 @@ ABI = {
     "sdpa_attention_host": (ctypes.c_int, [_V, _V, _V, ctypes.c_int]),
     "sdpa_attention_device": (ctypes.c_int, [_V, _dpp, _V, ctypes.c_int]),
     "sdpa_attention_device_full": (ctypes.c_int, [_V, _dpp, _dpp, _ip, ctypes.c_int, ctypes.c_int, _dpp, _V, ctypes.c_int]),
+    "sdpa_enqueue_device_full": (ctypes.c_int, [_V, _dpp, _dpp, _ip, ctypes.c_int, ctypes.c_int, _dpp, _V, ctypes.c_int]),
+    "sdpa_synchronize": (ctypes.c_int, [_V]),
     "sdpa_scatter_attention": (ctypes.c_int, [_V, _V, _V, _V, _V] + [ctypes.c_int] * 4),
     "sdpa_online_softmax_partials": (ctypes.c_int, [_V, ctypes.c_int, _V, ctypes.c_int, _V, _V, _V]),
     "sdpa_last_timings": (ctypes.c_int, [_V, _fp]),
@@ -298,17 +300,23 @@ class Context:
         _check(lib().sdpa_attention_device(self._h, self._ptr_array(Q_ptrs), ctypes.c_void_p(result_ptr or 0), m),
                "sdpa_attention_device")
 
-    def attention_device_full(self, K_ptrs, V_ptrs, n_local, dk: int, dv: int, Q_ptrs, result_ptr: int | None, m: int) -> None:
-        """The whole path on device-resident fp64 arrays in one C call (K/V cast, Q batches, merge)."""
+    def attention_device_full(self, K_ptrs, V_ptrs, n_local, dk: int, dv: int, Q_ptrs, result_ptr: int | None, m: int,
+                              blocking: bool = True) -> None:
+        """The whole path on device-resident fp64 arrays in one C call (K/V cast, Q batches, merge).
+        ``blocking=False`` only enqueues the pass (``synchronize()`` waits for all queued passes)."""
         key = (tuple(K_ptrs), tuple(V_ptrs), tuple(n_local), tuple(Q_ptrs))
         if getattr(self, "_full_key", None) != key:   # marshal the pointer arrays once per distinct argument set
             counts = (ctypes.c_int * self.num_local)(*[int(c) for c in n_local])
             self._full_args = (self._ptr_array(K_ptrs), self._ptr_array(V_ptrs), counts, self._ptr_array(Q_ptrs))
             self._full_key = key
         ka, va, counts, qa = self._full_args
-        _check(lib().sdpa_attention_device_full(self._h, ka, va, counts, dk, dv, qa, ctypes.c_void_p(result_ptr or 0), m),
-               "sdpa_attention_device_full")
+        fn = lib().sdpa_attention_device_full if blocking else lib().sdpa_enqueue_device_full
+        _check(fn(self._h, ka, va, counts, dk, dv, qa, ctypes.c_void_p(result_ptr or 0), m),
+               "sdpa_attention_device_full" if blocking else "sdpa_enqueue_device_full")
         self.dk, self.dv = dk, dv
+
+    def synchronize(self) -> None:
+        _check(lib().sdpa_synchronize(self._h), "sdpa_synchronize")
 
     def scatter_attention(self, Q=None, K=None, V=None, result=None):
         """Reference calling convention across processes: data on the shard-0 process only."""

@@ -78,6 +78,15 @@ def _rank_worker(rank, world, port, out_dir, id_file):
             np.testing.assert_allclose(got, ref, rtol=0, atol=atol)
         else:
             assert got is None
+        # (1b) device-resident, queued passes (bench.py's timed loop): five passes back to back, one wait
+        Kd, Vd, Qd = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (K[first:first + count], V[first:first + count], Q))
+        out = torch.zeros(m, d, dtype=torch.float64, device="cuda") if rank == 0 else None
+        for _ in range(5):
+            ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [count], d, d, [Qd.data_ptr()],
+                                      out.data_ptr() if out is not None else None, m, blocking=False)
+        ctx.synchronize()
+        if rank == 0:
+            np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=atol)
         # (2) the reference's calling convention: data on rank 0 only (mpi.c:508-517)
         got2 = ctx.scatter_attention(Q, K, V) if rank == 0 else ctx.scatter_attention()
         if rank == 0:

@@ -156,6 +156,30 @@ def test_device_resident_api(sdpa, oracle, torch_cuda):
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=F32_ATOL)
 
 
+@pytest.mark.parametrize("precision", ["f32", "bf16"])
+def test_queued_passes_match_blocking(sdpa, oracle, torch_cuda, precision):
+    """sdpa_enqueue_device_full: passes queued back to back (different K/V/Q each) give the blocking results."""
+    torch = torch_cuda
+    cases = [oracle.make_inputs(384, 1024 + 256 * k, 128, 128, seed=20 + k) for k in range(3)]
+    dev = [[torch.from_numpy(a).cuda() for a in c] for c in cases]
+    outs_q = [torch.zeros(384, 128, dtype=torch.float64, device="cuda") for _ in cases]
+    outs_b = [torch.zeros(384, 128, dtype=torch.float64, device="cuda") for _ in cases]
+    with sdpa.Context(precision=precision) as ctx:
+        for (Qd, Kd, Vd), o in zip(dev, outs_b):
+            ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], 128, 128, [Qd.data_ptr()], o.data_ptr(), 384)
+        for rep in range(2):
+            for (Qd, Kd, Vd), o in zip(dev, outs_q):
+                ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], 128, 128, [Qd.data_ptr()], o.data_ptr(), 384,
+                                          blocking=False)
+        ctx.synchronize()
+        acc = ctx.accumulated_timings(reset=True)
+        assert acc["calls"] == 9 and acc["total_ms"] >= acc["fused_ms"] > 0
+    for (Q, K, V), a, b in zip(cases, outs_q, outs_b):
+        assert torch.equal(a, b)
+        tol = F32_ATOL if precision == "f32" else BF16_ATOL
+        np.testing.assert_allclose(a.cpu().numpy(), oracle.attention_f64(Q, K, V), rtol=0, atol=tol)
+
+
 def test_accumulated_stage_timings(sdpa, oracle, torch_cuda):
     """Stage times are recorded per call and only evaluated on demand; the accumulated view
     sums every call since the last reset (bench.py reads it once after its timed loop)."""
