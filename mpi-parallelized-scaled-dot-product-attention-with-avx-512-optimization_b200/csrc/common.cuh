@@ -119,5 +119,9 @@ struct PeerSync {
 sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
                                       const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
                                       const PeerSync& sync, cudaStream_t stream);
+// Sliced merge, root side: wait for every rank's "my rows are staged" flag (sync.ready), copy the staged fp64 batch
+// to dst, then raise sync.consumed.
+sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, int dv, const PeerSync& sync, int ranks,
+                                  cudaStream_t stream);
 
 }  // namespace sdpa

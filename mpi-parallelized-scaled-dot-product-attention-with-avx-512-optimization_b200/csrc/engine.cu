@@ -198,10 +198,16 @@ struct sdpa_ctx {
         bool ready = false;
         int cap_rows = 0, dv = 0;
         DevBuf xbuf[2];                 // [contrib rows*dv | tmax rows | lsum rows], one per ping-pong slot
-        DevBuf flags;                   // uint32: ready[2], consumed[2], block_counter[2]
-        std::vector<void*> peer_x[2];   // root: every shard's xbuf (own pointer for itself)
-        std::vector<unsigned int*> peer_flags;  // root: every shard's flag block
-        unsigned int* root_flags = nullptr;     // non-root: the root's flag block
+        // uint32 flags: [0..1] ready[slot], [2..3] consumed[slot] (root's copy is the one polled), [4..5] root-merge block
+        // counter, [6..7] slice-merge block counter, [8..9] collect block counter, [64 + slot*64 + r] "rank r's rows of
+        // the batch are staged" (root's copy, written by rank r over NVLink)
+        DevBuf flags;
+        DevBuf stage[2];                // fp64 batch assembled from every rank's slice (the root's copy is the one used)
+        std::vector<void*> peer_x[2];   // every rank's xbuf (own pointer for itself)
+        std::vector<unsigned int*> peer_flags;  // every rank's flag block
+        unsigned int* root_flags = nullptr;     // the root's flag block (== peer_flags[0])
+        double* root_stage[2] = {nullptr, nullptr};
+        bool sliced = true;             // every rank merges its share of the rows (default) / the root merges all rows
         std::vector<void*> opened;      // IPC mappings to close
         unsigned int epoch = 0;         // global batch counter, identical on every rank
         unsigned int slot_epoch[2] = {0, 0};
@@ -500,6 +506,7 @@ static void ipc_close(sdpa_ctx* ctx)
     ctx->ipc.peer_x[1].clear();
     ctx->ipc.peer_flags.clear();
     ctx->ipc.root_flags = nullptr;
+    ctx->ipc.root_stage[0] = ctx->ipc.root_stage[1] = nullptr;
     ctx->ipc.ready = false;
 }
 
@@ -519,17 +526,25 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         x.xbuf[b].release();
         SDPA_TRY(x.xbuf[b].reserve(xbytes));
     }
+    for (int b = 0; b < 2; ++b) {
+        x.stage[b].release();
+        SDPA_TRY(x.stage[b].reserve((size_t)rows_cap * dv * sizeof(double)));
+    }
     if (!x.flags.p) {
-        SDPA_TRY(x.flags.reserve(256));
-        SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 256));
+        SDPA_TRY(x.flags.reserve(1024));
+        SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 1024));
         x.epoch = 0;
         x.slot_epoch[0] = x.slot_epoch[1] = 0;
+        const char* mode = getenv("SDPA_IPC_MERGE");   // "root": the root GPU merges every row (first form of the exchange)
+        x.sliced = !(mode && !strcmp(mode, "root"));
     }
-    struct Handles { cudaIpcMemHandle_t x0, x1, fl; };
+    struct Handles { cudaIpcMemHandle_t x0, x1, fl, s0, s1; };
     Handles mine;
     SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.x0, x.xbuf[0].p));
     SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.x1, x.xbuf[1].p));
     SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.fl, x.flags.p));
+    SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.s0, x.stage[0].p));
+    SDPA_CUDA_TRY(cudaIpcGetMemHandle(&mine.s1, x.stage[1].p));
     const int world = ctx->world;
     DevBuf dsend, drecv;
     SDPA_TRY(dsend.reserve(sizeof(Handles)));
@@ -546,29 +561,38 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         x.opened.push_back(*out);
         return SDPA_OK;
     };
-    if (s.grank == 0) {
-        x.peer_x[0].assign(world, nullptr);
-        x.peer_x[1].assign(world, nullptr);
-        x.peer_flags.assign(world, nullptr);
-        for (int r = 0; r < world; ++r) {
-            if (r == 0) {
-                x.peer_x[0][r] = x.xbuf[0].p;
-                x.peer_x[1][r] = x.xbuf[1].p;
-                x.peer_flags[r] = x.flags.as<unsigned int>();
-                continue;
-            }
-            void* p = nullptr;
+    // every rank maps every other rank's state slots and flags (sliced merge: all-to-all reads), and the root's staging
+    x.peer_x[0].assign(world, nullptr);
+    x.peer_x[1].assign(world, nullptr);
+    x.peer_flags.assign(world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        if (r == s.grank) {
+            x.peer_x[0][r] = x.xbuf[0].p;
+            x.peer_x[1][r] = x.xbuf[1].p;
+            x.peer_flags[r] = x.flags.as<unsigned int>();
+            continue;
+        }
+        if (s.grank != 0 && r != 0 && !x.sliced) continue;   // root merge: non-root ranks only need the root's flags
+        void* p = nullptr;
+        if (s.grank == 0 || x.sliced) {
             SDPA_TRY(open(all[r].x0, &p));
             x.peer_x[0][r] = p;
             SDPA_TRY(open(all[r].x1, &p));
             x.peer_x[1][r] = p;
-            SDPA_TRY(open(all[r].fl, &p));
-            x.peer_flags[r] = reinterpret_cast<unsigned int*>(p);
         }
-    } else {
+        SDPA_TRY(open(all[r].fl, &p));
+        x.peer_flags[r] = reinterpret_cast<unsigned int*>(p);
+    }
+    x.root_flags = x.peer_flags[0];
+    if (s.grank == 0) {
+        x.root_stage[0] = x.stage[0].as<double>();
+        x.root_stage[1] = x.stage[1].as<double>();
+    } else if (x.sliced) {
         void* p = nullptr;
-        SDPA_TRY(open(all[0].fl, &p));
-        x.root_flags = reinterpret_cast<unsigned int*>(p);
+        SDPA_TRY(open(all[0].s0, &p));
+        x.root_stage[0] = reinterpret_cast<double*>(p);
+        SDPA_TRY(open(all[0].s1, &p));
+        x.root_stage[1] = reinterpret_cast<double*>(p);
     }
     x.cap_rows = rows_cap;
     x.dv = dv;
@@ -759,7 +783,44 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             Shard& s = ctx->shards[0];
             sdpa_ctx::Ipc& x = ctx->ipc;
             SDPA_CUDA_TRY(cudaSetDevice(s.dev));
-            if (s.grank == 0) {
+            if (x.sliced) {
+                // every rank merges its share of the batch rows from all ranks' states (all-to-all reads over NVLink),
+                // writes the fp64 rows into the root's staging buffer and raises its "staged" flag there; the root then
+                // moves the assembled batch to its destination and releases the slots.
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
+                const int base = bs / world, rem = bs % world;
+                const int my_rows = base + (s.grank < rem ? 1 : 0);
+                const int my_first = s.grank * base + std::min(s.grank, rem);
+                const float* cp[64];
+                const float* tp[64];
+                const float* lp[64];
+                PeerSync sync;
+                for (int r = 0; r < world; ++r) {
+                    const float* pb = reinterpret_cast<const float*>(x.peer_x[b][r]);
+                    cp[r] = pb + (size_t)my_first * dv;
+                    tp[r] = pb + (size_t)x.cap_rows * dv + my_first;
+                    lp[r] = pb + (size_t)x.cap_rows * dv + x.cap_rows + my_first;
+                    sync.ready[r] = x.peer_flags[r] + b;
+                }
+                sync.consumed = x.root_flags + 64 + b * 64 + s.grank;   // "rank grank's rows are staged", in the root's memory
+                sync.block_counter = x.flags.as<unsigned int>() + 6 + b;
+                sync.epoch = x.epoch;
+                SDPA_TRY(time_begin(s, 2, s.s_comm));
+                SDPA_TRY(launch_merge_peers_synced(cp, tp, lp, world, my_rows, dv, x.root_stage[b] + (size_t)my_first * dv, sync,
+                                                   s.s_comm));
+                if (s.grank == 0) {
+                    PeerSync col;
+                    for (int r = 0; r < world; ++r) col.ready[r] = x.flags.as<unsigned int>() + 64 + b * 64 + r;
+                    col.consumed = x.flags.as<unsigned int>() + 2 + b;
+                    col.block_counter = x.flags.as<unsigned int>() + 8 + b;
+                    col.epoch = x.epoch;
+                    double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+                    SDPA_TRY(launch_collect_slices(dst, x.stage[b].as<double>(), bs, dv, col, world, s.s_comm));
+                }
+                SDPA_TRY(time_end(s, 2, s.s_comm));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
+                if (s.grank != 0) SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+            } else if (s.grank == 0) {
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
                 const float* cp[64];
                 const float* tp[64];
@@ -1221,6 +1282,8 @@ sdpa_status sdpa_ctx_destroy(sdpa_ctx* ctx)
         ctx->ipc.xbuf[0].release();
         ctx->ipc.xbuf[1].release();
         ctx->ipc.flags.release();
+        ctx->ipc.stage[0].release();
+        ctx->ipc.stage[1].release();
     }
     for (Shard& s : ctx->shards) shard_destroy(s, api);
     delete ctx;

@@ -85,10 +85,13 @@ merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restric
     if (sync.enabled) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
+            __threadfence_system();   // the rows just written may sit in another GPU's memory (sliced merge)
             if (atomicAdd(sync.block_counter, 1u) == gridDim.x - 1) {
                 *sync.block_counter = 0;
-                st_release_sys(sync.consumed, sync.epoch);   // every block has read the peers' buffers: they may be reused
+                __threadfence_system();
+                // root merge: every block has read the peers' buffers, they may be reused;
+                // sliced merge: this rank's rows of the result are in the root's staging buffer
+                st_release_sys(sync.consumed, sync.epoch);
             }
         }
     }
@@ -200,7 +203,28 @@ finalize_reduced_kernel(double* __restrict__ out64, const float* __restrict__ re
     for (int d = lane; d < dv; d += 32) out64[(size_t)row * dv + d] = (double)(reduced[(size_t)row * dv + d] * inv);
 }
 
+// Root GPU, sliced merge: wait until every rank has delivered its rows of the batch into the staging buffer,
+// move them to their destination (the caller's result array or the D2H buffer) and release the slot.
+__global__ void __launch_bounds__(256)
+collect_slices_kernel(double2* __restrict__ dst, const double2* __restrict__ src, size_t units, SyncArgs sync, int count)
+{
+    if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.epoch, 3);
+    __syncthreads();
+    const size_t total = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += total) dst[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(sync.block_counter, 1u) == gridDim.x - 1) {
+            *sync.block_counter = 0;
+            __threadfence_system();
+            st_release_sys(sync.consumed, sync.epoch);   // staging slot and every rank's state slot may be reused
+        }
+    }
+}
+
 }  // namespace
+
 
 sdpa_status launch_finalize_reduced(double* out64, const float* reduced, const float* gsum, int rows, int dv,
                                     cudaStream_t stream)
@@ -270,7 +294,7 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
                                       const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
                                       const PeerSync& sync, cudaStream_t stream)
 {
-    if (rows <= 0) return SDPA_OK;
+    if (rows < 0) rows = 0;   // a rank without rows still has to raise its flag: one block, no row work
     if (shards < 1 || shards > 64) {
         set_error("peer merge supports 1..64 shards (got %d)", shards);
         return SDPA_ERR_INVALID;
@@ -287,11 +311,37 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     sa.block_counter = sync.block_counter;
     sa.epoch = sync.epoch;
     sa.enabled = 1;
-    const int blocks = ceil_div(rows, kWarpsPerBlock);
+    const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     bool vec_ok = al16(out64);
     for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
     merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
                                                                          nullptr, 1.f, vec_ok, sa);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, int dv, const PeerSync& sync, int ranks,
+                                  cudaStream_t stream)
+{
+    if (ranks < 1 || ranks > 64) {
+        set_error("collect_slices supports 1..64 ranks (got %d)", ranks);
+        return SDPA_ERR_INVALID;
+    }
+    if (((size_t)rows * dv) % 2 != 0 || !al16(dst) || !al16(staged)) {
+        set_error("collect_slices needs 16-byte aligned buffers and an even element count");
+        return SDPA_ERR_INVALID;
+    }
+    SyncArgs sa{};
+    for (int r = 0; r < ranks; ++r) sa.ready[r] = sync.ready[r];
+    sa.consumed = sync.consumed;
+    sa.block_counter = sync.block_counter;
+    sa.epoch = sync.epoch;
+    sa.enabled = 1;
+    const size_t units = (size_t)rows * dv / 2;
+    const int blocks = (int)std::max<size_t>(1, std::min<size_t>(148 * 4, (units + 255) / 256));
+    collect_slices_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<double2*>(dst), reinterpret_cast<const double2*>(staged),
+                                                      units, sa, ranks);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

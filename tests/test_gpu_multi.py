@@ -68,8 +68,12 @@ def _rank_worker(rank, world, port, out_dir, id_file):
     Q, K, V = o.make_inputs(m, n, d, d, seed=77)
     ref = o.attention_f64_numpy(Q, K, V) if rank == 0 else None
     first, count = parallel.shard_rows(n, world, rank)
-    for prec, atol, merge in (("f32", 1e-5, "nccl2"), ("bf16", 1e-2, "nccl3"), ("bf16", 1e-2, "peer"), ("f32", 1e-5, "peer")):
+    for prec, atol, merge in (("f32", 1e-5, "nccl2"), ("bf16", 1e-2, "nccl3"), ("bf16", 1e-2, "peer"), ("f32", 1e-5, "peer"),
+                              ("bf16", 1e-2, "peer-root")):
         # (1) pre-sharded inputs, one context per rank (bench.py's model); merge="peer" = CUDA-IPC device-side exchange
+        # (every rank merges its share of the rows; "peer-root" = the first form, the root GPU merges all rows)
+        os.environ["SDPA_IPC_MERGE"] = "root" if merge == "peer-root" else "sliced"
+        merge = "peer" if merge == "peer-root" else merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge=merge)
         ctx.load_kv_host([K[first:first + count]], [V[first:first + count]])
         for _ in range(2):   # twice: slot reuse across calls
