@@ -119,6 +119,18 @@ struct PeerSync {
 sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
                                       const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
                                       const PeerSync& sync, cudaStream_t stream);
+// Sliced merge, source side: merge the split states of `rows` rows and write each row's state into the inbox segment of
+// the rank owning its slice (slice r = rows/world + (r < rows%world) consecutive rows), then raise flag[r] = epoch at every rank.
+struct RouteTargets {
+    float* o[64];
+    float* tmax[64];
+    float* lsum[64];
+    unsigned int* flag[64];
+    unsigned int* block_counter;   // local scratch
+    unsigned int epoch;
+    int world;
+};
+sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const RouteTargets& to, cudaStream_t stream);
 // Sliced merge, root side: wait for every rank's "my rows are staged" flag (sync.ready), copy the staged fp64 batch
 // to dst, then raise sync.consumed.
 sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, int dv, const PeerSync& sync, int ranks,

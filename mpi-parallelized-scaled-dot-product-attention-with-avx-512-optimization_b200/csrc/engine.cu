@@ -196,11 +196,12 @@ struct sdpa_ctx {
     // device-side exchange across processes (one GPU per process): state buffers + flags shared through CUDA IPC
     struct Ipc {
         bool ready = false;
-        int cap_rows = 0, dv = 0;
+        int cap_rows = 0, dv = 0, slice_cap = 0;
         DevBuf xbuf[2];                 // [contrib rows*dv | tmax rows | lsum rows], one per ping-pong slot
-        // uint32 flags: [0..1] ready[slot], [2..3] consumed[slot] (root's copy is the one polled), [4..5] root-merge block
-        // counter, [6..7] slice-merge block counter, [8..9] collect block counter, [64 + slot*64 + r] "rank r's rows of
-        // the batch are staged" (root's copy, written by rank r over NVLink)
+        // uint32 flags: [0..1] ready[slot] (root merge), [2..3] consumed[slot] (root's copy is the one polled), block
+        // counters [4..5] root merge, [6..7] slice merge, [8..9] collect, [10..11] routed split merge;
+        // [64 + slot*64 + r] "rank r's rows of the batch are staged" (root's copy, written by rank r over NVLink);
+        // [128 + slot*64 + r] "source rank r has delivered its state of my rows into my inbox" (written by rank r)
         DevBuf flags;
         DevBuf stage[2];                // fp64 batch assembled from every rank's slice (the root's copy is the one used)
         std::vector<void*> peer_x[2];   // every rank's xbuf (own pointer for itself)
@@ -521,7 +522,12 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
     SDPA_CUDA_TRY(cudaDeviceSynchronize());
     ipc_close(ctx);
     // every rank re-allocates together (the decision depends only on arguments all ranks share)
-    const size_t xbytes = ((size_t)rows_cap * dv + 2 * (size_t)rows_cap) * sizeof(float);
+    // root merge: [o rows*dv | tmax rows | lsum rows]; sliced merge: one inbox segment per source rank,
+    // [o slice*dv | tmax slice | lsum slice] each, slice = rows of one rank's share (rounded up to a multiple of 4)
+    const int slice_cap = ((rows_cap + ctx->world - 1) / ctx->world + 3) & ~3;
+    const size_t xbytes = std::max(((size_t)rows_cap * dv + 2 * (size_t)rows_cap),
+                                   (size_t)ctx->world * slice_cap * ((size_t)dv + 2)) * sizeof(float);
+    x.slice_cap = slice_cap;
     for (int b = 0; b < 2; ++b) {
         x.xbuf[b].release();
         SDPA_TRY(x.xbuf[b].reserve(xbytes));
@@ -763,8 +769,25 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                         if (i == 0) ++x.epoch;
                         if (s.grank != 0 && x.slot_epoch[b] != 0)   // the root must have consumed the slot's previous content
                             SDPA_TRY(launch_wait_flag(x.root_flags + 2 + b, x.slot_epoch[b], s.s_compute));
-                        SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, xc, xt, xl, false, s.s_compute));
-                        SDPA_TRY(launch_signal_flag(x.flags.as<unsigned int>() + b, x.epoch, s.s_compute));
+                        if (x.sliced) {
+                            // push: every row's merged state goes straight into the inbox of the rank that owns its slice
+                            RouteTargets to;
+                            const size_t seg = (size_t)x.slice_cap * ((size_t)dv + 2);
+                            for (int r = 0; r < world; ++r) {
+                                float* in = reinterpret_cast<float*>(x.peer_x[b][r]) + (size_t)s.grank * seg;
+                                to.o[r] = in;
+                                to.tmax[r] = in + (size_t)x.slice_cap * dv;
+                                to.lsum[r] = to.tmax[r] + x.slice_cap;
+                                to.flag[r] = x.peer_flags[r] + 128 + b * 64 + s.grank;
+                            }
+                            to.block_counter = x.flags.as<unsigned int>() + 10 + b;
+                            to.epoch = x.epoch;
+                            to.world = world;
+                            SDPA_TRY(launch_merge_splits_routed(part, bs, dv, to, s.s_compute));
+                        } else {
+                            SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, xc, xt, xl, false, s.s_compute));
+                            SDPA_TRY(launch_signal_flag(x.flags.as<unsigned int>() + b, x.epoch, s.s_compute));
+                        }
                         x.slot_epoch[b] = x.epoch;
                     } else {
                     float* lsum_dst = (two_coll && !use_peer) ? s.contrib[b].as<float>() + (size_t)bs * dv : s.lsum[b].as<float>();
@@ -784,9 +807,9 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             sdpa_ctx::Ipc& x = ctx->ipc;
             SDPA_CUDA_TRY(cudaSetDevice(s.dev));
             if (x.sliced) {
-                // every rank merges its share of the batch rows from all ranks' states (all-to-all reads over NVLink),
-                // writes the fp64 rows into the root's staging buffer and raises its "staged" flag there; the root then
-                // moves the assembled batch to its destination and releases the slots.
+                // every rank merges its share of the batch rows from its inbox (filled by all ranks' routed split merges:
+                // all-to-all posted stores over NVLink), writes the fp64 rows into the root's staging buffer and raises its
+                // "staged" flag there; the root then moves the assembled batch to its destination and releases the slots.
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
                 const int base = bs / world, rem = bs % world;
                 const int my_rows = base + (s.grank < rem ? 1 : 0);
@@ -795,12 +818,13 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 const float* tp[64];
                 const float* lp[64];
                 PeerSync sync;
-                for (int r = 0; r < world; ++r) {
-                    const float* pb = reinterpret_cast<const float*>(x.peer_x[b][r]);
-                    cp[r] = pb + (size_t)my_first * dv;
-                    tp[r] = pb + (size_t)x.cap_rows * dv + my_first;
-                    lp[r] = pb + (size_t)x.cap_rows * dv + x.cap_rows + my_first;
-                    sync.ready[r] = x.peer_flags[r] + b;
+                const size_t seg = (size_t)x.slice_cap * ((size_t)dv + 2);
+                for (int r = 0; r < world; ++r) {   // local inbox: segment r holds source r's state of my rows
+                    const float* in = x.xbuf[b].as<float>() + (size_t)r * seg;
+                    cp[r] = in;
+                    tp[r] = in + (size_t)x.slice_cap * dv;
+                    lp[r] = tp[r] + x.slice_cap;
+                    sync.ready[r] = x.flags.as<unsigned int>() + 128 + b * 64 + r;
                 }
                 sync.consumed = x.root_flags + 64 + b * 64 + s.grank;   // "rank grank's rows are staged", in the root's memory
                 sync.block_counter = x.flags.as<unsigned int>() + 6 + b;

@@ -58,6 +58,10 @@ __global__ void signal_flag_kernel(unsigned int* flag, unsigned int epoch)
 __global__ void wait_flag_kernel(const unsigned int* flag, unsigned int epoch) { spin_until(flag, epoch, 1); }
 
 template <bool FINAL>
+__device__ __forceinline__ void merge_one_row(const struct StatePtrs& st, int count, int row, int dv, double* __restrict__ out64_row,
+                                              float* __restrict__ contrib_row, float* __restrict__ tmax_dst,
+                                              float* __restrict__ lsum_dst, float max_unit, bool vec_ok);
+template <bool FINAL>
 __device__ __forceinline__ void merge_rows(const struct StatePtrs& st, int count, int rows, int dv, double* __restrict__ out64,
                                            float* __restrict__ contrib, float* __restrict__ tmax_out,
                                            float* __restrict__ lsum_out, float max_unit, bool vec_ok);
@@ -102,10 +106,19 @@ __device__ __forceinline__ void merge_rows(const StatePtrs& st, int count, int r
                                            float* __restrict__ contrib, float* __restrict__ tmax_out,
                                            float* __restrict__ lsum_out, float max_unit, bool vec_ok)
 {
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * kWarpsPerBlock + warp;
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= rows) return;
+    merge_one_row<FINAL>(st, count, row, dv, FINAL ? out64 + (size_t)row * dv : nullptr, FINAL ? nullptr : contrib + (size_t)row * dv,
+                         FINAL ? nullptr : tmax_out + row, FINAL ? nullptr : lsum_out + row, max_unit, vec_ok);
+}
+
+// One warp merges `count` states of row `row`; the destinations are already resolved to the row.
+template <bool FINAL>
+__device__ __forceinline__ void merge_one_row(const StatePtrs& st, int count, int row, int dv, double* __restrict__ out64_row,
+                                              float* __restrict__ contrib_row, float* __restrict__ tmax_dst,
+                                              float* __restrict__ lsum_dst, float max_unit, bool vec_ok)
+{
+    const int lane = threadIdx.x & 31;
 
     // lanes hold the per-state statistics (count <= 64: two per lane)
     float t0 = lane < count ? st.tmax[lane][row] : -CUDART_INF_F;
@@ -137,11 +150,11 @@ __device__ __forceinline__ void merge_rows(const StatePtrs& st, int count, int r
                 acc.w = fmaf(v.w, w, acc.w);
             }
             if (FINAL) {
-                double2* dst = reinterpret_cast<double2*>(out64 + (size_t)row * dv + d);
+                double2* dst = reinterpret_cast<double2*>(out64_row + d);
                 dst[0] = make_double2((double)(acc.x * inv), (double)(acc.y * inv));
                 dst[1] = make_double2((double)(acc.z * inv), (double)(acc.w * inv));
             } else {
-                *reinterpret_cast<float4*>(contrib + (size_t)row * dv + d) = acc;
+                *reinterpret_cast<float4*>(contrib_row + d) = acc;
             }
         }
     } else {
@@ -151,13 +164,13 @@ __device__ __forceinline__ void merge_rows(const StatePtrs& st, int count, int r
                 const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
                 acc = fmaf(st.o[s][(size_t)row * dv + d], w, acc);
             }
-            if (FINAL) out64[(size_t)row * dv + d] = (double)(acc * inv);
-            else contrib[(size_t)row * dv + d] = acc;
+            if (FINAL) out64_row[d] = (double)(acc * inv);
+            else contrib_row[d] = acc;
         }
     }
     if (!FINAL && lane == 0) {
-        tmax_out[row] = gmax * max_unit;  // max_unit = 1 (log2 domain) or ln2 (reference's lmax)
-        lsum_out[row] = gsum;
+        *tmax_dst = gmax * max_unit;  // max_unit = 1 (log2 domain) or ln2 (reference's lmax)
+        *lsum_dst = gsum;
     }
 }
 
@@ -201,6 +214,47 @@ finalize_reduced_kernel(double* __restrict__ out64, const float* __restrict__ re
     const float g = gsum[row];
     const float inv = (g == 0.f) ? 0.f : 1.f / g;
     for (int d = lane; d < dv; d += 32) out64[(size_t)row * dv + d] = (double)(reduced[(size_t)row * dv + d] * inv);
+}
+
+// Split merge with routing (push form of the cross-GPU exchange): the merged state of row `row` is written straight
+// into the inbox of the rank that owns the row's slice -- a posted NVLink store instead of a remote read later -- and the
+// last block raises this rank's "delivered" flag at every peer.
+struct RouteArgs {
+    float* o[64];               // per destination rank: this source's segment of its inbox (rows of its slice)
+    float* tmax[64];
+    float* lsum[64];
+    unsigned int* flag[64];     // per destination rank: "source delivered epoch e"
+    unsigned int* block_counter;
+    unsigned int epoch;
+    int base, rem, world;       // slice r has base + (r < rem) rows, slices are consecutive
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+merge_route_kernel(StatePtrs st, int count, int rows, int dv, RouteArgs rt, bool vec_ok)
+{
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row < rows) {
+        const int boundary = rt.rem * (rt.base + 1);
+        int r, local;
+        if (row < boundary) {
+            r = row / (rt.base + 1);
+            local = row - r * (rt.base + 1);
+        } else {
+            r = rt.rem + (row - boundary) / rt.base;
+            local = (row - boundary) - (r - rt.rem) * rt.base;
+        }
+        merge_one_row<false>(st, count, row, dv, nullptr, rt.o[r] + (size_t)local * dv, rt.tmax[r] + local, rt.lsum[r] + local,
+                             1.f, vec_ok);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(rt.block_counter, 1u) == gridDim.x - 1) {
+            *rt.block_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < rt.world; ++r) st_release_sys(rt.flag[r], rt.epoch);
+        }
+    }
 }
 
 // Root GPU, sliced merge: wait until every rank has delivered its rows of the batch into the staging buffer,
@@ -316,6 +370,41 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
     merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
                                                                          nullptr, 1.f, vec_ok, sa);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const RouteTargets& to, cudaStream_t stream)
+{
+    if (part.splits < 1 || part.splits > 64 || to.world < 1 || to.world > 64) {
+        set_error("routed merge supports 1..64 split states and ranks");
+        return SDPA_ERR_INVALID;
+    }
+    if (rows < 0) rows = 0;
+    StatePtrs st;
+    bool vec_ok = true;
+    for (int s = 0; s < part.splits; ++s) {
+        st.o[s] = part.o + (size_t)s * part.rows_capacity * dv;
+        st.tmax[s] = part.tmax + (size_t)s * part.rows_capacity;
+        st.lsum[s] = part.lsum + (size_t)s * part.rows_capacity;
+        vec_ok = vec_ok && al16(st.o[s]);
+    }
+    RouteArgs rt;
+    for (int r = 0; r < to.world; ++r) {
+        rt.o[r] = to.o[r];
+        rt.tmax[r] = to.tmax[r];
+        rt.lsum[r] = to.lsum[r];
+        rt.flag[r] = to.flag[r];
+        vec_ok = vec_ok && al16(to.o[r]);
+    }
+    rt.block_counter = to.block_counter;
+    rt.epoch = to.epoch;
+    rt.world = to.world;
+    rt.base = rows / to.world;
+    rt.rem = rows % to.world;
+    merge_route_kernel<<<std::max(1, ceil_div(rows, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, rt,
+                                                                                                       vec_ok);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

@@ -6,15 +6,15 @@ LIST=${2:-$N}
 mkdir -p gpurun_out
 OUT=gpurun_out
 rm -f $OUT/summary_multi.log
-timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -x -p no:cacheprovider > $OUT/pytest_multi.log 2>&1
+timeout 400 python -m pytest tests/test_gpu_multi.py -q -m gpu -x -p no:cacheprovider > $OUT/pytest_multi.log 2>&1
 echo "pytest_multi rc=$?" >> $OUT/summary_multi.log
 for G in $LIST; do
   for MODE in sliced root; do
     if [ $G -eq 1 ]; then
       [ $MODE = root ] && continue
-      timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline > $OUT/scale_g${G}_$MODE.json 2> $OUT/scale_g${G}_$MODE.err
+      timeout 240 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu-baseline > $OUT/scale_g${G}_$MODE.json 2> $OUT/scale_g${G}_$MODE.err
     else
-      SDPA_IPC_MERGE=$MODE NCCL_DEBUG=WARN timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 \
+      SDPA_IPC_MERGE=$MODE NCCL_DEBUG=WARN timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus $G --steps 20 --warmup 3 > $OUT/scale_g${G}_$MODE.json 2> $OUT/scale_g${G}_$MODE.err
     fi
     echo "bench gpus=$G mode=$MODE rc=$?" >> $OUT/summary_multi.log
