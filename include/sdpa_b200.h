@@ -133,6 +133,14 @@ sdpa_status sdpa_load_kv_host_full(sdpa_ctx* ctx, const double* K, const double*
 sdpa_status sdpa_attention_host(sdpa_ctx* ctx, const double* Q, double* result, int m);
 sdpa_status sdpa_attention_device(sdpa_ctx* ctx, const double* const* Q_dev, double* result_dev, int m);
 
+/* Pinned host memory for callers that choose their allocator (the harness does; replaces read_matrix's malloc,
+ * attention-mpi.c:417-423).  Arrays from malloc work too: pageable sources are staged through a pinned ring by a small
+ * pool of copy threads (SDPA_STAGING_THREADS, default cores/8 capped at 8; SDPA_HOST_STAGING=0 leaves it to the driver). */
+void* sdpa_host_alloc(size_t bytes);
+void sdpa_host_free(void* p);
+/* The staging pool's multi-threaded memcpy by itself (no CUDA): returns the number of threads that took part. */
+int sdpa_host_copy(void* dst, const void* src, size_t bytes);
+
 /* load_kv_device + attention_device in one call (the whole attention() path on device-resident fp64). */
 sdpa_status sdpa_attention_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
                                        const int* n_local, int dk, int dv, const double* const* Q_dev,

@@ -136,4 +136,9 @@ sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const Ro
 sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, int dv, const PeerSync& sync, int ranks,
                                   cudaStream_t stream);
 
+// host_staging.cu: host -> device copies that run at the pinned rate for pageable sources too (pinned ring + copy threads)
+bool host_ptr_is_pageable(const void* p);
+sdpa_status h2d_any(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream);
+int host_staging_lanes();
+
 }  // namespace sdpa

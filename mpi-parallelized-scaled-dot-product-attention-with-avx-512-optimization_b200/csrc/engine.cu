@@ -200,8 +200,9 @@ struct sdpa_ctx {
         DevBuf xbuf[2];                 // [contrib rows*dv | tmax rows | lsum rows], one per ping-pong slot
         // uint32 flags: [0..1] ready[slot] (root merge), [2..3] consumed[slot] (root's copy is the one polled), block
         // counters [4..5] root merge, [6..7] slice merge, [8..9] collect, [10..11] routed split merge;
-        // [64 + slot*64 + r] "rank r's rows of the batch are staged" (root's copy, written by rank r over NVLink);
-        // [128 + slot*64 + r] "source rank r has delivered its state of my rows into my inbox" (written by rank r)
+        // [kFlagStaged + slot*64 + r] "rank r's rows of the batch are staged" (root's copy, written by rank r over NVLink);
+        // [kFlagDelivered + slot*64 + r] "source rank r has delivered its state of my rows into my inbox" (written by rank r)
+        static constexpr int kFlagStaged = 256, kFlagDelivered = 512;   // two slots x 64 ranks each; 4096-byte block
         DevBuf flags;
         DevBuf stage[2];                // fp64 batch assembled from every rank's slice (the root's copy is the one used)
         std::vector<void*> peer_x[2];   // every rank's xbuf (own pointer for itself)
@@ -373,7 +374,7 @@ static sdpa_status upload_cast(Shard& s, int prec, void* dst, const double* src,
         const int b = c & 1;
         SDPA_TRY(s.kv_stage[b].reserve(std::min(kStageElems, count) * sizeof(double)));
         SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_stage_free[b], 0));
-        SDPA_CUDA_TRY(cudaMemcpyAsync(s.kv_stage[b].p, src + done, len * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
+        SDPA_TRY(h2d_any(s.kv_stage[b].p, src + done, len * sizeof(double), s.s_in));   // pinned: direct; pageable: staged
         SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_ready[b], s.s_in));
         SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_stage_ready[b], 0));
         SDPA_TRY(cast_in(prec, (char*)dst + done * esz, s.kv_stage[b].as<double>(), len, s.s_compute));
@@ -537,8 +538,8 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         SDPA_TRY(x.stage[b].reserve((size_t)rows_cap * dv * sizeof(double)));
     }
     if (!x.flags.p) {
-        SDPA_TRY(x.flags.reserve(1024));
-        SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 1024));
+        SDPA_TRY(x.flags.reserve(4096));
+        SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 4096));
         x.epoch = 0;
         x.slot_epoch[0] = x.slot_epoch[1] = 0;
         const char* mode = getenv("SDPA_IPC_MERGE");   // "root": the root GPU merges every row (first form of the exchange)
@@ -714,8 +715,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             } else if (have_q) {
                 // copy stream: wait until the cast of batch ii-2 released this buffer
                 if (ii >= 2) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_q_free[b], 0));
-                SDPA_CUDA_TRY(cudaMemcpyAsync(s.q64[b].p, Q_host + (size_t)row0 * dk, (size_t)bs * dk * sizeof(double),
-                                              cudaMemcpyHostToDevice, s.s_in));
+                SDPA_TRY(h2d_any(s.q64[b].p, Q_host + (size_t)row0 * dk, (size_t)bs * dk * sizeof(double), s.s_in));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_ready[b], s.s_in));
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_q_ready[b], 0));
                 compute_stream_touched(s);
@@ -778,7 +778,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                 to.o[r] = in;
                                 to.tmax[r] = in + (size_t)x.slice_cap * dv;
                                 to.lsum[r] = to.tmax[r] + x.slice_cap;
-                                to.flag[r] = x.peer_flags[r] + 128 + b * 64 + s.grank;
+                                to.flag[r] = x.peer_flags[r] + sdpa_ctx::Ipc::kFlagDelivered + b * 64 + s.grank;
                             }
                             to.block_counter = x.flags.as<unsigned int>() + 10 + b;
                             to.epoch = x.epoch;
@@ -824,9 +824,9 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                     cp[r] = in;
                     tp[r] = in + (size_t)x.slice_cap * dv;
                     lp[r] = tp[r] + x.slice_cap;
-                    sync.ready[r] = x.flags.as<unsigned int>() + 128 + b * 64 + r;
+                    sync.ready[r] = x.flags.as<unsigned int>() + sdpa_ctx::Ipc::kFlagDelivered + b * 64 + r;
                 }
-                sync.consumed = x.root_flags + 64 + b * 64 + s.grank;   // "rank grank's rows are staged", in the root's memory
+                sync.consumed = x.root_flags + sdpa_ctx::Ipc::kFlagStaged + b * 64 + s.grank;   // "rank grank's rows are staged", in the root's memory
                 sync.block_counter = x.flags.as<unsigned int>() + 6 + b;
                 sync.epoch = x.epoch;
                 SDPA_TRY(time_begin(s, 2, s.s_comm));
@@ -834,7 +834,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                                    s.s_comm));
                 if (s.grank == 0) {
                     PeerSync col;
-                    for (int r = 0; r < world; ++r) col.ready[r] = x.flags.as<unsigned int>() + 64 + b * 64 + r;
+                    for (int r = 0; r < world; ++r) col.ready[r] = x.flags.as<unsigned int>() + sdpa_ctx::Ipc::kFlagStaged + b * 64 + r;
                     col.consumed = x.flags.as<unsigned int>() + 2 + b;
                     col.block_counter = x.flags.as<unsigned int>() + 8 + b;
                     col.epoch = x.epoch;
@@ -1062,7 +1062,7 @@ static sdpa_status scatter_operand(sdpa_ctx* ctx, Shard& s, const NcclApi* api, 
                 const int b = c & 1;
                 SDPA_TRY(s.kv_stage[b].reserve(kStageElems * sizeof(double)));
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_stage_free[b], 0));
-                SDPA_CUDA_TRY(cudaMemcpyAsync(s.kv_stage[b].p, src + done, len * sizeof(double), cudaMemcpyHostToDevice, s.s_in));
+                SDPA_TRY(h2d_any(s.kv_stage[b].p, src + done, len * sizeof(double), s.s_in));   // pinned: direct; pageable: staged
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_ready[b], s.s_in));
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_stage_ready[b], 0));
                 void* dst = (char*)my_dst + done * esz;

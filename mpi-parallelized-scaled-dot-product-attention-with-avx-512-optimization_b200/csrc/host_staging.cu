@@ -1,0 +1,238 @@
+// host_staging.cu -- host memory -> HBM for callers that hand over PAGEABLE arrays.
+//
+// The reference harness reads Q, K, V into malloc'd memory (attention-mpi.c:417-423) and the drop-in
+// attention() receives exactly those pointers.  cudaMemcpyAsync from pageable memory is staged by the
+// driver on one thread and runs at a fraction of the PCIe rate; for the c3 problem (142.6 MB of fp64
+// input) that transfer IS the elapsed time of the call.  Here a small pool of host threads copies the
+// next chunk into a pinned ring while the previous chunk is on the wire, so the link stays busy at the
+// pinned rate as long as the pool's memcpy bandwidth exceeds it.  Pinned or registered sources
+// (sdpa_host_alloc, cudaHostAlloc, cudaHostRegister, torch pin_memory) skip the ring.
+//
+// SURVEY 8(f) rank 1 (host I/O + staging path); replaces the root's cvt + Bcast/Scatterv staging of
+// attention-mpi.c:213-266 on the host side of the link.
+#include "common.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace sdpa {
+
+namespace {
+
+constexpr size_t kChunkBytes = (size_t)8 << 20;   // one ring slot
+constexpr int kSlots = 4;
+constexpr int kMaxDevices = 64;
+
+// Fixed pool of helper threads; parallel_copy() splits one memcpy over the helpers and the caller.
+class CopyPool {
+public:
+    CopyPool()
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        int n = (int)(hw / 8);
+        if (const char* e = getenv("SDPA_STAGING_THREADS")) n = atoi(e) - 1;
+        n = std::max(1, std::min(n, 7));
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            quit_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread& t : workers_) t.join();
+    }
+    int lanes() const { return (int)workers_.size() + 1; }
+
+    void parallel_copy(char* dst, const char* src, size_t bytes)
+    {
+        const int parts = lanes();
+        const size_t piece = ((bytes / parts) + 4095) & ~(size_t)4095;   // page-sized pieces
+        if (bytes < ((size_t)1 << 20) || piece == 0) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        size_t off = piece;   // the caller copies [0, piece)
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            while (off < bytes) {
+                const size_t len = std::min(piece, bytes - off);
+                jobs_.push_back(Job{dst + off, src + off, len});
+                ++pending_;
+                off += len;
+            }
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(piece, bytes));
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    struct Job {
+        char* dst;
+        const char* src;
+        size_t len;
+    };
+    void run()
+    {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return quit_ || !jobs_.empty(); });
+                if (quit_ && jobs_.empty()) return;
+                j = jobs_.back();
+                jobs_.pop_back();
+            }
+            memcpy(j.dst, j.src, j.len);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::vector<Job> jobs_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    int pending_ = 0;
+    bool quit_ = false;
+};
+
+}  // namespace
+
+// small public face of the pool for sdpa_host_copy (function-local static: created on first use)
+struct CopyPoolHandle {
+    CopyPool pool;
+    int copy(void* dst, const void* src, size_t bytes)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        pool.parallel_copy(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+        return pool.lanes();
+    }
+    std::mutex mu;
+};
+
+namespace {
+
+struct Stager {
+    std::mutex mu;
+    char* ring[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kSlots][kMaxDevices] = {};
+    cudaEvent_t in_flight[kSlots] = {nullptr, nullptr, nullptr, nullptr};   // last H2D issued from the slot
+    unsigned long long next = 0;
+    CopyPool* pool = nullptr;
+    bool enabled = true;
+    bool configured = false;
+};
+Stager g_stager;
+
+sdpa_status stager_prepare(Stager& st)
+{
+    if (!st.configured) {
+        const char* e = getenv("SDPA_HOST_STAGING");   // 0: leave pageable sources to the driver (for comparison)
+        st.enabled = !(e && *e == '0');
+        st.configured = true;
+    }
+    if (!st.enabled) return SDPA_OK;
+    if (!st.ring[0]) {
+        for (int k = 0; k < kSlots; ++k)
+            SDPA_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&st.ring[k]), kChunkBytes, cudaHostAllocPortable));
+    }
+    if (!st.pool) st.pool = new CopyPool();
+    return SDPA_OK;
+}
+
+}  // namespace
+
+bool host_ptr_is_pageable(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();   // old drivers report plain host memory as an error
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+sdpa_status h2d_any(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream)
+{
+    if (bytes == 0) return SDPA_OK;
+    if (!host_ptr_is_pageable(src_host)) {
+        SDPA_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
+        return SDPA_OK;
+    }
+    Stager& st = g_stager;
+    std::lock_guard<std::mutex> lk(st.mu);
+    SDPA_TRY(stager_prepare(st));
+    if (!st.enabled) {
+        SDPA_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, stream));
+        return SDPA_OK;
+    }
+    int dev = 0;
+    SDPA_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) {
+        set_error("h2d_any: device index %d out of range", dev);
+        return SDPA_ERR_INVALID;
+    }
+    const char* src = static_cast<const char*>(src_host);
+    char* dst = static_cast<char*>(dst_dev);
+    for (size_t off = 0; off < bytes; off += kChunkBytes) {
+        const size_t len = std::min(kChunkBytes, bytes - off);
+        const int slot = (int)(st.next++ % kSlots);
+        if (st.in_flight[slot]) SDPA_CUDA_TRY(cudaEventSynchronize(st.in_flight[slot]));   // the slot's last copy has left
+        st.pool->parallel_copy(st.ring[slot], src + off, len);
+        SDPA_CUDA_TRY(cudaMemcpyAsync(dst + off, st.ring[slot], len, cudaMemcpyHostToDevice, stream));
+        if (!st.ev[slot][dev]) SDPA_CUDA_TRY(cudaEventCreateWithFlags(&st.ev[slot][dev], cudaEventDisableTiming));
+        SDPA_CUDA_TRY(cudaEventRecord(st.ev[slot][dev], stream));
+        st.in_flight[slot] = st.ev[slot][dev];
+    }
+    return SDPA_OK;
+}
+
+int host_staging_lanes()
+{
+    Stager& st = g_stager;
+    std::lock_guard<std::mutex> lk(st.mu);
+    return st.pool ? st.pool->lanes() : 0;
+}
+
+}  // namespace sdpa
+
+extern "C" {
+
+/* Pinned host memory for callers that can choose their allocator (the harness does): transfers from it run at the
+ * full PCIe rate without the staging ring.  Plays the part of read_matrix's malloc (attention-mpi.c:417-423). */
+void* sdpa_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        sdpa::set_error("sdpa_host_alloc: cannot pin %zu bytes", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void sdpa_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+/* The staging pool's multi-threaded memcpy on its own (no CUDA involved): lets tests and host-side benchmarks check
+ * the copy that feeds the pinned ring.  Returns the number of threads that took part. */
+int sdpa_host_copy(void* dst, const void* src, size_t bytes)
+{
+    static sdpa::CopyPoolHandle pool;
+    return pool.copy(dst, src, bytes);
+}
+
+}  // extern "C"

@@ -76,6 +76,9 @@ ABI = {
     "sdpa_attention_host": (ctypes.c_int, [_V, _V, _V, ctypes.c_int]),
     "sdpa_attention_device": (ctypes.c_int, [_V, _dpp, _V, ctypes.c_int]),
     "sdpa_attention_device_full": (ctypes.c_int, [_V, _dpp, _dpp, _ip, ctypes.c_int, ctypes.c_int, _dpp, _V, ctypes.c_int]),
+    "sdpa_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "sdpa_host_free": (None, [_V]),
+    "sdpa_host_copy": (ctypes.c_int, [_V, _V, ctypes.c_size_t]),
     "sdpa_enqueue_device_full": (ctypes.c_int, [_V, _dpp, _dpp, _ip, ctypes.c_int, ctypes.c_int, _dpp, _V, ctypes.c_int]),
     "sdpa_synchronize": (ctypes.c_int, [_V]),
     "sdpa_scatter_attention": (ctypes.c_int, [_V, _V, _V, _V, _V] + [ctypes.c_int] * 4),

@@ -50,3 +50,20 @@ def test_no_cpu_fallback(sdpa):
 
 def test_version_string(sdpa):
     assert "sm_100a" in sdpa.version()
+
+
+def test_staging_pool_copy_is_exact(sdpa):
+    """The multi-threaded memcpy that feeds the pinned staging ring (csrc/host_staging.cu): every size class,
+    odd offsets, repeated use of the pool."""
+    import numpy as np
+    rng = np.random.default_rng(11)
+    L = sdpa.lib()
+    for nbytes in (0, 1, 4095, 1 << 20, (1 << 20) + 1, 3 * (1 << 20) + 12345, 8 << 20, (8 << 20) + 4097):
+        src = rng.integers(0, 256, nbytes + 64, dtype=np.uint8)
+        dst = np.zeros(nbytes + 64, dtype=np.uint8)
+        for off in (0, 3):
+            dst[:] = 0
+            lanes = L.sdpa_host_copy(dst.ctypes.data + off, src.ctypes.data + off, nbytes)
+            assert lanes >= 2
+            assert np.array_equal(dst[off:off + nbytes], src[off:off + nbytes])
+            assert not dst[:off].any() and not dst[off + nbytes:].any()
