@@ -69,11 +69,11 @@ def _rank_worker(rank, world, port, out_dir, id_file):
     ref = o.attention_f64_numpy(Q, K, V) if rank == 0 else None
     first, count = parallel.shard_rows(n, world, rank)
     for prec, atol, merge in (("f32", 1e-5, "nccl2"), ("bf16", 1e-2, "nccl3"), ("bf16", 1e-2, "peer"), ("f32", 1e-5, "peer"),
-                              ("bf16", 1e-2, "peer-root")):
+                              ("bf16", 1e-2, "peer-sliced"), ("f32", 1e-5, "peer-sliced")):
         # (1) pre-sharded inputs, one context per rank (bench.py's model); merge="peer" = CUDA-IPC device-side exchange
-        # (every rank merges its share of the rows; "peer-root" = the first form, the root GPU merges all rows)
-        os.environ["SDPA_IPC_MERGE"] = "root" if merge == "peer-root" else "sliced"
-        merge = "peer" if merge == "peer-root" else merge
+        # (the root GPU merges all rows; "peer-sliced" = every rank merges its share of the rows from a pushed inbox)
+        os.environ["SDPA_IPC_MERGE"] = "sliced" if merge == "peer-sliced" else "root"
+        merge = "peer" if merge == "peer-sliced" else merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge=merge)
         ctx.load_kv_host([K[first:first + count]], [V[first:first + count]])
         for _ in range(2):   # twice: slot reuse across calls
