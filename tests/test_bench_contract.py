@@ -32,3 +32,21 @@ def test_our_arm_refuses_without_gpu(sdpa):
         pytest.skip("GPU present")
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300, cwd=str(ROOT))
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_clock_sampler_summary_and_graceful_start():
+    """bench.py's clock sampler: idle samples are dropped, the median / reasons / power come from the loaded ones;
+    without NVML or nvidia-smi (this container) start() returns an inert sampler instead of failing."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    s = bench.ClockSampler(0, None, allow_subprocess=False)
+    s.rows = [(1965.0, 1965.0, 120.0, []), (1800.0, 1965.0, 900.0, ["sw_power_cap"]), (1780.0, 1965.0, 950.0, ["sw_power_cap"]),
+              (1770.0, 1965.0, 910.0, [])]
+    out = s.summary()
+    assert out["sm_mhz"] == 1780.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"] and out["power_w_max"] == 950.0
+    live = bench.ClockSampler(0, None, allow_subprocess=False).start()
+    with live:
+        pass
+    live.close()
+    assert live.summary()["samples"] >= 0

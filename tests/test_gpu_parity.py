@@ -234,6 +234,10 @@ def test_harness_protocol(sdpa, oracle, torch_cuda, tmp_path):
     oracle.write_data_file(bad, Q, K, V, ref + 0.05)
     r = subprocess.run([str(exe), str(good)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("Correct!\nElapsed time: ") and r.stdout.rstrip().endswith("us"), r
+    # malloc'd matrices like the reference's read_matrix (mpi.c:417-423): the library stages them itself
+    import os
+    r = subprocess.run([str(exe), str(good)], capture_output=True, text=True, timeout=300, env={**os.environ, "HARNESS_PAGEABLE": "1"})
+    assert r.returncode == 0 and r.stdout.startswith("Correct!\nElapsed time: "), r
     r = subprocess.run([str(exe), str(bad)], capture_output=True, text=True, timeout=300)
     assert "Wrong!" in r.stdout
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
