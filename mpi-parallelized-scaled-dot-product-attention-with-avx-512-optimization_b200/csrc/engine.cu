@@ -193,6 +193,12 @@ struct sdpa_ctx {
     bool last_timing_valid = true;          // false: last_timing[0..3] still have to be computed from the event pairs
     double acc_fused_launches = 0, acc_calls = 0;
     const char* last_kernel = "none";
+    // EXPERIMENTAL (SDPA_OVERLAP_PASSES=1, one GPU per process, queued passes only; off by default, not yet measured):
+    // consecutive queued passes alternate exchange slots and are not joined at the end of the call, so the comm stream
+    // merges pass i while the compute stream already runs the cast and fused kernel of pass i+1.
+    bool overlap_passes = false;
+    unsigned long long batch_seq = 0;       // batches issued in overlap mode (slot = batch_seq & 1)
+    bool exchange_pending = false;          // overlap mode left exchange work behind: drain before freeing / reallocating slots
     // device-side exchange across processes (one GPU per process): state buffers + flags shared through CUDA IPC
     struct Ipc {
         bool ready = false;
@@ -279,6 +285,7 @@ static sdpa_status fold_timings(Shard& s)
 {
     SDPA_CUDA_TRY(cudaSetDevice(s.dev));
     SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));   // queued passes (sdpa_enqueue_*) must have finished
+    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_comm));
     for (int w = 0; w < 4; ++w) {
         double ms = 0.0;
         SDPA_TRY(sum_pairs(s, w, 0, &ms));
@@ -512,12 +519,33 @@ static void ipc_close(sdpa_ctx* ctx)
     ctx->ipc.ready = false;
 }
 
+// Overlap mode: wait until the root has consumed every slot this rank published and all streams are idle.
+static sdpa_status drain_exchange(sdpa_ctx* ctx)
+{
+    if (!ctx->exchange_pending) return SDPA_OK;
+    for (Shard& s : ctx->shards) {
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        if (ctx->ipc.ready && s.grank != 0) {
+            for (int b = 0; b < 2; ++b)
+                if (ctx->ipc.slot_epoch[b] != 0)
+                    SDPA_TRY(launch_wait_flag(ctx->ipc.root_flags + 2 + b, ctx->ipc.slot_epoch[b], s.s_compute));
+            compute_stream_touched(s);
+        }
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_comm));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_out));
+    }
+    ctx->exchange_pending = false;
+    return SDPA_OK;
+}
+
 static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
 {
     sdpa_ctx::Ipc& x = ctx->ipc;
     if (x.ready && x.cap_rows >= rows_cap && x.dv == dv) return SDPA_OK;
     const NcclApi* api = nccl_api();
     if (!api) return SDPA_ERR_NCCL;
+    SDPA_TRY(drain_exchange(ctx));
     Shard& s = ctx->shards[0];
     SDPA_CUDA_TRY(cudaSetDevice(s.dev));
     SDPA_CUDA_TRY(cudaDeviceSynchronize());
@@ -637,6 +665,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     const NcclApi* api = nullptr;
     const bool use_peer = world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && ctx->peer_ok && world == L;
     const bool use_ipc = world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && L == 1 && world > L;   // one GPU per process
+    const bool overlap = !blocking && use_ipc && ctx->overlap_passes && Q_dev != nullptr && result_on_device;
     const bool two_coll = ctx->cfg.merge != SDPA_MERGE_NCCL;   // NCCL2 (default) unless the reference's 3-collective form is asked for
     if ((world > 1 && !use_peer && !use_ipc) || q_from_root) {
         api = nccl_api();
@@ -704,7 +733,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     for (int ii = 0; ii < num_iter; ++ii) {
         const int row0 = ii * B;
         const int bs = std::min(B, m - row0);
-        const int b = ii & 1;
+        const int b = overlap ? (int)(ctx->batch_seq & 1) : (ii & 1);
 
         // ---- per shard: Q batch in, cast, fused kernel, split merge -------------------------
         for (int i = 0; i < L; ++i) {
@@ -725,7 +754,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 q_src_dev = s.q64[b].as<double>();
             }
             // slot b (contrib/out buffers) must have been drained by batch ii-2's collectives / D2H
-            if (ii >= 2 && use_out) {
+            if ((overlap ? ctx->batch_seq >= 2 : ii >= 2) && use_out) {
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_slot_free[b], 0));
                 compute_stream_touched(s);
             }
@@ -994,9 +1023,10 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                               cudaMemcpyDeviceToHost, s.s_out));
             SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_out));
         }
+        if (overlap) ++ctx->batch_seq;
     }
 
-    if (use_ipc && ctx->shards[0].grank != 0) {
+    if (use_ipc && ctx->shards[0].grank != 0 && !overlap) {
         // do not return (and possibly free or overwrite the slots) before the root has read them
         Shard& s = ctx->shards[0];
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
@@ -1012,7 +1042,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         Shard& s = ctx->shards[i];
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         cudaStream_t side[3] = {s.s_in, s.s_comm, s.s_out};
-        const bool used[3] = {use_in, use_comm, use_out};
+        const bool used[3] = {use_in, use_comm && !overlap, use_out && !overlap};   // overlap: the slots' own guards order the passes
         for (int j = 0; j < 3; ++j) {
             if (!used[j]) continue;
             SDPA_CUDA_TRY(cudaEventRecord(s.ev_join[j], side[j]));
@@ -1028,6 +1058,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     }
 
     const double hp2 = host_prof ? host_now_us() : 0.0;
+    if (overlap) ctx->exchange_pending = true;
     ctx->last_timing_valid = false;   // evaluated lazily by sdpa_last_timings / sdpa_accumulated_timings
     ctx->acc_fused_launches += fused_launches;
     ctx->acc_calls += 1;
@@ -1241,6 +1272,10 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
     ctx->cfg = cfg;
     ctx->world = world;
     ctx->rank_base = cfg.rank_base;
+    {
+        const char* ov = getenv("SDPA_OVERLAP_PASSES");
+        ctx->overlap_passes = ov && *ov == '1';
+    }
     ctx->shards.resize(L);
     sdpa_status st = SDPA_OK;
     for (int i = 0; i < L && st == SDPA_OK; ++i) {
@@ -1303,6 +1338,7 @@ sdpa_status sdpa_ctx_destroy(sdpa_ctx* ctx)
     for (Shard& s : ctx->shards)
         if (s.comm) api = nccl_api();
     if (!ctx->shards.empty()) {
+        drain_exchange(ctx);
         cudaSetDevice(ctx->shards[0].dev);
         cudaDeviceSynchronize();
         ipc_close(ctx);
@@ -1396,6 +1432,7 @@ sdpa_status sdpa_synchronize(sdpa_ctx* ctx)
         set_error("sdpa_synchronize: ctx is NULL");
         return SDPA_ERR_INVALID;
     }
+    SDPA_TRY(drain_exchange(ctx));
     for (Shard& s : ctx->shards) {
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
@@ -1447,6 +1484,7 @@ sdpa_status sdpa_last_timings(sdpa_ctx* ctx, float* out6)
         for (Shard& s : ctx->shards) {
             SDPA_CUDA_TRY(cudaSetDevice(s.dev));
             SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));   // queued passes (sdpa_enqueue_*) must have finished
+            SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_comm));
             const int slot[4] = {3, 0, 1, 2};   // out[0] total, [1] casts, [2] fused, [3] merge
             for (int k = 0; k < 4; ++k) {
                 double ms = 0.0;

@@ -52,6 +52,41 @@ def _free_port():
     return p
 
 
+def _overlap_worker(rank, world, port, out_dir):
+    """Queued passes with SDPA_OVERLAP_PASSES=1 (experimental): the exchange of pass i overlaps the compute of pass i+1."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), SDPA_OVERLAP_PASSES="1")
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from sdpa_b200 import parallel
+    from oracle import oracle as o
+
+    m, d = 1500, 128
+    cases = [o.make_inputs(m, 4000 + 300 * k, d, d, seed=90 + k) for k in range(3)]   # different K/V/Q per pass
+    for prec, atol in (("bf16", 1e-2), ("f32", 1e-5)):
+        ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge="peer")
+        dev, outs = [], []
+        for Q, K, V in cases:
+            first, count = parallel.shard_rows(K.shape[0], world, rank)
+            dev.append([torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (K[first:first + count], V[first:first + count], Q)])
+            outs.append(torch.zeros(m, d, dtype=torch.float64, device="cuda") if rank == 0 else None)
+        for rep in range(3):
+            for (Kd, Vd, Qd), out in zip(dev, outs):
+                ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], d, d, [Qd.data_ptr()],
+                                          out.data_ptr() if out is not None else None, m, blocking=False)
+        ctx.synchronize()
+        if rank == 0:
+            for (Q, K, V), out in zip(cases, outs):
+                np.testing.assert_allclose(out.cpu().numpy(), o.attention_f64_numpy(Q, K, V), rtol=0, atol=atol)
+        ctx.close()
+    dist.barrier()
+    Path(out_dir, f"ok{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
 def _rank_worker(rank, world, port, out_dir, id_file):
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
@@ -115,4 +150,14 @@ def test_one_process_per_gpu(sdpa, oracle, tmp_path):
     import torch.multiprocessing as mp
     world = 2
     mp.spawn(_rank_worker, args=(world, _free_port(), str(tmp_path), str(tmp_path / "nccl_id")), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(os.environ.get("SDPA_TEST_EXPERIMENTAL") != "1", reason="experimental path: set SDPA_TEST_EXPERIMENTAL=1")
+def test_overlapped_queued_passes(sdpa, oracle, tmp_path):
+    _need_gpus(sdpa, 2)
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_overlap_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
