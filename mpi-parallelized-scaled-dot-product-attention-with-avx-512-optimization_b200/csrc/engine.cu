@@ -154,7 +154,6 @@ struct Shard {
     DevBuf out32[2], out64[2];                  // root: reduced fp32 batch / fp64 batch for D2H
     cudaEvent_t ev_compute_done[2] = {nullptr, nullptr}, ev_slot_free[2] = {nullptr, nullptr};
     cudaEvent_t ev_comm_done[2] = {nullptr, nullptr};
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // K/V casts of a device-resident call that wait for the first Q batch so that all three share one launch
     void* pend_dst[2] = {nullptr, nullptr};
     const double* pend_src[2] = {nullptr, nullptr};
@@ -331,8 +330,6 @@ static sdpa_status shard_init(Shard& s)
         SDPA_CUDA_TRY(mk(&s.ev_comm_done[b]));
     }
     for (int j = 0; j < 3; ++j) SDPA_CUDA_TRY(mk(&s.ev_join[j]));
-    SDPA_CUDA_TRY(cudaEventCreate(&s.ev_begin));
-    SDPA_CUDA_TRY(cudaEventCreate(&s.ev_end));
     int sms = 0;
     SDPA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.dev));
     s.sm_count = sms > 0 ? sms : 148;
@@ -353,7 +350,7 @@ static void shard_destroy(Shard& s, const NcclApi* api)
     cudaEvent_t evs[] = {s.ev_stage_ready[0], s.ev_stage_ready[1], s.ev_stage_free[0], s.ev_stage_free[1],
                          s.ev_q_ready[0], s.ev_q_ready[1], s.ev_q_free[0], s.ev_q_free[1],
                          s.ev_compute_done[0], s.ev_compute_done[1], s.ev_slot_free[0], s.ev_slot_free[1],
-                         s.ev_comm_done[0], s.ev_comm_done[1], s.ev_begin, s.ev_end,
+                         s.ev_comm_done[0], s.ev_comm_done[1],
                          s.ev_join[0], s.ev_join[1], s.ev_join[2]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
