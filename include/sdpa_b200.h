@@ -49,6 +49,14 @@ typedef enum sdpa_merge {
                             [contrib | lsum] with the normalisation + fp64 cast fused after it (default)   */
 } sdpa_merge;
 
+/* How one process spreads the problem over its GPUs -- the GPU analogue of the reference's Bcast-vs-Scatterv
+ * switch for K/V (mpi.c:213-215).  Applies to sdpa_load_kv_host_full / attention() with num_local > 1. */
+typedef enum sdpa_distribution {
+    SDPA_DIST_KV = 0,  /* K/V rows sharded by owner_count/owner_disp, Q replicated, one exchange per batch (the reference's way) */
+    SDPA_DIST_Q = 1,   /* K/V replicated on every GPU, Q rows sharded, no exchange: pays when n is small                        */
+    SDPA_DIST_AUTO = 2 /* DIST_Q when n*(dk+dv)*4 bytes < 64 MiB (the reference's own threshold), else DIST_KV                  */
+} sdpa_distribution;
+
 typedef struct sdpa_config {
     int precision;   /* sdpa_precision                                              */
     int q_batch;     /* Q rows per ping-pong batch (reference: B=512, mpi.c:200); 0 = engine default */
@@ -58,7 +66,8 @@ typedef struct sdpa_config {
     int first_device;/* CUDA ordinal of the first local GPU                         */
     int world_size;  /* total K/V shards over all processes; 0 = num_local          */
     int rank_base;   /* global shard index of this process's first local GPU        */
-    int reserved[8];
+    int distribution;/* sdpa_distribution (single-process contexts)                 */
+    int reserved[7];
 } sdpa_config;
 
 typedef struct sdpa_ctx sdpa_ctx;

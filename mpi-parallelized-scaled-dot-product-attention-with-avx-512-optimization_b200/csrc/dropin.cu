@@ -89,6 +89,8 @@ sdpa_ctx* get_ctx(int mpi_rank, int mpi_size)
     const char* mg = getenv("SDPA_MERGE");
     cfg.merge = (mg && !strcmp(mg, "peer")) ? SDPA_MERGE_PEER : (mg && !strcmp(mg, "nccl3")) ? SDPA_MERGE_NCCL : SDPA_MERGE_NCCL2;
     if (mpi_size <= 1) {
+        const char* dist = getenv("SDPA_DISTRIBUTION");   // kv (default, the reference's sharding) | q | auto
+        cfg.distribution = (dist && !strcmp(dist, "q")) ? SDPA_DIST_Q : (dist && !strcmp(dist, "auto")) ? SDPA_DIST_AUTO : SDPA_DIST_KV;
         cfg.num_local = env_int("SDPA_NGPUS", 1);
         cfg.first_device = env_int("SDPA_FIRST_DEVICE", 0);
         cfg.world_size = cfg.num_local;

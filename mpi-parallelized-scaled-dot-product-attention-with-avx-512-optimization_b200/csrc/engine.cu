@@ -195,6 +195,7 @@ struct sdpa_ctx {
     // EXPERIMENTAL (SDPA_OVERLAP_PASSES=1, one GPU per process, queued passes only; off by default, not yet measured):
     // consecutive queued passes alternate exchange slots and are not joined at the end of the call, so the comm stream
     // merges pass i while the compute stream already runs the cast and fused kernel of pass i+1.
+    bool qshard = false;                    // SDPA_DIST_Q in effect: every shard holds ALL K/V rows, Q rows are sharded, no exchange
     bool overlap_passes = false;
     unsigned long long batch_seq = 0;       // batches issued in overlap mode (slot = batch_seq & 1)
     bool exchange_pending = false;          // overlap mode left exchange work behind: drain before freeing / reallocating slots
@@ -408,6 +409,7 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
     ctx->dk = dk;
     ctx->dv = dv;
     ctx->prec = prec;
+    ctx->qshard = false;   // sdpa_load_kv_host_full sets it again when it replicates
     const size_t esz = elem_size(prec);
     for (size_t i = 0; i < ctx->shards.size(); ++i) {
         Shard& s = ctx->shards[i];
@@ -1072,6 +1074,118 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
 
 
 // ---------------------------------------------------------------------------
+// SDPA_DIST_Q: K/V replicated on every local GPU (sdpa_load_kv_host_full), Q rows sharded by
+// owner_count/owner_disp over the GPUs, every GPU writes its own rows of the result -- no exchange at all.
+// The GPU analogue of the reference's small-problem branch (Bcast of the whole K/V, mpi.c:213-231); SURVEY 8(f) rank 3.
+// Same per-batch pipeline as attention_impl (H2D on the copy-in stream, cast + fused kernel + split merge on the
+// compute stream, D2H on the copy-out stream, two slots), once per GPU.
+// ---------------------------------------------------------------------------
+static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double* result, int m)
+{
+    if (!ctx || m < 0 || (m > 0 && (!Q || !result))) {
+        set_error("attention (Q-sharded): bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    const int dk = ctx->dk, dv = ctx->dv;
+    const int L = (int)ctx->shards.size();
+    ctx->last_kernel = ctx->prec == SDPA_PREC_BF16 ? "bf16_umma" : "f32_simt";
+    for (float& t : ctx->last_timing) t = 0.f;
+    ctx->last_timing_valid = true;
+    if (m == 0) return SDPA_OK;
+
+    int most_rows = 0;
+    for (int i = 0; i < L; ++i) most_rows = std::max(most_rows, sdpa_owner_count(m, L, i));
+    const int B = pick_q_batch(ctx, most_rows);
+    int splits = ctx->cfg.kv_splits;
+    if (splits <= 0)
+        splits = ctx->prec == SDPA_PREC_BF16 ? attn_umma_pick_splits(B, ctx->shards[0].n_local, ctx->shards[0].sm_count)
+                                             : attn_f32_pick_splits(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
+    splits = std::max(1, std::min(splits, 64));
+    const unsigned long long launches_before = launch_count();
+    int fused_launches = 0;
+
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        SDPA_TRY(reserve_batch_buffers(ctx, s, B, splits, true));   // every GPU delivers rows: all need the fp64 out buffers
+        if (s.marks_used > 2048) SDPA_TRY(fold_timings(s));
+        for (int w = 0; w < 4; ++w) s.tpair_last[w] = s.tpair[w].size();
+        compute_stream_touched(s);
+        if (ctx->prec == SDPA_PREC_BF16)
+            for (int b = 0; b < 2; ++b)
+                SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk));
+        SDPA_TRY(time_begin(s, 3, s.s_compute));
+        cudaEvent_t begun = s.marks[s.tpair[3].back()];
+        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, begun, 0));
+        SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, begun, 0));
+    }
+
+    const int num_iter = ceil_div(most_rows, B);
+    for (int ii = 0; ii < num_iter; ++ii) {
+        const int b = ii & 1;
+        for (int i = 0; i < L; ++i) {
+            Shard& s = ctx->shards[i];
+            const int my_rows = sdpa_owner_count(m, L, i);
+            const int row0 = ii * B;
+            if (row0 >= my_rows) continue;
+            const int bs = std::min(B, my_rows - row0);
+            const size_t grow0 = (size_t)sdpa_owner_disp(m, L, i) + row0;   // first global row of this batch
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            if (ii >= 2) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, s.ev_q_free[b], 0));
+            SDPA_TRY(h2d_any(s.q64[b].p, Q + grow0 * dk, (size_t)bs * dk * sizeof(double), s.s_in));
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_ready[b], s.s_in));
+            SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_q_ready[b], 0));
+            if (ii >= 2) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_slot_free[b], 0));   // out64[b] has been copied out
+            compute_stream_touched(s);
+
+            SDPA_TRY(time_begin(s, 0, s.s_compute));
+            SDPA_TRY(cast_in(ctx->prec, s.qc[b].p, s.q64[b].as<double>(), (size_t)bs * dk, s.s_compute));
+            SDPA_TRY(time_end(s, 0, s.s_compute));
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_free[b], s.s_compute));
+
+            Partials part{s.part_o.as<float>(), s.part_tmax.as<float>(), s.part_lsum.as<float>(), splits, B};
+            double* dst = s.out64[b].as<double>();
+            SDPA_TRY(time_begin(s, 1, s.s_compute));
+            SDPA_TRY(run_fused(ctx, s, b, bs, splits, part, splits == 1 ? dst : nullptr));
+            SDPA_TRY(time_end(s, 1, s.s_compute));
+            ++fused_launches;
+            if (splits > 1) {
+                SDPA_TRY(time_begin(s, 2, s.s_compute));
+                SDPA_TRY(launch_merge_splits(part, bs, dv, dst, nullptr, nullptr, nullptr, false, s.s_compute));
+                SDPA_TRY(time_end(s, 2, s.s_compute));
+            }
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
+            SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, s.ev_compute_done[b], 0));
+            SDPA_CUDA_TRY(cudaMemcpyAsync(result + grow0 * dv, dst, (size_t)bs * dv * sizeof(double), cudaMemcpyDeviceToHost, s.s_out));
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_out));
+        }
+    }
+
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        cudaStream_t side[2] = {s.s_in, s.s_out};
+        for (int j = 0; j < 2; ++j) {
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_join[j], side[j]));
+            SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_join[j], 0));
+        }
+        compute_stream_touched(s);
+        SDPA_TRY(time_end(s, 3, s.s_compute));
+    }
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+    }
+    ctx->last_timing_valid = false;
+    ctx->acc_fused_launches += fused_launches;
+    ctx->acc_calls += 1;
+    ctx->last_timing[4] = (float)fused_launches;
+    ctx->last_timing[5] = (float)(launch_count() - launches_before);
+    return SDPA_OK;
+}
+
+// ---------------------------------------------------------------------------
 // One process per GPU, data on rank 0 only: the reference's own calling convention
 // (mpi.c:193-197 dims Bcast, mpi.c:213-266 K/V distribution, mpi.c:305,327 Q Ibcast).
 // Rank 0 uploads each destination's rows in fp64 chunks, casts them on its GPU and
@@ -1375,17 +1489,25 @@ sdpa_status sdpa_load_kv_host_full(sdpa_ctx* ctx, const double* K, const double*
     const int L = (int)ctx->shards.size();
     std::vector<const double*> kp(L), vp(L);
     std::vector<int> cnt(L);
+    // Distribution policy, the GPU analogue of the reference's Bcast-vs-Scatterv switch (mpi.c:213-215: K/V under 64 MiB
+    // in fp32 are broadcast whole): with K/V replicated the Q rows can be sharded instead and no exchange is needed.
+    const int mode = ctx->cfg.distribution;
+    const bool small = (size_t)n * ((size_t)dk + dv) * sizeof(float) < ((size_t)64 << 20);
+    const bool replicate = L > 1 && n > 0 && (mode == SDPA_DIST_Q || (mode == SDPA_DIST_AUTO && small));
     for (int i = 0; i < L; ++i) {
-        cnt[i] = sdpa_owner_count(n, L, i);
-        const int d = sdpa_owner_disp(n, L, i);
+        cnt[i] = replicate ? n : sdpa_owner_count(n, L, i);
+        const int d = replicate ? 0 : sdpa_owner_disp(n, L, i);
         kp[i] = K ? K + (size_t)d * dk : nullptr;
         vp[i] = V ? V + (size_t)d * dv : nullptr;
     }
-    return load_kv(ctx, kp.data(), vp.data(), cnt.data(), dk, dv, false);
+    SDPA_TRY(load_kv(ctx, kp.data(), vp.data(), cnt.data(), dk, dv, false));
+    ctx->qshard = replicate;
+    return SDPA_OK;
 }
 
 sdpa_status sdpa_attention_host(sdpa_ctx* ctx, const double* Q, double* result, int m)
 {
+    if (ctx && ctx->qshard && ctx->dk != 0) return attention_qshard_host(ctx, Q, result, m);
     return attention_impl(ctx, Q, nullptr, result, false, m);
 }
 
@@ -1394,6 +1516,10 @@ sdpa_status sdpa_attention_device(sdpa_ctx* ctx, const double* const* Q_dev, dou
     if (m > 0 && !Q_dev) {
         set_error("sdpa_attention_device: Q_dev is NULL");
         return SDPA_ERR_INVALID;
+    }
+    if (ctx && ctx->qshard) {
+        set_error("sdpa_attention_device: the resident K/V is replicated (SDPA_DIST_Q); that distribution serves host arrays only");
+        return SDPA_ERR_UNSUPPORTED;
     }
     return attention_impl(ctx, nullptr, Q_dev, result_dev, true, m);
 }

@@ -31,6 +31,8 @@ LIB_PATH = PKG_DIR / "libsdpa_b200.so"
 PREC_AUTO, PREC_F32, PREC_BF16 = 0, 1, 2
 MERGE_NCCL, MERGE_PEER, MERGE_NCCL2 = 0, 1, 2
 _MERGE = {"nccl": MERGE_NCCL2, "nccl2": MERGE_NCCL2, "nccl3": MERGE_NCCL, "peer": MERGE_PEER}
+DIST_KV, DIST_Q, DIST_AUTO = 0, 1, 2
+_DIST = {"kv": DIST_KV, "q": DIST_Q, "auto": DIST_AUTO}
 _PREC = {"auto": PREC_AUTO, "f32": PREC_F32, "fp32": PREC_F32, "bf16": PREC_BF16}
 
 _dp = ctypes.POINTER(ctypes.c_double)
@@ -53,7 +55,8 @@ class Config(ctypes.Structure):
         ("first_device", ctypes.c_int),
         ("world_size", ctypes.c_int),
         ("rank_base", ctypes.c_int),
-        ("reserved", ctypes.c_int * 8),
+        ("distribution", ctypes.c_int),
+        ("reserved", ctypes.c_int * 7),
     ]
 
 
@@ -213,7 +216,7 @@ class Context:
 
     def __init__(self, precision: str | int = "auto", q_batch: int = 0, kv_splits: int = 0, merge: str = "nccl2",
                  num_local: int = 1, first_device: int = 0, world_size: int = 0, rank_base: int = 0,
-                 nccl_id: bytes | None = None):
+                 nccl_id: bytes | None = None, distribution: str = "kv"):
         L = lib()
         cfg = Config()
         L.sdpa_config_init(ctypes.byref(cfg))
@@ -222,6 +225,7 @@ class Context:
         cfg.merge = _MERGE[merge]
         cfg.num_local, cfg.first_device = int(num_local), int(first_device)
         cfg.world_size, cfg.rank_base = int(world_size), int(rank_base)
+        cfg.distribution = _DIST[distribution]
         self.num_local = int(num_local)
         self.world_size = int(world_size) if world_size else int(num_local)
         self.rank_base = int(rank_base)

@@ -30,6 +30,8 @@ def test_config_struct_layout(sdpa):
     cfg = sdpa.Config()
     sdpa.lib().sdpa_config_init(ctypes.byref(cfg))
     assert cfg.precision == sdpa.PREC_AUTO and cfg.num_local == 1 and cfg.merge == sdpa.MERGE_NCCL2
+    assert cfg.distribution == sdpa.DIST_KV                       # the reference's K/V sharding is the default
+    assert sdpa.Config.distribution.offset == 8 * 4               # right behind rank_base; the struct size did not move
 
 
 def test_owner_map_matches_reference_formula(sdpa, oracle):

@@ -33,6 +33,23 @@ def test_single_process_two_gpus(sdpa, oracle, merge, prec, m, n, d, atol):
     assert oracle.verify_rule(got, ref)
 
 
+@pytest.mark.parametrize("prec,atol", [("f32", 1e-5), ("bf16", 1e-2)])
+def test_single_process_q_sharded_distribution(sdpa, oracle, prec, atol):
+    """SDPA_DIST_Q: K/V replicated, Q rows sharded over the GPUs, no exchange (small-n policy, mpi.c:213-231);
+    DIST_AUTO picks it below the reference's 64 MiB threshold and keeps K/V sharding above it."""
+    _need_gpus(sdpa, 2)
+    Q, K, V = oracle.make_inputs(1301, 777, 128, 128, seed=41)      # ragged on both sides, several 512-row batches
+    ref = oracle.attention_f64(Q, K, V)
+    for dist in ("q", "auto"):
+        with sdpa.Context(precision=prec, num_local=2, q_batch=512, distribution=dist) as ctx:
+            ctx.load_kv_host_full(K, V)
+            for _ in range(2):
+                got = ctx.attention_host(Q)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=atol)
+            assert ctx.last_timings()["fused_launches"] == 4     # 651 rows on GPU 0 and 650 on GPU 1: two 512-row batches each
+            np.testing.assert_allclose(ctx.attention_host(Q[:1]), ref[:1], rtol=0, atol=atol)   # fewer rows than GPUs
+
+
 def test_single_process_empty_shard(sdpa, oracle):
     _need_gpus(sdpa, 2)
     Q, K, V = oracle.make_inputs(50, 1, 32, 32, seed=5)   # n=1 < 2 shards: GPU 1 owns nothing (lmax=-inf, mpi.c:172)
