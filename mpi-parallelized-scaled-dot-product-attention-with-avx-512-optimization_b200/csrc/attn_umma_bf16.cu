@@ -1,7 +1,7 @@
 // attn_umma_bf16.cu -- fused QK^T -> online softmax -> .V on the 5th-generation tensor cores
 // (tcgen05.mma, accumulators in TMEM, operands staged by TMA), bf16 operands / fp32 accumulate.
 //
-// Three kernel generations live here behind one launcher (launch_attn_umma); all produce the same
+// Four kernel generations live here behind one launcher (launch_attn_umma); all produce the same
 // partial softmax state and pass the same parity tests:
 //   attn_umma_kernel_v7  DEFAULT.  Cluster of two CTAs forming one M=256 tcgen05.mma.cta_group::2 (each CTA keeps
 //                        half of every K/V tile), S and P double-buffered in TMEM (no MMA waits for the softmax of
@@ -10,6 +10,9 @@
 //                        the overflow-guard fallback of every generation.  Described right below.
 //   attn_umma_kernel_v6  (SDPA_UMMA_V6=1) v7's pipeline without the 2-CTA MMA (K/V multicast instead); kept as the
 //                        measured stepping stone (profiles/README.md).
+//   attn_umma_kernel_v8  (SDPA_UMMA_V8=1, EXPERIMENTAL, single GPU) v7 made persistent: one cluster per SM pair walks a
+//                        contiguous range of (row block, key tile) units; written after the round's GPU budget was
+//                        spent -- its barrier protocol is checked by tools/v8_protocol_sim.py, not yet by hardware.
 //
 // The B200 counterpart of online_softmax_attention (attention-mpi.c:168-189): where the
 // reference does one AVX-512 dot (dot_avx512, :103-121) and one axpy (axpy_avx512, :123-140)
@@ -352,6 +355,7 @@ struct KernelParams {
     long long* trace;    // TRACE build only: clock64 stamps of CTA (0,0), [role][iteration][event]
     unsigned int* guard; // fast mode writes `epoch` here when an exponent would overflow; the safe kernel runs iff *guard == epoch
     unsigned int epoch;
+    WorkMap wm;          // v8 only: the persistent kernel's work decomposition
 };
 
 constexpr int TRACE_ITERS = 24, TRACE_EVENTS = 8, TRACE_ROLES = 6;
@@ -1601,6 +1605,415 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
     }
 }
 
+// =====================================================================================
+// v8 (SDPA_UMMA_V8=1, EXPERIMENTAL: written after the round's GPU budget was spent, not yet run on hardware).
+// v7's pipeline made PERSISTENT: one cluster per SM pair walks a contiguous range of the linear work space
+// (row block of 256 rows, key tile) -- "stream-K" over the key axis.  With 74 clusters every cluster gets
+// RB*T/74 key tiles (+-1): no wave quantisation (v7 on c3: 288 equal units on 74 slots = 97.3 %), the prologue
+// (barrier init, TMEM alloc, cluster sync, first loads) runs once per SM instead of once per 57-tile unit, and a
+// row block is cut into ~T*74/(RB*T) + 1 pieces instead of 9 splits, so the split merge reads a third of the partials.
+// A cluster's range crosses row-block boundaries: it is processed as SEGMENTS (row block, first tile, tile count).
+// What v7 keeps per launch is carried across segments here:
+//   * K/V rings and the S/P double buffers run on ONE tile counter g over all segments of the cluster, so the
+//     S MMAs of the next segment's first tiles are issued while the current segment drains (no pipeline refill);
+//   * Q has two shared-memory slots (segment parity); q_free (a commit behind the segment's last S MMA) lets the
+//     producer overwrite a slot two segments later;
+//   * the single O accumulator is handed back by o_free: every softmax warp of both CTAs arrives after it has read
+//     its share of O in the segment's epilogue; the first PV of the next segment waits for it;
+//   * the softmax reference is per segment: the group owning the segment's first tile (g & 1) fixes and publishes it.
+// The partial state of segment (rb, piece) goes to partial slot `piece` = cluster - first cluster touching rb; the
+// merge reads pieces(rb) states per row (merge_pieces_kernel), or all max_pieces after the SAFE twin ran.
+// =====================================================================================
+struct __align__(1024) SharedV8 {
+    uint8_t q[2][TILE_BYTES];
+    uint8_t k[V7_KSTAGES][HALF_TILE_BYTES];
+    uint8_t v[V7_VSTAGES][HALF_TILE_BYTES];
+    uint64_t q_full[2], q_free[2];
+    uint64_t k_full[V7_KSTAGES], k_empty[V7_KSTAGES];
+    uint64_t v_full[V7_VSTAGES], v_empty[V7_VSTAGES];
+    uint64_t s_full[2], p_ready[2], s_free[2], pv_done[2], o_done, o_free;
+    uint32_t tmem_base;
+    float xchg[2][4][TILE];   // [first-tile max | final sum][group*2 + part][row]
+    float mref[TILE];
+};
+
+// Walks the segments of the unit range [begin, end) of one cluster.
+struct SegCursor {
+    int u, uend, T;
+    int seg, rb, t0, nt;
+    __device__ __forceinline__ void init(int begin, int end, int tiles_per_row_block)
+    {
+        u = begin;
+        uend = end;
+        T = tiles_per_row_block;
+        seg = -1;
+        nt = 0;
+        rb = t0 = 0;
+    }
+    __device__ __forceinline__ bool next()
+    {
+        u += nt;
+        if (u >= uend) {
+            nt = 0;
+            return false;
+        }
+        rb = u / T;
+        t0 = u - rb * T;
+        nt = min(T - t0, uend - u);
+        ++seg;
+        return true;
+    }
+};
+
+template <int POLY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
+attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
+{
+    constexpr int NPARTS = 2, GROUPS = 2;
+    extern __shared__ uint8_t smem_raw[];
+    SharedV8& sm = *reinterpret_cast<SharedV8*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int cluster = blockIdx.x >> 1;
+    const uint32_t rank = cluster_cta_rank();      // 0 = leader (issues the MMAs); rank r keeps keys [64r,64r+64) of K and columns [64r,64r+64) of V
+    const bool leader = rank == 0;
+    const WorkMap wm = prm.wm;
+    const int T = wm.T;
+    const int unit_begin = (int)wm_begin(wm, cluster), unit_end = (int)wm_begin(wm, cluster + 1);
+    const int total_tiles = unit_end - unit_begin;   // identical in both CTAs of the cluster
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_khalf);
+        prefetch_tensormap(&map_q);
+        prefetch_tensormap(&map_k);
+        prefetch_tensormap(&map_v);
+        mbar_init(&sm.o_done, 1);
+        mbar_init(&sm.o_free, 2 * 4 * NPARTS * GROUPS);   // leader's copy: every softmax warp of BOTH CTAs has read its share of O
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.q_full[i], 2);       // leader's copy: one arrival per CTA's producer + all bytes
+            mbar_init(&sm.q_free[i], 1);       // both CTAs: the commit behind the last S MMA that read the slot
+            mbar_init(&sm.s_full[i], 1);
+            mbar_init(&sm.p_ready[i], 2 * 4 * NPARTS);
+            mbar_init(&sm.s_free[i], 2 * 4 * NPARTS);
+            mbar_init(&sm.pv_done[i], 1);
+        }
+        for (int i = 0; i < V7_KSTAGES; ++i) {
+            mbar_init(&sm.k_full[i], 2);
+            mbar_init(&sm.k_empty[i], 1);
+        }
+        for (int i = 0; i < V7_VSTAGES; ++i) {
+            mbar_init(&sm.v_full[i], 2);
+            mbar_init(&sm.v_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_2cta(&sm.tmem_base, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tcgen05_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (total_tiles > 0) {
+            if (warp == 0) {
+                // ================================ TMA producer ================================
+                SegCursor cur;
+                cur.init(unit_begin, unit_end, T);
+                int g = 0;
+                while (cur.next()) {
+                    const int qs = cur.seg & 1;
+                    if (cur.seg >= 2) mbar_wait(&sm.q_free[qs], (uint32_t)((cur.seg >> 1) - 1) & 1u, 120 + qs);
+                    if (elect_one_sync()) {
+                        const int qrow = (2 * cur.rb + (int)rank) * TILE;
+                        if (leader) mbar_arrive_expect_tx(&sm.q_full[qs], 2 * TILE_BYTES);
+                        else mbar_arrive_cluster(map_to_cta(&sm.q_full[qs], 0));
+                        tma_load_2d_2sm(sm.q[qs], &map_q, &sm.q_full[qs], 0, qrow);
+                        tma_load_2d_2sm(sm.q[qs] + HALF_BYTES, &map_q, &sm.q_full[qs], 64, qrow);
+                    }
+                    __syncwarp();
+                    for (int j = 0; j < cur.nt; ++j, ++g) {
+                        const int ks = g % V7_KSTAGES, vs = g % V7_VSTAGES;
+                        const uint32_t kph = (uint32_t)(g / V7_KSTAGES) & 1u, vph = (uint32_t)(g / V7_VSTAGES) & 1u;
+                        const int key0 = (cur.t0 + j) * TILE;
+                        mbar_wait(&sm.k_empty[ks], kph ^ 1u, 100 + ks);
+                        if (elect_one_sync()) {
+                            if (leader) mbar_arrive_expect_tx(&sm.k_full[ks], TILE_BYTES);
+                            else mbar_arrive_cluster(map_to_cta(&sm.k_full[ks], 0));
+                            tma_load_2d_2sm(sm.k[ks], &map_khalf, &sm.k_full[ks], 0, key0 + 64 * (int)rank);
+                            tma_load_2d_2sm(sm.k[ks] + HALF_TILE_BYTES / 2, &map_khalf, &sm.k_full[ks], 64, key0 + 64 * (int)rank);
+                        }
+                        mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
+                        if (elect_one_sync()) {
+                            if (leader) mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
+                            else mbar_arrive_cluster(map_to_cta(&sm.v_full[vs], 0));
+                            tma_load_2d_2sm(sm.v[vs], &map_v, &sm.v_full[vs], 64 * (int)rank, key0);
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else if (warp == 1) {
+                // ================================ MMA issuer (leader CTA only) ==================
+                if (leader) {
+                constexpr uint32_t idesc_qk = make_idesc(2 * TILE, TILE, 0);
+                constexpr uint32_t idesc_pv = make_idesc(2 * TILE, HEAD, 1);
+                const uint64_t dq[2] = {desc_kmajor(smem_u32(sm.q[0]), 0), desc_kmajor(smem_u32(sm.q[1]), 0)};
+                uint64_t dkk[V7_KSTAGES], dvv[V7_VSTAGES];
+#pragma unroll
+                for (int i = 0; i < V7_KSTAGES; ++i) dkk[i] = make_desc(smem_u32(sm.k[i]), 16u, 1024u);
+#pragma unroll
+                for (int i = 0; i < V7_VSTAGES; ++i) dvv[i] = make_desc(smem_u32(sm.v[i]), HALF_TILE_BYTES, 1024u);
+                const uint16_t both = 0x3;
+
+                SegCursor cs, cp;   // the S stream runs two tiles ahead of the PV stream, possibly in the next segment
+                cs.init(unit_begin, unit_end, T);
+                cp.init(unit_begin, unit_end, T);
+                cs.next();
+                cp.next();
+                int js = 0, jp = 0;
+
+                auto issue_s = [&](int g) {
+                    const int sb = g & 1, ks = g % V7_KSTAGES, qs = cs.seg & 1;
+                    if (js == 0) mbar_wait(&sm.q_full[qs], (uint32_t)(cs.seg >> 1) & 1u, 201 + qs);
+                    mbar_wait(&sm.k_full[ks], (uint32_t)(g / V7_KSTAGES) & 1u, 204 + ks);
+                    tcgen05_fence_after();
+                    const bool last_of_segment = (js == cs.nt - 1);
+                    if (elect_one_sync()) {
+                        const uint64_t a0 = dq[qs], b0 = dkk[ks];
+                        const uint32_t d = tmem + V6_S + 128u * sb;
+#pragma unroll
+                        for (int kk = 0; kk < HEAD / 16; ++kk) {
+                            const uint64_t offa = (uint64_t)(((kk >> 2) * HALF_BYTES + (kk & 3) * 32u) >> 4);
+                            const uint64_t offb = (uint64_t)(((kk >> 2) * (HALF_TILE_BYTES / 2) + (kk & 3) * 32u) >> 4);
+                            umma_ss_2cta(d, a0 + offa, b0 + offb, idesc_qk, kk > 0 ? 1u : 0u);
+                        }
+                        umma_commit_2cta(&sm.s_full[sb], both);
+                        umma_commit_2cta(&sm.k_empty[ks], both);
+                        if (last_of_segment) umma_commit_2cta(&sm.q_free[qs], both);   // no later MMA reads this Q slot
+                    }
+                    __syncwarp();
+                    if (++js == cs.nt) {
+                        cs.next();
+                        js = 0;
+                    }
+                };
+                auto issue_pv = [&](int g) {
+                    const int pb = g & 1, vs = g % V7_VSTAGES;
+                    const bool first = (jp == 0), last = (jp == cp.nt - 1);
+                    // the accumulator still holds the previous segment until all of its epilogue reads are done
+                    if (first && cp.seg >= 1) mbar_wait(&sm.o_free, (uint32_t)(cp.seg - 1) & 1u, 220);
+                    mbar_wait(&sm.v_full[vs], (uint32_t)(g / V7_VSTAGES) & 1u, 210 + vs);
+                    mbar_wait(&sm.p_ready[pb], (uint32_t)(g >> 1) & 1u, 214 + pb);
+                    tcgen05_fence_after();
+                    if (elect_one_sync()) {
+                        const uint64_t b0 = dvv[vs];
+                        const uint32_t d = tmem + V6_O;
+                        const uint32_t a = tmem + V6_P + 64u * pb;
+#pragma unroll
+                        for (int kk = 0; kk < TILE / 16; ++kk)
+                            umma_ts_2cta(d, a + 8u * kk, b0 + (uint64_t)((kk * 2048u) >> 4), idesc_pv, (!first || kk > 0) ? 1u : 0u);
+                        umma_commit_2cta(&sm.pv_done[pb], both);
+                        umma_commit_2cta(&sm.v_empty[vs], both);
+                        if (last) umma_commit_2cta(&sm.o_done, both);
+                    }
+                    __syncwarp();
+                    if (++jp == cp.nt) {
+                        cp.next();
+                        jp = 0;
+                    }
+                };
+
+                issue_s(0);
+                if (total_tiles > 1) issue_s(1);
+                for (int g = 0; g < total_tiles; ++g) {
+                    if (g + 2 < total_tiles) {
+                        mbar_wait(&sm.s_free[g & 1], (uint32_t)(g >> 1) & 1u, 216 + (g & 1));
+                        issue_s(g + 2);
+                    }
+                    issue_pv(g);
+                }
+                }
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        constexpr int COLS = TILE / NPARTS;             // 64 keys (S columns) per thread
+        constexpr int OCOLS = HEAD / (NPARTS * GROUPS);  // 32 output columns per thread in the epilogue
+        const int sw = warp - 4;
+        const int group = sw / (4 * NPARTS);
+        const int half = (sw % (4 * NPARTS)) >> 2;
+        const int gp = group * NPARTS + half;
+        const int quad = warp & 3;
+        const int row_in_tile = quad * 32 + lane;
+        if (total_tiles > 0) {
+            const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+            const uint32_t o_addr = tmem + lane_base + V6_O + (uint32_t)OCOLS * gp;
+            const float scale = prm.scale_log2;
+            const uint64_t scale2 = pack_f32x2(scale, scale);
+            const int bar_id = 1 + quad;
+            const int bar_all = 5 + quad;
+            const uint32_t leader_pready[2] = {map_to_cta(&sm.p_ready[0], 0), map_to_cta(&sm.p_ready[1], 0)};
+            const uint32_t leader_sfree[2] = {map_to_cta(&sm.s_free[0], 0), map_to_cta(&sm.s_free[1], 0)};
+            const uint32_t leader_ofree = map_to_cta(&sm.o_free, 0);
+
+            float m_ref = -CUDART_INF_F;
+            float lsum = 0.f;
+
+            auto exp_chunk = [&](const uint32_t* sv, uint64_t neg_ref2, uint64_t& acc0, uint64_t& acc1, uint32_t* pr) {
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+                    const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
+                    float p0, p1;
+                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
+                    if (poly) {
+                        exp2_poly_x2(t2, p0, p1);
+                    } else {
+                        float t0, t1;
+                        unpack_f32x2(t2, t0, t1);
+                        p0 = fast_exp2(t0);
+                        p1 = fast_exp2(t1);
+                    }
+                    const uint64_t p2 = pack_f32x2(p0, p1);
+                    if (c & 4) acc1 = add_f32x2(acc1, p2);
+                    else acc0 = add_f32x2(acc0, p2);
+                    pr[c / 2] = pack_bf16x2(p0, p1);
+                }
+            };
+
+            // g: tile counter of the cluster (buffers and barrier phases), key_tile: index of the tile in the shard
+            auto tile_step = [&](int g, int key_tile, auto masked_tag, auto first_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
+                constexpr bool FIRST = decltype(first_tag)::value;
+                const int sb = g & 1;
+                const uint32_t s_addr = tmem + lane_base + V6_S + 128u * sb + (uint32_t)COLS * half;
+                const uint32_t p_addr = tmem + lane_base + V6_P + 64u * sb + (uint32_t)(COLS / 2) * half;
+                mbar_wait(&sm.s_full[sb], (uint32_t)(g >> 1) & 1u, 300 + sb);
+                tcgen05_fence_after();
+
+                uint32_t sr[COLS];
+                SDPA_TMEM_LD32(s_addr, sr);
+                SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
+                tmem_wait_ld();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_sfree[sb]);
+                if constexpr (MASKED) {
+                    const int keys_left = prm.n - key_tile * TILE - COLS * half;
+#pragma unroll
+                    for (int c = 0; c < COLS; ++c)
+                        if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
+                }
+                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+#pragma unroll
+                for (int c = 0; c < COLS; c += 8) {
+                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1])));
+                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
+                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
+                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
+                }
+                const float my_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                if constexpr (FIRST) {
+                    // the reference of the segment: its first tile's row max, agreed by the two halves, published to the other group
+                    sm.xchg[0][half][row_in_tile] = my_max;
+                    named_barrier_sync(bar_id, 32 * NPARTS);
+                    m_ref = fmaxf(sm.xchg[0][0][row_in_tile], sm.xchg[0][1][row_in_tile]);
+                    if (half == 0) sm.mref[row_in_tile] = m_ref;
+                    named_barrier_sync(bar_all, 32 * NPARTS * GROUPS);
+                }
+                const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
+                uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+                uint32_t pr[COLS / 2];
+#pragma unroll
+                for (int ch = 0; ch < COLS / 16; ++ch) exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr + 8 * ch);
+                if (g >= 2) mbar_wait(&sm.pv_done[sb], (uint32_t)((g >> 1) - 1) & 1u, 310 + sb);
+                tcgen05_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < COLS / 16; ++ch) SDPA_TMEM_ST8(p_addr + 8 * ch, (pr + 8 * ch));
+                float a0, a1, a2, a3;
+                unpack_f32x2(acc0, a0, a1);
+                unpack_f32x2(acc1, a2, a3);
+                lsum += (a0 + a1) + (a2 + a3);
+                if constexpr (!FIRST) {
+                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
+                        if (lane == 0) atomicExch(prm.guard, prm.epoch);
+                    }
+                }
+                tmem_wait_st();
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_pready[sb]);
+            };
+
+            SegCursor cur;
+            cur.init(unit_begin, unit_end, T);
+            int g0 = 0;   // tile counter at the start of the segment
+            while (cur.next()) {
+                const bool ragged = (prm.n % TILE) != 0 && (cur.t0 + cur.nt) == T;   // the segment ends with the shard's partial tile
+                m_ref = -CUDART_INF_F;
+                lsum = 0.f;
+                int g;
+                if (group == (g0 & 1)) {   // this group owns the segment's first tile: it fixes the reference
+                    if (ragged && cur.nt == 1) tile_step(g0, cur.t0, std::true_type{}, std::true_type{});
+                    else tile_step(g0, cur.t0, std::false_type{}, std::true_type{});
+                    g = g0 + 2;
+                } else {
+                    named_barrier_sync(bar_all, 32 * NPARTS * GROUPS);
+                    m_ref = sm.mref[row_in_tile];
+                    g = g0 + 1;
+                }
+                for (; g < g0 + cur.nt; g += 2) {
+                    if (ragged && g == g0 + cur.nt - 1) tile_step(g, cur.t0 + (g - g0), std::true_type{}, std::false_type{});
+                    else tile_step(g, cur.t0 + (g - g0), std::false_type{}, std::false_type{});
+                }
+
+                // ---------------- epilogue of the segment ----------------
+                sm.xchg[1][gp][row_in_tile] = lsum;
+                named_barrier_sync(bar_all, 32 * NPARTS * GROUPS);
+                lsum = 0.f;
+#pragma unroll
+                for (int p = 0; p < NPARTS * GROUPS; ++p) lsum += sm.xchg[1][p][row_in_tile];
+                mbar_wait(&sm.o_done, (uint32_t)cur.seg & 1u, 320);
+                tcgen05_fence_after();
+                const int grow = (2 * cur.rb + (int)rank) * TILE + row_in_tile;
+                const int piece = cluster - wm_cluster_of(wm, (long long)cur.rb * T);
+                const bool valid = grow < prm.rows;
+                {
+                    uint32_t orr[32];
+                    SDPA_TMEM_LD32(o_addr, orr);
+                    tmem_wait_ld();
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(leader_ofree);   // my share of O is in registers: the accumulator may be reused
+                    if (valid) {
+                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)piece * prm.rows_capacity + grow) * HEAD + OCOLS * gp);
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            dst[c / 4] = make_float4(__uint_as_float(orr[c]), __uint_as_float(orr[c + 1]),
+                                                     __uint_as_float(orr[c + 2]), __uint_as_float(orr[c + 3]));
+                    }
+                }
+                if (valid && gp == 0) {
+                    prm.part_tmax[(size_t)piece * prm.rows_capacity + grow] = m_ref * scale;
+                    prm.part_lsum[(size_t)piece * prm.rows_capacity + grow] = lsum;
+                }
+                g0 += cur.nt;
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        tmem_dealloc_2cta(tmem, 512);
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1655,6 +2068,11 @@ struct UmmaPlan {
     bool attr_set[64] = {};
     unsigned int* guard = nullptr;   // device word for the overflow guard (on the plan's device)
     unsigned int epoch = 0;
+    bool allow_v8 = false;           // set per call by the engine: the caller merges with launch_merge_pieces
+    bool last_v8 = false;            // the last launch used the persistent kernel; last_wm / last_pieces describe its partials
+    WorkMap last_wm{0, 0, 0};
+    int last_pieces = 0;
+    bool attr8_set[64] = {};
 };
 
 sdpa_status umma_plan_create(UmmaPlan** plan)
@@ -1702,12 +2120,59 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
 }
 
 // Kernel generation: v6 (cluster of two 128-row CTAs, chain-free pipeline) unless SDPA_UMMA_V6=0 asks for v5.
+static bool trace_env_set()
+{
+    const char* t = getenv("SDPA_UMMA_TRACE");
+    return t && *t;
+}
+
 static bool use_v6()
 {
     const char* e7 = getenv("SDPA_UMMA_V7");
     const char* e = getenv("SDPA_UMMA_V6");
     if (e7 ? (*e7 == '1') : (e == nullptr)) return true;   // v7 (default) shares v6's grid shape (128-row CTAs in clusters of two)
     return e ? (*e != '0') : kDefaultV6;
+}
+
+// Persistent kernel (EXPERIMENTAL, SDPA_UMMA_V8=1): its work map for (rows, n) on sm_count SMs, or false when the shape
+// does not suit it (too little work per cluster, or more pieces per row block than the merge takes).
+static bool v8_work_map(int rows, int n, int sm_count, WorkMap* wm, int* max_pieces)
+{
+    const char* e = getenv("SDPA_UMMA_V8");
+    if (!(e && *e == '1') || rows <= 0 || n <= 0) return false;
+    WorkMap w;
+    w.T = ceil_div(n, TILE);
+    w.RB = ceil_div(rows, 2 * TILE);
+    w.C = std::max(1, sm_count / 2);
+    if (wm_total(w) < 4LL * w.C || wm_total(w) > 0x3fffffffLL) return false;
+    int mp = 0;
+    for (int rb = 0; rb < w.RB; ++rb) mp = std::max(mp, wm_pieces(w, rb));
+    if (mp < 1 || mp > 64) return false;
+    *wm = w;
+    *max_pieces = mp;
+    return true;
+}
+
+int attn_umma_v8_pieces(int rows, int n, int sm_count)
+{
+    WorkMap w;
+    int mp = 0;
+    return v8_work_map(rows, n, sm_count, &w, &mp) ? mp : 0;
+}
+
+void umma_plan_allow_v8(UmmaPlan* plan, bool allow)
+{
+    if (plan) plan->allow_v8 = allow;
+}
+
+bool umma_plan_last_v8(const UmmaPlan* plan, WorkMap* wm, int* max_pieces, const unsigned int** guard, unsigned int* epoch)
+{
+    if (!plan || !plan->last_v8) return false;
+    *wm = plan->last_wm;
+    *max_pieces = plan->last_pieces;
+    *guard = plan->guard;
+    *epoch = plan->epoch;
+    return true;
 }
 
 int attn_umma_pick_splits(int rows, int n, int sm_count)
@@ -1739,7 +2204,6 @@ int attn_umma_pick_splits(int rows, int n, int sm_count)
 sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part, double* out64,
                              int sm_count, cudaStream_t stream)
 {
-    (void)sm_count;
     if (!plan || !plan->kv_bound || q_slot < 0 || q_slot > 1 || !plan->q_bound[q_slot]) {
         set_error("launch_attn_umma: plan is not bound");
         return SDPA_ERR_INVALID;
@@ -1818,6 +2282,13 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     const bool parts4 = env_parts ? (atoi(env_parts) == 4) : (kDefaultParts == 4);
     dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v6: 128 rows per CTA, clusters of two along x
     const size_t smem6 = sizeof(SharedV6) + 1024;
+    // persistent kernel: only when the engine announced that it merges by pieces, no direct fp64 output, and the caller's
+    // split count is the map's piece count (the SAFE twin behind it then fills every partial slot the merge may read)
+    WorkMap wm8{0, 0, 0};
+    int pieces8 = 0;
+    const bool use_v8 = plan->allow_v8 && out64 == nullptr && !force_safe && !(trace_env_set()) &&
+                        v8_work_map(rows, plan->n, sm_count, &wm8, &pieces8) && pieces8 == splits;
+    plan->last_v8 = false;
     const char* trace_path = getenv("SDPA_UMMA_TRACE");   // developer aid: dump a clock64 timeline of CTA (0,0)
     if (trace_path && *trace_path) {
         const size_t count = (size_t)TRACE_ROLES * TRACE_ITERS * TRACE_EVENTS;
@@ -1848,6 +2319,22 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     } else if (force_safe) {
         SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
         prm.epoch = 0xffffffffu;
+    } else if (use_v8) {
+        const int dev8 = dev;
+        const size_t smem8 = sizeof(SharedV8) + 1024;
+        if (dev8 < 64 && !plan->attr8_set[dev8]) {
+            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            plan->attr8_set[dev8] = true;
+        }
+        prm.wm = wm8;
+        const dim3 grid8(2 * wm8.C, 1);
+        if (poly == 4) attn_umma_kernel_v8<4><<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else attn_umma_kernel_v8<0><<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        count_launch();
+        plan->last_v8 = true;
+        plan->last_wm = wm8;
+        plan->last_pieces = pieces8;
     } else if (v7) {
 #define SDPA_LAUNCH_V7(P, G) attn_umma_kernel_v7<false, P, 2, G><<<grid6, 128 + 256 * G, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
         if (!groups2) SDPA_LAUNCH_V7(4, 1);

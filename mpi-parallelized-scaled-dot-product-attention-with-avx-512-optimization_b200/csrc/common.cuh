@@ -84,6 +84,11 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
                              double* out64, int sm_count, cudaStream_t stream);
 bool attn_umma_supported(int dk, int dv);
 int attn_umma_pick_splits(int rows, int n, int sm_count);
+// Persistent fused kernel (EXPERIMENTAL, SDPA_UMMA_V8=1): partial slots per row block for (rows, n), 0 = not applicable.
+struct WorkMap;
+int attn_umma_v8_pieces(int rows, int n, int sm_count);
+void umma_plan_allow_v8(UmmaPlan* plan, bool allow);   // the caller will merge with launch_merge_pieces
+bool umma_plan_last_v8(const UmmaPlan* plan, WorkMap* wm, int* max_pieces, const unsigned int** guard, unsigned int* epoch);
 
 // Merge of partial states (the arithmetic of mpi.c:340-362 in the log2 domain).
 //   mode FINAL   : out64[row][d] = sum_s o_s w_s / sum_s lsum_s w_s     (gsum==0 -> 0)
@@ -119,6 +124,9 @@ struct PeerSync {
 sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
                                       const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
                                       const PeerSync& sync, cudaStream_t stream);
+// Split merge behind the persistent fused kernel: per row, wm_pieces(row block) states (all max_pieces if *guard == epoch).
+sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64,
+                                const unsigned int* guard, unsigned int epoch, cudaStream_t stream);
 // Sliced merge, source side: merge the split states of `rows` rows and write each row's state into the inbox segment of
 // the rank owning its slice (slice r = rows/world + (r < rows%world) consecutive rows), then raise flag[r] = epoch at every rank.
 struct RouteTargets {
@@ -135,6 +143,27 @@ sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const Ro
 // to dst, then raise sync.consumed.
 sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, int dv, const PeerSync& sync, int ranks,
                                   cudaStream_t stream);
+
+// Work decomposition of the persistent fused kernel (attn_umma_kernel_v8): the linear space (row block of 256 rows, key
+// tile) has W = RB*T units; cluster c of C owns units [c*W/C, (c+1)*W/C).  A row block is therefore cut into
+// wm_pieces(rb) consecutive pieces, piece p computed by cluster wm_cluster_of(rb*T) + p and stored in partial slot p.
+struct WorkMap {
+    int T;    // key tiles per row block
+    int C;    // clusters (CTA pairs) in the grid
+    int RB;   // row blocks of 256 rows
+};
+__host__ __device__ inline long long wm_total(const WorkMap& w) { return (long long)w.RB * w.T; }
+__host__ __device__ inline long long wm_begin(const WorkMap& w, int c) { return (long long)c * wm_total(w) / w.C; }
+// the cluster whose range contains `unit`: the largest c with floor(c*W/C) <= unit
+__host__ __device__ inline int wm_cluster_of(const WorkMap& w, long long unit)
+{
+    const long long W = wm_total(w);
+    return (int)(((unit + 1) * w.C + W - 1) / W) - 1;
+}
+__host__ __device__ inline int wm_pieces(const WorkMap& w, int rb)
+{
+    return wm_cluster_of(w, (long long)(rb + 1) * w.T - 1) - wm_cluster_of(w, (long long)rb * w.T) + 1;
+}
 
 // host_staging.cu: host -> device copies that run at the pinned rate for pageable sources too (pinned ring + copy threads)
 bool host_ptr_is_pageable(const void* p);

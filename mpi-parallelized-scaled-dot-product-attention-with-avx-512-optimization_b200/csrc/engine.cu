@@ -697,6 +697,19 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                              : attn_f32_pick_splits(B, nmax, ctx->shards[0].sm_count);
     }
     splits = std::max(1, std::min(splits, 64));
+    // EXPERIMENTAL (SDPA_UMMA_V8=1, single GPU): the persistent fused kernel cuts every row block into pieces; its piece
+    // count replaces the split count and the merge reads pieces per row block (launch_merge_pieces).
+    bool by_pieces = false;
+    if (world == 1 && ctx->prec == SDPA_PREC_BF16 && ctx->cfg.kv_splits <= 0 && num_iter == 1) {
+        const int pieces = attn_umma_v8_pieces(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
+        if (pieces > 1) {
+            splits = pieces;
+            by_pieces = true;
+        }
+    }
+    if (ctx->prec == SDPA_PREC_BF16)
+        for (Shard& s : ctx->shards)
+            if (s.plan) umma_plan_allow_v8(s.plan, by_pieces);
 
     // which side streams this call touches (the others are neither forked nor joined: every stream operation
     // between two kernels costs front-end time on the GPU)
@@ -788,7 +801,14 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
 
             if (!(single && splits == 1)) {
                 SDPA_TRY(time_begin(s, 2, s.s_compute));
-                if (single) {
+                WorkMap wm;
+                int max_pieces = 0;
+                const unsigned int* guard = nullptr;
+                unsigned int guard_epoch = 0;
+                if (single && by_pieces && umma_plan_last_v8(s.plan, &wm, &max_pieces, &guard, &guard_epoch)) {
+                    SDPA_TRY(launch_merge_pieces(part, wm, max_pieces, bs, dv, final_dst, guard, guard_epoch, s.s_compute));
+                    ctx->last_kernel = "bf16_umma_v8";
+                } else if (single) {
                     SDPA_TRY(launch_merge_splits(part, bs, dv, final_dst, nullptr, nullptr, nullptr, false, s.s_compute));
                 } else {
                     if (use_ipc) {

@@ -257,6 +257,19 @@ merge_route_kernel(StatePtrs st, int count, int rows, int dv, RouteArgs rt, bool
     }
 }
 
+// Split merge behind the persistent fused kernel (attn_umma_kernel_v8): the number of partial states of a row is the
+// number of pieces its row block was cut into (wm_pieces), unless the overflow guard handed the launch to the SAFE
+// kernel, which fills all `max_pieces` slots with equal splits.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+merge_pieces_kernel(StatePtrs st, WorkMap wm, int max_pieces, int rows, int dv, double* __restrict__ out64, bool vec_ok,
+                    const unsigned int* __restrict__ guard, unsigned int epoch)
+{
+    const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int count = (*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256);
+    merge_one_row<true>(st, count, row, dv, out64 + (size_t)row * dv, nullptr, nullptr, nullptr, 1.f, vec_ok);
+}
+
 // Root GPU, sliced merge: wait until every rank has delivered its rows of the batch into the staging buffer,
 // move them to their destination (the caller's result array or the D2H buffer) and release the slot.
 __global__ void __launch_bounds__(256)
@@ -370,6 +383,29 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
     merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
                                                                          nullptr, 1.f, vec_ok, sa);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64,
+                                const unsigned int* guard, unsigned int epoch, cudaStream_t stream)
+{
+    if (rows <= 0) return SDPA_OK;
+    if (max_pieces < 1 || max_pieces > 64 || max_pieces > part.splits || !out64 || !guard) {
+        set_error("merge_pieces: bad arguments (pieces=%d, partial slots=%d)", max_pieces, part.splits);
+        return SDPA_ERR_INVALID;
+    }
+    StatePtrs st;
+    bool vec_ok = al16(out64);
+    for (int s = 0; s < max_pieces; ++s) {
+        st.o[s] = part.o + (size_t)s * part.rows_capacity * dv;
+        st.tmax[s] = part.tmax + (size_t)s * part.rows_capacity;
+        st.lsum[s] = part.lsum + (size_t)s * part.rows_capacity;
+        vec_ok = vec_ok && al16(st.o[s]);
+    }
+    merge_pieces_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, vec_ok,
+                                                                                          guard, epoch);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

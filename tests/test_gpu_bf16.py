@@ -126,3 +126,30 @@ def test_bf16_kernel_variants(sdpa, oracle, monkeypatch, env):
     np.testing.assert_allclose(got, ref, rtol=0, atol=BF16_ATOL)
     Qb, Kb, Vb = (oracle.bf16_round(a).astype(np.float64) for a in (Q, K, V))
     np.testing.assert_allclose(got, oracle.attention_f64_numpy(Qb, Kb, Vb), rtol=0, atol=BF16_KERNEL_ATOL)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SDPA_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental kernel (written without GPU access): set SDPA_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("m,n,gain", [(512, 32768, 1.0), (700, 32768 + 77, 1.0), (8192, 16384, 1.0), (300, 40000, 3.0)])
+def test_bf16_persistent_kernel_v8(sdpa, oracle, monkeypatch, m, n, gain):
+    """attn_umma_kernel_v8 (SDPA_UMMA_V8=1): persistent clusters walking (row block, key tile) ranges, pieces instead of
+    splits, merge by pieces.  Shapes: a range crossing row blocks, ragged keys + a partial row block, many row blocks,
+    and scaled keys (the overflow guard may hand the launch to the SAFE twin, which fills every partial slot)."""
+    monkeypatch.setenv("SDPA_UMMA_V8", "1")
+    Q, K, V = oracle.make_inputs(m, n, 128, 128, seed=m + n)
+    K = K * gain
+    with sdpa.Context(precision="bf16") as ctx:
+        ctx.load_kv_host_full(K, V)
+        got = ctx.attention_host(Q)
+        assert ctx.last_kernel() == "bf16_umma_v8"
+        again = ctx.attention_host(Q)
+    assert np.array_equal(got, again)
+    Qb, Kb, Vb = (oracle.bf16_round(a).astype(np.float64) for a in (Q, K, V))
+    rows = slice(None) if m <= 1024 else np.random.default_rng(0).choice(m, 512, replace=False)
+    ref_b = oracle.attention_f64_numpy(Qb[rows], Kb, Vb)
+    np.testing.assert_allclose(got[rows], ref_b, rtol=0, atol=BF16_KERNEL_ATOL if gain == 1.0 else 2e-2)
+    monkeypatch.delenv("SDPA_UMMA_V8")
+    with sdpa.Context(precision="bf16") as ctx:   # the default kernel on the same data
+        ctx.load_kv_host_full(K, V)
+        base = ctx.attention_host(Q)
+    np.testing.assert_allclose(got, base, rtol=0, atol=2e-3 if gain == 1.0 else 2e-2)
