@@ -447,7 +447,7 @@ def run_ours(args) -> None:
     flops_per_launch = 2.0 * m * n_local * (DK + DV) * K / max(1.0, fused["launches"])
     avg_ms = fused["ms"] / max(1.0, fused["launches"])
     achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-    if kernel_name == "bf16_umma":
+    if kernel_name.startswith("bf16_umma"):
         peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
         bound_note = "tcgen05 bf16 dense; peak = cuBLAS bf16 burst"
     else:
@@ -470,7 +470,7 @@ def run_ours(args) -> None:
         line = {
             "metric": "attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if kernel_name == "bf16_umma" else "f32", "data": "synthetic N(0,1), seeded",
+            "dtype": "bf16" if kernel_name.startswith("bf16_umma") else "f32", "data": "synthetic N(0,1), seeded",
             "q_rows_per_s": m * K / (ms_dev * 1e-3),
             "config": {"workload": desc, "m": m, "n": n, "n_per_gpu": n_local, "dk": DK, "dv": DV,
                        "parallelism": f"kv-shard x{world} (owner_count/owner_disp), Q replicated",
