@@ -1131,9 +1131,11 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
         if (s.marks_used > 2048) SDPA_TRY(fold_timings(s));
         for (int w = 0; w < 4; ++w) s.tpair_last[w] = s.tpair[w].size();
         compute_stream_touched(s);
-        if (ctx->prec == SDPA_PREC_BF16)
+        if (ctx->prec == SDPA_PREC_BF16) {
+            umma_plan_allow_v8(s.plan, false);   // this path merges by splits
             for (int b = 0; b < 2; ++b)
                 SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk));
+        }
         SDPA_TRY(time_begin(s, 3, s.s_compute));
         cudaEvent_t begun = s.marks[s.tpair[3].back()];
         SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, begun, 0));
