@@ -34,11 +34,6 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 DK = DV = 128
-CONFIGS = {
-    # name: (m, keys per GPU, precision, description)
-    "c3": (8192, 65536, "bf16", "c3: m=8192 n=65536/GPU dk=dv=128 bf16->fp32 tensor-core path"),
-    "c2": (4096, 4096, "f32", "c2: m=4096 n=4096 dk=dv=128 fp32, no sharding"),
-}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -190,6 +185,73 @@ class ClockSampler:
                 "window": "timed region + ~1 s of the same steps (samples with power draw >= 300 W)"}
 
 
+# --------------------------------------------------------------------------- workloads (BASELINE.json configs)
+# c3 is the headline (weak scaling: 65536 keys per GPU, Q replicated, n = 65536*N; N=1 is exactly c3).  c2 / c4 / c5 are
+# run at their BASELINE shapes behind the headline when the GPU count matches (c2 at N=1, c4 at N=4, c5 at N=8) and are
+# reported under "configs".  c1 (serial fp64, m=n=512, d=64) is the CPU correctness reference: a parity-test case.
+CONFIGS = {
+    "c3": {"m": 8192, "n_per_gpu": 65536, "prec": "bf16", "tol": 1e-2, "gpus": None,
+           "desc": "c3: m=8192 n=65536/GPU dk=dv=128 bf16->fp32 tensor-core path"},
+    "c2": {"m": 4096, "n_total": 4096, "prec": "f32", "tol": 1e-5, "gpus": 1,
+           "desc": "c2: m=4096 n=4096 dk=dv=128 fp32, no sharding"},
+    "c4": {"m": 16384, "n_total": 262144, "prec": "bf16", "tol": 1e-2, "gpus": 4,
+           "desc": "c4: m=16384 n=262144 dk=dv=128, K/V sharded over 4 GPUs, Q ping-pong batches + exchange per batch"},
+    "c5": {"m": 32768, "n_total": 1048576, "prec": "bf16", "tol": 1e-2, "gpus": 8,
+           "desc": "c5: m=32768 n=1048576 dk=dv=128, K/V sharded over 8 GPUs, Q ping-pong batches + exchange per batch"},
+}
+EXTRAS_BY_GPUS = {1: ["c2"], 4: ["c4"], 8: ["c5"]}
+Q_SEED, SHARD_SEED0, PARITY_SEED, PARITY_ROWS = 1234, 1000, 777, 64
+
+
+def owner_count(n: int, size: int, rank: int) -> int:      # attention-mpi.c:19-22
+    return n // size + (1 if rank < n % size else 0)
+
+
+def config_shape(name: str, world: int, m_override: int = 0, n_per_gpu_override: int = 0):
+    """(m, [keys of every rank's shard]) of a configuration on `world` GPUs."""
+    c = CONFIGS[name]
+    m = m_override or c["m"]
+    if "n_per_gpu" in c or n_per_gpu_override:
+        per = n_per_gpu_override or c["n_per_gpu"]
+        return m, [per] * world
+    return m, [owner_count(c["n_total"], world, r) for r in range(world)]
+
+
+def make_q(m: int):
+    import torch
+    g = torch.Generator().manual_seed(Q_SEED)
+    return torch.randn(m, DK, dtype=torch.float64, generator=g)
+
+
+def make_shard(rank: int, rows: int):
+    """The K/V rows of shard `rank`: seeded by the shard index only, so rank 0 can regenerate every shard for the oracle check."""
+    import torch
+    g = torch.Generator().manual_seed(SHARD_SEED0 + rank)
+    K = torch.randn(rows, DK, dtype=torch.float64, generator=g)
+    V = torch.randn(rows, DV, dtype=torch.float64, generator=g)
+    return K, V
+
+
+def parity_rows(m: int):
+    import numpy as np
+    rng = np.random.default_rng(PARITY_SEED)
+    return np.sort(rng.choice(m, size=min(PARITY_ROWS, m), replace=False))
+
+
+def oracle_rows(m: int, shard_rows, rows):
+    """fp64 oracle (oracle.attention_f64_numpy = attention.c:20-75) of the selected Q rows against the FULL K/V,
+    every shard regenerated from its seed.  Checker only: runs outside every timed region, on rank 0."""
+    import numpy as np
+    from oracle import oracle
+    Q = make_q(m).numpy()[rows]
+    Ks, Vs = [], []
+    for r, cnt in enumerate(shard_rows):
+        K, V = make_shard(r, cnt)
+        Ks.append(K.numpy())
+        Vs.append(V.numpy())
+    return oracle.attention_f64_numpy(Q, np.concatenate(Ks), np.concatenate(Vs))
+
+
 # --------------------------------------------------------------------------- reference / CPU baseline
 def cpu_cores() -> int:
     try:
@@ -198,59 +260,84 @@ def cpu_cores() -> int:
         return os.cpu_count() or 1
 
 
-def physical_cores() -> int:
-    """Ranks for the reference's MPI path: physical cores (its authors ran 16 ranks on 36-core nodes)."""
+def physical_core_cpus():
+    """One logical CPU per physical core among the CPUs this process may run on (the reference's authors ran one MPI
+    rank per core, README.md:137-141); the shim pins rank r to the r-th entry so ranks never share or migrate."""
     try:
-        pairs = set()
-        phys = core = None
-        for line in Path("/proc/cpuinfo").read_text().splitlines():
-            if line.startswith("physical id"):
+        allowed = sorted(os.sched_getaffinity(0))
+    except Exception:
+        allowed = list(range(os.cpu_count() or 1))
+    try:
+        seen, cpus = set(), []
+        cpu = phys = core = None
+        for line in Path("/proc/cpuinfo").read_text().splitlines() + [""]:
+            if line.startswith("processor"):
+                cpu = int(line.split(":")[1])
+            elif line.startswith("physical id"):
                 phys = line.split(":")[1].strip()
             elif line.startswith("core id"):
                 core = line.split(":")[1].strip()
-                pairs.add((phys, core))
-        n = len(pairs)
-        return max(1, min(n if n else cpu_cores(), cpu_cores()))
+            elif not line.strip() and cpu is not None:
+                if cpu in allowed and (phys, core) not in seen:
+                    seen.add((phys, core))
+                    cpus.append(cpu)
+                cpu = phys = core = None
+        return cpus or allowed
     except Exception:
-        return cpu_cores()
+        return allowed
+
+
+def physical_cores() -> int:
+    return max(1, len(physical_core_cpus()))
+
+
+REF_ROWS = 2048      # Q rows of the CPU arm's sample: the SAME for every GPU count (the K/V side is always complete)
 
 
 class ReferenceSample:
-    """A bounded sample of the workload for the CPU arm: `rows` Q rows against the FULL K/V of the
-    configuration, written in the reference's file format with a correct answer block (its harness
-    prints the elapsed time only when its own verify() passes, attention-mpi.c:526-532)."""
+    """A bounded sample of the workload for the CPU arm: `rows` Q rows against the FULL K/V of the configuration,
+    written in the reference's file format with a correct answer block (its harness prints the elapsed time only when
+    its own verify() passes, attention-mpi.c:526-532).  A second, one-row file times what the reference spends before
+    its batch loop -- dims broadcast, root-side cvt_d2f of K and V, Bcast/Scatterv (attention-mpi.c:193-266) -- which is
+    inside its `Elapsed time` and does not shrink with the row sample."""
 
-    def __init__(self, n: int, target_pairs: float = 2.0 ** 27):
+    def __init__(self, n: int, rows: int = REF_ROWS):
         from oracle import oracle
         import numpy as np
         self.oracle = oracle
         self.n = n
-        self.rows = int(max(64, min(4096, target_pairs // max(1, n))))
+        self.rows = int(rows)
         Q, K, V = oracle.make_inputs(self.rows, n, DK, DV, seed=4242)
         ans = oracle.attention_f64_numpy(Q, K, V)
         base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
         self.dir = tempfile.mkdtemp(prefix="sdpa_ref_", dir=base)
         self.path = os.path.join(self.dir, "sample.bin")
         oracle.write_data_file(self.path, Q, K, V, ans)
+        self.path1 = os.path.join(self.dir, "one_row.bin")
+        oracle.write_data_file(self.path1, Q[:1], K, V, ans[:1])
         self.Q, self.K, self.V, self.ans = Q, K, V, ans
         self.np = np
+        self.cpus = physical_core_cpus()
 
     def close(self):
         shutil.rmtree(self.dir, ignore_errors=True)
 
     def kind_and_cores(self):
         if self.oracle.ref_available("mpi"):
-            return "reference", physical_cores()
+            return "reference", len(self.cpus)
         return "port", int(self.oracle.lib().oracle_num_threads())
+
+    def _run_file(self, path) -> float:
+        ok, us, out = self.oracle.run_reference(path, "mpi", ranks=len(self.cpus), timeout=1800, pin_cpus=self.cpus)
+        if not ok or us is None:
+            raise RuntimeError(f"reference binary did not verify: {out[-400:]}")
+        return us * 1e-6
 
     def run_once(self) -> float:
         """Seconds for one pass over the sample (the program's own Elapsed time for kind=reference)."""
-        kind, cores = self.kind_and_cores()
+        kind, _ = self.kind_and_cores()
         if kind == "reference":
-            ok, us, out = self.oracle.run_reference(self.path, "mpi", ranks=cores, timeout=1800)
-            if not ok or us is None:
-                raise RuntimeError(f"reference binary did not verify: {out[-400:]}")
-            return us * 1e-6
+            return self._run_file(self.path)
         t0 = time.perf_counter()
         got = self.oracle.sharded_attention_f32(self.Q, self.K, self.V, shards=1)
         dt = time.perf_counter() - t0
@@ -258,40 +345,61 @@ class ReferenceSample:
             raise RuntimeError("oracle port failed its own check")
         return dt
 
+    def distribution_seconds(self):
+        """The reference's K/V cast + distribution time (one-row run), or None for the port."""
+        kind, _ = self.kind_and_cores()
+        if kind != "reference":
+            return None
+        return min(self._run_file(self.path1) for _ in range(2))
+
     def describe(self):
-        return f"{self.rows} Q rows x full K/V (n={self.n}, dk=dv={DK}), program's own timer"
+        return (f"{self.rows} Q rows x full K/V (n={self.n}, dk=dv={DK}), program's own timer, "
+                f"one rank pinned per physical core")
 
 
 def tflops_from_rows_per_s(rows_per_s: float, n: int) -> float:
     return rows_per_s * 2.0 * n * (DK + DV) / 1e12
 
 
+def shared_config(name: str, world: int, m: int, n: int, n_local: int) -> dict:
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": CONFIGS[name]["desc"], "m": m, "n": n, "n_per_gpu": n_local, "dk": DK, "dv": DV,
+            "sharding": f"kv-rows/{world} (owner_count/owner_disp), Q replicated",
+            "l2": "inputs_larger_than_l2 (fp64 Q+K+V per GPU = %d MiB)" % ((n_local * (DK + DV) + m * DK) * 8 >> 20)}
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    m, n_per_gpu, prec, desc = CONFIGS[args.config]
-    n = n_per_gpu * args.gpus
-    sample = ReferenceSample(n)
+    m, shard_rows = config_shape(args.config, args.gpus, args.m, args.n_per_gpu)
+    n = sum(shard_rows)
+    sample = ReferenceSample(n, rows=min(REF_ROWS, m))
     try:
         kind, cores = sample.kind_and_cores()
         for _ in range(max(0, args.warmup)):
             sample.run_once()
         times = [sample.run_once() for _ in range(max(1, args.steps))]
+        dist_s = sample.distribution_seconds()
     finally:
         sample.close()
     total = sum(times)
     rows_per_s = sample.rows * len(times) / total
     value = tflops_from_rows_per_s(rows_per_s, n)
+    step_s = total / len(times)
+    cb = {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample.describe(),
+          "q_rows_per_s": rows_per_s, "rows": sample.rows, "seconds_per_pass": step_s,
+          "kv_cast_and_distribution_s": dist_s,
+          "batch_loop_s": (step_s - dist_s) if dist_s is not None else None,
+          "note": "value = sample rows / program's Elapsed time, which includes the root's K/V cast + distribution "
+                  "(attention-mpi.c:213-266); that part grows with n and does not shrink with the row sample"}
     line = {
         "impl": "reference", "metric": "attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * step_s, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,1), seeded",
         "q_rows_per_s": rows_per_s,
-        "config": {"workload": desc, "m": m, "n": n, "dk": DK, "dv": DV, "sharding": f"kv-rows/{args.gpus}",
-                   "note": "CPU arm runs a bounded Q-row sample against the full K/V; FLOP rate is size-independent"},
-        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample.describe(),
-                         "q_rows_per_s": rows_per_s},
+        "config": shared_config(args.config, args.gpus, m, n, shard_rows[0]),
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -299,8 +407,61 @@ def run_reference_arm(args) -> None:
 
 
 # --------------------------------------------------------------------------- our arm
+class Workload:
+    """One configuration resident on this rank: pinned host arrays, fp64 device arrays, the two step functions."""
+
+    def __init__(self, torch, ctx, name, rank, world, m, shard_rows):
+        self.torch, self.ctx, self.name, self.rank, self.world = torch, ctx, name, rank, world
+        self.m, self.shard_rows = m, shard_rows
+        self.n_local = shard_rows[rank]
+        self.n = sum(shard_rows)
+        self.Qh = make_q(m).pin_memory()
+        K, V = make_shard(rank, self.n_local)
+        self.Kh, self.Vh = K.pin_memory(), V.pin_memory()
+        self.Rh = torch.zeros(m, DV, dtype=torch.float64).pin_memory() if rank == 0 else None
+        self.Qd, self.Kd, self.Vd = self.Qh.cuda(), self.Kh.cuda(), self.Vh.cuda()
+        self.Rd = torch.zeros(m, DV, dtype=torch.float64, device="cuda") if rank == 0 else None
+        self._kd, self._vd, self._qd = [self.Kd.data_ptr()], [self.Vd.data_ptr()], [self.Qd.data_ptr()]
+        self._rd = self.Rd.data_ptr() if self.Rd is not None else None
+        self.flops_step = 2.0 * m * self.n * (DK + DV)
+
+    def step_device(self):
+        # queued pass (sdpa_enqueue_device_full): K steps run back to back in stream order, one wait at the end
+        self.ctx.attention_device_full(self._kd, self._vd, [self.n_local], DK, DV, self._qd, self._rd, self.m, blocking=False)
+
+    def step_host(self):
+        self.ctx.load_kv_host_ptrs([self.Kh.data_ptr()], [self.Vh.data_ptr()], [self.n_local], DK, DV)
+        self.ctx.attention_host_ptr(self.Qh.data_ptr(), self.Rh.data_ptr() if self.Rh is not None else None, self.m)
+
+    def h2d_bytes(self):
+        return (self.n * (DK + DV) + self.world * self.m * DK) * 8     # every rank uploads its shard and the replicated Q
+
+    def d2h_bytes(self):
+        return self.m * DV * 8
+
+    def parity_check(self, tol):
+        """Rank 0: a seeded row subset of BOTH results (device-resident pass, host pass) against the fp64 oracle on the
+        full K/V (all shards regenerated).  The reference's own acceptance rule (0.02, attention-mpi.c:476) is checked too."""
+        import numpy as np
+        rows = parity_rows(self.m)
+        ref = oracle_rows(self.m, self.shard_rows, rows)
+        idx = self.torch.from_numpy(rows)
+        dev = self.Rd.cpu()[idx].numpy()
+        host = self.Rh[idx].numpy()
+        e_dev = float(np.abs(dev - ref).max()) if np.isfinite(dev).all() else float("inf")
+        e_host = float(np.abs(host - ref).max()) if np.isfinite(host).all() else float("inf")
+        err = max(e_dev, e_host)
+        return {"rows": int(len(rows)), "against": "oracle.attention_f64_numpy (attention.c:20-75) on the full K/V, all shards regenerated from their seeds",
+                "max_abs_err": err, "max_abs_err_device_path": e_dev, "max_abs_err_host_path": e_host, "tol": tol,
+                "reference_gate_0.02": bool(err <= 0.02), "ok": bool(err <= tol)}
+
+    def free(self):
+        for a in ("Qd", "Kd", "Vd", "Rd", "Qh", "Kh", "Vh", "Rh"):
+            setattr(self, a, None)
+        self.torch.cuda.empty_cache()
+
+
 def run_ours(args) -> None:
-    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -321,48 +482,18 @@ def run_ours(args) -> None:
     import sdpa_b200
     from sdpa_b200 import parallel
 
-    m, n_local, prec, desc = CONFIGS[args.config]
-    if args.m:
-        m = args.m
-    if args.n_per_gpu:
-        n_local = args.n_per_gpu
-    if args.precision:
-        prec = args.precision
-    n = n_local * world
-    flops_step = 2.0 * m * n * (DK + DV)
-
-    # ---- synthetic inputs: Q replicated (same seed), one K/V shard per rank -----------------
-    g = torch.Generator().manual_seed(1234)
-    Qh = torch.randn(m, DK, dtype=torch.float64, generator=g).pin_memory()
-    g = torch.Generator().manual_seed(1000 + rank)
-    Kh = torch.randn(n_local, DK, dtype=torch.float64, generator=g).pin_memory()
-    Vh = torch.randn(n_local, DV, dtype=torch.float64, generator=g).pin_memory()
-    Rh = torch.zeros(m, DV, dtype=torch.float64).pin_memory() if rank == 0 else None
-    Qd, Kd, Vd = Qh.cuda(), Kh.cuda(), Vh.cuda()
-    Rd = torch.zeros(m, DV, dtype=torch.float64, device="cuda") if rank == 0 else None
-
-    if world > 1:
-        ctx = parallel.bootstrap_context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, local_rank=local_rank,
-                                         merge=args.merge)
-    else:
-        ctx = sdpa_b200.Context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, first_device=local_rank)
-
-    kd, vd, qd, rd = [Kd.data_ptr()], [Vd.data_ptr()], [Qd.data_ptr()], (Rd.data_ptr() if Rd is not None else None)
-
-    def step_device():
-        # queued pass (sdpa_enqueue_device_full): K steps run back to back in stream order, one wait at the end
-        ctx.attention_device_full(kd, vd, [n_local], DK, DV, qd, rd, m, blocking=False)
-
-    def step_host():
-        ctx.load_kv_host_ptrs([Kh.data_ptr()], [Vh.data_ptr()], [n_local], DK, DV)
-        ctx.attention_host_ptr(Qh.data_ptr(), Rh.data_ptr() if Rh is not None else None, m)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, collect=None):
+    def make_ctx(prec):
+        if world > 1:
+            return parallel.bootstrap_context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits,
+                                              local_rank=local_rank, merge=args.merge)
+        return sdpa_b200.Context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, first_device=local_rank)
+
+    def timed(ctx, fn, steps, collect=None):
         barrier()
         if collect is not None:
             ctx.accumulated_timings(reset=True)   # stage events are queried once, after the loop
@@ -377,6 +508,60 @@ def run_ours(args) -> None:
             collect(ctx.accumulated_timings(reset=True))
         return parallel.max_over_ranks(e0.elapsed_time(e1))  # ms, max over ranks
 
+    def measure(name, W, K, sampler=None, m_override=0, n_per_gpu_override=0, prec_override=None):
+        """Warm-up, K timed device-resident steps, K timed host (e2e) steps, oracle parity check.  Collective over ranks."""
+        cfg = CONFIGS[name]
+        prec = prec_override or cfg["prec"]
+        m, shard_rows = config_shape(name, world, m_override, n_per_gpu_override)
+        ctx = make_ctx(prec)
+        wl = Workload(torch, ctx, name, rank, world, m, shard_rows)
+        for _ in range(W):
+            wl.step_device()
+        ctx.synchronize()
+        stage = {"ms": 0.0, "launches": 0.0, "cast_ms": 0.0, "merge_ms": 0.0, "total_ms": 0.0}
+
+        def collect(t):
+            stage["ms"] += t["fused_ms"]
+            stage["launches"] += t["fused_launches"]
+            stage["cast_ms"] += t["cast_ms"]
+            stage["merge_ms"] += t["merge_ms"]
+            stage["total_ms"] += t["total_ms"]
+
+        clocks = None
+        launches0 = sdpa_b200.launch_count()
+        if sampler is not None:
+            with sampler as clk:
+                ms_dev = timed(ctx, wl.step_device, K, collect)
+                launches = sdpa_b200.launch_count() - launches0   # kernels launched inside the timed region only
+                # The timed region is a few milliseconds: keep the identical load running so the sampler sees it.
+                # Every step is collective across ranks, so the extra steps are a COUNT derived from the
+                # max-reduced time (identical on all ranks), never a per-rank wall-clock loop.
+                extra = int(min(20000, max(1, 1000.0 / max(ms_dev / K, 1e-3))))
+                for _ in range(extra):
+                    wl.step_device()
+                ctx.synchronize()
+                barrier()
+            clocks = clk.summary()
+        else:
+            ms_dev = timed(ctx, wl.step_device, K, collect)
+            launches = sdpa_b200.launch_count() - launches0
+        kernel_name = ctx.last_kernel()
+        # e2e: pinned host buffers through the C ABI (blocking calls, the reference's semantics)
+        for _ in range(2):
+            wl.step_host()
+        ms_host = timed(ctx, wl.step_host, K)
+        parity = wl.parity_check(cfg["tol"] if prec != "f32" else min(cfg["tol"], 1e-5)) if rank == 0 else None
+        res = {
+            "name": name, "m": m, "n": wl.n, "n_local": wl.n_local, "prec": prec, "kernel": kernel_name, "steps": K, "warmup": W,
+            "ms_dev": ms_dev, "ms_host": ms_host, "flops_step": wl.flops_step, "launches": int(launches),
+            "value": wl.flops_step * K / (ms_dev * 1e-3) / 1e12, "e2e_value": wl.flops_step * K / (ms_host * 1e-3) / 1e12,
+            "h2d": wl.h2d_bytes(), "d2h": wl.d2h_bytes(), "stage": stage, "clocks": clocks, "parity": parity,
+            "q_batches": -(-m // (args.q_batch or 8192)),
+        }
+        wl.free()
+        ctx.close()
+        return res
+
     # NVML attach happens here, before the warm-up: nothing driver-side may start inside the timed region
     try:
         gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
@@ -386,32 +571,8 @@ def run_ours(args) -> None:
     barrier()
 
     W, K = max(3, args.warmup), max(1, args.steps)
-    for _ in range(W):
-        step_device()
-    ctx.synchronize()
-
-    # ---- value: inputs resident in HBM ---------------------------------------------------------
-    fused = {"ms": 0.0, "launches": 0.0, "cast_ms": 0.0, "merge_ms": 0.0}
-
-    def collect(t):
-        fused["ms"] += t["fused_ms"]
-        fused["launches"] += t["fused_launches"]
-        fused["cast_ms"] += t["cast_ms"]
-        fused["merge_ms"] += t["merge_ms"]
-
-    launches0 = sdpa_b200.launch_count()
-    with sampler as clk:
-        ms_dev = timed(step_device, K, collect)
-        launches = sdpa_b200.launch_count() - launches0   # kernels launched inside the timed region only
-        # The timed region is a few milliseconds: keep the identical load running so the sampler sees it.
-        # Every step is collective across ranks, so the extra steps are a COUNT derived from the
-        # max-reduced time (identical on all ranks), never a per-rank wall-clock loop.
-        extra = int(min(20000, max(1, 1000.0 / max(ms_dev / K, 1e-3))))
-        for _ in range(extra):
-            step_device()
-        ctx.synchronize()
-        barrier()
-    clocks = clk.summary()
+    head = measure(args.config, W, K, sampler, args.m, args.n_per_gpu, args.precision)
+    clocks = head["clocks"]
     sampler.close()
     if world > 1:   # every rank sampled its own GPU: report the slowest median clock and the union of the reasons
         per_rank = [None] * world
@@ -424,89 +585,107 @@ def run_ours(args) -> None:
         pw = [c["power_w_max"] for c in per_rank if c and c["power_w_max"]]
         clocks["power_w_max"] = max(pw) if pw else None
         clocks["per_rank_sm_mhz"] = [c["sm_mhz"] if c else None for c in per_rank]
-    kernel_name = ctx.last_kernel()
 
-    # ---- e2e: pinned host buffers through the C ABI -------------------------------------------
-    for _ in range(2):
-        step_host()
-    ms_host = timed(step_host, K)
-
-    # ---- correctness guard on rank 0: device and host paths agree, result is finite -----------
-    ok = True
-    if rank == 0:
-        a, b = Rd.cpu().numpy(), Rh.numpy()
-        ok = bool(np.isfinite(a).all() and np.abs(a - b).max() < 1e-6)
-
-    value = flops_step * K / (ms_dev * 1e-3) / 1e12
-    e2e_value = flops_step * K / (ms_host * 1e-3) / 1e12
-    h2d = world * (n_local * (DK + DV) + m * DK) * 8
-    d2h = m * DV * 8
+    # ---- the other BASELINE configurations that fit this GPU count, at their stated shapes -----------------
+    extras = {}
+    extra_names = [x for x in (args.extra.split(",") if args.extra else EXTRAS_BY_GPUS.get(world, [])) if x and x != "none"]
+    if args.m or args.n_per_gpu or args.config != "c3":
+        extra_names = [x for x in extra_names if args.extra]   # shape overrides / other headline: only what was asked for
+    for name in extra_names:
+        r = measure(name, 3, max(3, min(K, 10)))
+        if rank == 0:
+            extras[name] = {
+                "workload": CONFIGS[name]["desc"], "m": r["m"], "n": r["n"], "n_per_gpu": r["n_local"], "kernel": r["kernel"],
+                "value": r["value"], "unit": "TFLOP/s", "ms_per_step": r["ms_dev"] / r["steps"], "steps": r["steps"],
+                "q_rows_per_s": r["m"] * r["steps"] / (r["ms_dev"] * 1e-3), "q_batches_per_step": r["q_batches"],
+                "e2e": {"value": r["e2e_value"], "unit": "TFLOP/s", "ms_per_step": r["ms_host"] / r["steps"],
+                        "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                "stage_ms_per_step": {"cast": r["stage"]["cast_ms"] / r["steps"], "fused": r["stage"]["ms"] / r["steps"],
+                                      "merge": r["stage"]["merge_ms"] / r["steps"]},
+                "gpu_launches": r["launches"], "parity_check": r["parity"],
+            }
 
     # ---- roofline of the dominant kernel (the fused attention kernel), this rank ---------------
     peaks, peaks_src = load_peaks()
-    flops_per_launch = 2.0 * m * n_local * (DK + DV) * K / max(1.0, fused["launches"])
-    avg_ms = fused["ms"] / max(1.0, fused["launches"])
+    st = head["stage"]
+    m, n, n_local = head["m"], head["n"], head["n_local"]
+    kernel_name = head["kernel"]
+    flops_per_launch = 2.0 * m * n_local * (DK + DV) * K / max(1.0, st["launches"])
+    avg_ms = st["ms"] / max(1.0, st["launches"])
     achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
-    if kernel_name.startswith("bf16_umma"):
-        peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
-        bound_note = "tcgen05 bf16 dense; peak = cuBLAS bf16 burst"
-    else:
-        peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
-        bound_note = "fp32 CUDA-core kernel reported against the bf16 tensor peak (its own FFMA ceiling is ~72 TFLOP/s)"
-    traffic = None
+    peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+    bound_note = {"bf16_umma": "tcgen05 bf16 dense; peak = cuBLAS bf16 burst",
+                  "f32_simt": "fp32 CUDA-core kernel reported against the bf16 tensor peak (its own FFMA ceiling is ~72 TFLOP/s)"}.get(
+                      kernel_name, "tcgen05, bf16 operands; peak = cuBLAS bf16 burst (split-precision kernels execute 3 MMAs per algorithmic MMA)")
+    traffic, traffic_src = None, None
     prof = ROOT / "profiles" / "fused_kernel_traffic.json"
     if prof.exists():
         try:
-            traffic = json.loads(prof.read_text()).get(kernel_name, {}).get("dram_bytes_per_launch")
+            ent = json.loads(prof.read_text()).get(kernel_name, {})
+            traffic = ent.get("dram_bytes_per_launch")
+            traffic_src = "static: %s" % ent.get("source", "ncu --set full capture under profiles/")
         except Exception:
             traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic, "kernel": kernel_name, "avg_launch_ms": avg_ms, "launches": fused["launches"],
+                "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "avg_launch_ms": avg_ms, "launches": st["launches"],
                 "flops_per_launch": flops_per_launch, "peak_source": peaks_src, "note": bound_note,
                 "frac_of_sustained": achieved / float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))}
 
     line = None
+    failed = False
     if rank == 0:
+        ms_dev, ms_host = head["ms_dev"], head["ms_host"]
         line = {
-            "metric": "attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": "attention_tflops", "value": head["value"], "unit": "TFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if kernel_name.startswith("bf16_umma") else "f32", "data": "synthetic N(0,1), seeded",
+            "dtype": "f32" if kernel_name == "f32_simt" else "bf16", "data": "synthetic N(0,1), seeded",
             "q_rows_per_s": m * K / (ms_dev * 1e-3),
-            "config": {"workload": desc, "m": m, "n": n, "n_per_gpu": n_local, "dk": DK, "dv": DV,
-                       "parallelism": f"kv-shard x{world} (owner_count/owner_disp), Q replicated",
-                       "merge": "none" if world == 1 else {"peer": "device-side exchange: root merge kernel reads shard states over NVLink (CUDA IPC) behind epoch flags",
-                                                           "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
-                                                           "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],
-                       "submission": "K passes queued back to back (sdpa_enqueue_device_full), one wait after the last; e2e uses the blocking host call",
-                       "l2": "inputs_larger_than_l2 (fp64 Q+K+V per GPU = %d MiB)" % ((n_local * (DK + DV) + m * DK) * 8 >> 20),
-                       "kernel": kernel_name},
-            "e2e": {"value": e2e_value, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "config": shared_config(args.config, world, m, n, n_local),
+            "impl_detail": {
+                "precision": head["prec"], "kernel": kernel_name,
+                "merge": "none" if world == 1 else {"peer": "device-side exchange: root merge kernel reads shard states over NVLink (CUDA IPC) behind epoch flags",
+                                                    "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
+                                                    "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],
+                "submission": "K passes queued back to back (sdpa_enqueue_device_full), one wait after the last; e2e uses the blocking host call"},
+            "e2e": {"value": head["e2e_value"], "unit": "TFLOP/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
                     "ms_per_step": ms_host / K, "q_rows_per_s": m * K / (ms_host * 1e-3)},
-            "gpu_launches": int(launches),
+            "gpu_launches": head["launches"],
             "clocks": clocks,
             "roofline": roofline,
-            "stage_ms_per_step": {"cast_q": fused["cast_ms"] / K, "fused": fused["ms"] / K, "merge": fused["merge_ms"] / K},
-            "self_check": "ok" if ok else "MISMATCH between device-resident and host paths",
+            "stage_ms_per_step": {"cast": st["cast_ms"] / K, "fused": st["ms"] / K, "merge": st["merge_ms"] / K,
+                                  "library_total": st["total_ms"] / K},
+            "parity_check": head["parity"],
+            "configs": extras,
         }
+        failed = not head["parity"]["ok"] or any(not e["parity_check"]["ok"] for e in extras.values())
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            sample = ReferenceSample(n)
+            sample = ReferenceSample(n, rows=min(REF_ROWS, m))
             try:
                 kind, cores = sample.kind_and_cores()
                 dt = sample.run_once()
+                dist_s = sample.distribution_seconds()
             finally:
                 sample.close()
             rps = sample.rows / dt
             line["cpu_baseline"] = {"value": tflops_from_rows_per_s(rps, n), "unit": "TFLOP/s", "cores": cores, "kind": kind,
-                                    "sample": sample.describe(), "q_rows_per_s": rps, "seconds": dt}
+                                    "sample": sample.describe(), "q_rows_per_s": rps, "seconds": dt, "rows": sample.rows,
+                                    "kv_cast_and_distribution_s": dist_s,
+                                    "batch_loop_s": (dt - dist_s) if dist_s is not None else None}
         except Exception as exc:  # the baseline must not sink the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "TFLOP/s", "cores": 0, "kind": "unavailable", "sample": str(exc)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
+        flag = torch.tensor([1 if failed else 0], device="cuda")
+        dist.broadcast(flag, src=0)
+        failed = bool(flag.item())
         dist.destroy_process_group()
+    if failed:
+        if rank == 0:
+            print("bench.py: parity_check FAILED against the oracle", file=sys.stderr)
+        sys.exit(3)
 
 
 def main() -> None:
@@ -516,13 +695,15 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="c3")
-    ap.add_argument("--precision", choices=["auto", "f32", "bf16"], default=None)
+    ap.add_argument("--precision", choices=["auto", "f32", "bf16", "f32x3"], default=None)
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--n-per-gpu", type=int, default=0)
     ap.add_argument("--q-batch", type=int, default=0)
     ap.add_argument("--kv-splits", type=int, default=0)
     ap.add_argument("--merge", choices=["peer", "nccl2", "nccl3"], default="peer",
                     help="cross-GPU merge: peer = device-side exchange over CUDA-IPC peer memory (default); nccl2/nccl3 = NCCL collectives")
+    ap.add_argument("--extra", default="",
+                    help="comma list of further BASELINE configs to run behind the headline (default: c2 at 1 GPU, c4 at 4, c5 at 8; 'none' = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

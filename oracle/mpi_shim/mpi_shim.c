@@ -77,6 +77,29 @@ static void shim_barrier(void)
     }
 }
 
+/* MPI_SHIM_CPUS="c0,c1,...": rank r is pinned to CPU c[r % count] (one rank per physical core, as mpirun --bind-to core
+ * would do); without it the ranks float and the kernel may stack two of them on one core's hyperthreads. */
+static void shim_pin(int rank)
+{
+    const char* list = getenv("MPI_SHIM_CPUS");
+    if (!list || !*list) return;
+    int cpus[1024], n = 0;
+    const char* p = list;
+    while (*p && n < 1024) {
+        char* end = NULL;
+        long v = strtol(p, &end, 10);
+        if (end == p) break;
+        cpus[n++] = (int)v;
+        p = (*end == ',') ? end + 1 : end;
+        if (*end != ',') break;
+    }
+    if (n == 0) return;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET(cpus[rank % n], &set);
+    sched_setaffinity(0, sizeof(set), &set); /* best effort */
+}
+
 int MPI_Init(int* argc, char*** argv)
 {
     (void)argc; (void)argv;
@@ -85,7 +108,10 @@ int MPI_Init(int* argc, char*** argv)
     if (g_size < 1) g_size = 1;
     if (g_size > SHIM_MAX_RANKS) g_size = SHIM_MAX_RANKS;
     g_rank = 0;
-    if (g_size == 1) return MPI_SUCCESS;
+    if (g_size == 1) {
+        shim_pin(0);
+        return MPI_SUCCESS;
+    }
 
     const size_t bytes = 4096 + SHIM_CHUNK * (size_t)(g_size + 1);
     void* base = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
@@ -111,10 +137,12 @@ int MPI_Init(int* argc, char*** argv)
         }
         if (pid == 0) {
             g_rank = r;
+            shim_pin(r);
             return MPI_SUCCESS;
         }
         g_children[r] = pid;
     }
+    shim_pin(0);
     return MPI_SUCCESS;
 }
 

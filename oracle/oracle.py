@@ -258,11 +258,14 @@ def ref_available(kind: str = "mpi") -> bool:
     return p.exists() and os.access(p, os.X_OK) and (kind != "mpi" or host_has_avx512())
 
 
-def run_reference(data_file, kind: str = "mpi", ranks: int = 1, timeout: float = 600.0):
-    """Run a compiled reference binary on a data file.  Returns (correct, elapsed_us, stdout)."""
+def run_reference(data_file, kind: str = "mpi", ranks: int = 1, timeout: float = 600.0, pin_cpus=None):
+    """Run a compiled reference binary on a data file.  Returns (correct, elapsed_us, stdout).
+    pin_cpus: list of logical CPUs; shim rank r is pinned to pin_cpus[r % len] (the `mpirun --bind-to core` analogue)."""
     exe = REF_MPI if kind == "mpi" else REF_SERIAL
     env = dict(os.environ)
     env["MPI_SHIM_NP"] = str(int(ranks))
+    if pin_cpus:
+        env["MPI_SHIM_CPUS"] = ",".join(str(int(c)) for c in pin_cpus)
     proc = subprocess.run([str(exe), str(data_file)], capture_output=True, text=True, env=env, timeout=timeout)
     out = proc.stdout
     mt = _ELAPSED.search(out)

@@ -50,3 +50,37 @@ def test_clock_sampler_summary_and_graceful_start():
         pass
     live.close()
     assert live.summary()["samples"] >= 0
+
+
+def test_bench_config_shapes_match_baseline():
+    """c2/c4/c5 are run at the shapes BASELINE.json states; c3 keeps 65536 keys per GPU (weak scaling)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert bench.config_shape("c3", 8) == (8192, [65536] * 8)
+    assert bench.config_shape("c2", 1) == (4096, [4096])
+    assert bench.config_shape("c4", 4) == (16384, [65536] * 4)
+    assert bench.config_shape("c5", 8) == (32768, [131072] * 8)
+    m, rows = bench.config_shape("c5", 3)          # ragged owner_count split when run on another GPU count
+    assert m == 32768 and sum(rows) == 1048576 and rows == [349526, 349525, 349525]
+    assert bench.EXTRAS_BY_GPUS == {1: ["c2"], 4: ["c4"], 8: ["c5"]}
+
+
+def test_bench_parity_inputs_are_reproducible(oracle):
+    """The oracle check in bench.py regenerates every rank's shard from its seed on rank 0: the regenerated arrays must be
+    the ones the ranks built, and the row subset must be the same on every call."""
+    sys.path.insert(0, str(ROOT))
+    import numpy as np
+    import bench
+    shard_rows = [7, 5, 0, 3]
+    m = 50
+    rows = bench.parity_rows(m)
+    assert len(rows) == 50 and (rows == bench.parity_rows(m)).all()
+    assert len(bench.parity_rows(100000)) == bench.PARITY_ROWS
+    got = bench.oracle_rows(m, shard_rows, rows[:9])
+    K = np.concatenate([bench.make_shard(r, c)[0].numpy() for r, c in enumerate(shard_rows)])
+    V = np.concatenate([bench.make_shard(r, c)[1].numpy() for r, c in enumerate(shard_rows)])
+    ref = oracle.attention_f64(bench.make_q(m).numpy()[rows[:9]], K, V)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-13)
+    a, b = bench.make_shard(3, 11), bench.make_shard(3, 11)
+    assert (a[0] == b[0]).all() and (a[1] == b[1]).all()
+    assert not (bench.make_shard(2, 11)[0] == a[0]).all()
