@@ -1,15 +1,13 @@
 // attn_umma_bf16.cu -- fused QK^T -> online softmax -> .V on the 5th-generation tensor cores
 // (tcgen05.mma, accumulators in TMEM, operands staged by TMA), bf16 operands / fp32 accumulate.
 //
-// Four kernel generations live here behind one launcher (launch_attn_umma); all produce the same
+// Three kernel generations live here behind one launcher (launch_attn_umma); all produce the same
 // partial softmax state and pass the same parity tests:
 //   attn_umma_kernel_v7  DEFAULT.  Cluster of two CTAs forming one M=256 tcgen05.mma.cta_group::2 (each CTA keeps
 //                        half of every K/V tile), S and P double-buffered in TMEM (no MMA waits for the softmax of
 //                        its own S), two softmax groups ping-ponged over alternating key tiles.  See its banner.
 //   attn_umma_kernel     v5 (SDPA_UMMA_V7=0): one CTA, two Q tiles ping-ponged, P aliases S.  Its SAFE variant is
 //                        the overflow-guard fallback of every generation.  Described right below.
-//   attn_umma_kernel_v6  (SDPA_UMMA_V6=1) v7's pipeline without the 2-CTA MMA (K/V multicast instead); kept as the
-//                        measured stepping stone (profiles/README.md).
 //   attn_umma_kernel_v8  (SDPA_UMMA_V8=1, EXPERIMENTAL, single GPU) v7 made persistent: one cluster per SM pair walks a
 //                        contiguous range of (row block, key tile) units; written after the round's GPU budget was
 //                        spent -- its barrier protocol is checked by tools/v8_protocol_sim.py, not yet by hardware.
@@ -45,10 +43,7 @@
 // Shared memory: Q_A, Q_B, 2 x K, 2 x V tiles of 32 KiB = 192 KiB.
 // Roofline: tensor pipe, 4*128^3 flops per tile pair; algorithmic HBM bytes are the bf16
 // Q/K/V and the fp32 partial outputs.
-#include "common.cuh"
-
-#include <cuda.h>
-#include <math_constants.h>
+#include "umma_ptx.cuh"
 
 #include <type_traits>
 #include <vector>
@@ -58,17 +53,14 @@ namespace sdpa {
 
 namespace {
 
-constexpr int TILE = 128;            // rows per Q tile, keys per K/V tile
+using namespace umma;
+
 constexpr int HEAD = 128;            // dk == dv
 constexpr int BLOCK_ROWS = 2 * TILE; // Q rows per CTA
 constexpr int NTHREADS = 640;
 constexpr int STAGES = 2;
-constexpr uint32_t TILE_BYTES = TILE * HEAD * 2;      // 32 KiB
-constexpr uint32_t HALF_BYTES = TILE_BYTES / 2;       // one 64-column TMA box
 constexpr float kLazyThreshold = 8.0f;                // safe mode: rescale O only if the max grew by > 2^8
 constexpr float kGuardThreshold = 64.0f;              // fast mode: exponents beyond 2^64 hand the launch to the safe kernel
-constexpr int kDefaultParts = 2;                      // v6: softmax warpgroups per tile
-constexpr bool kDefaultV6 = false;                    // flipped once v6 is validated on hardware
 constexpr int kDefaultPoly = 0;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
 
 constexpr uint32_t TMEM_S = 0;    // + 128 * tile
@@ -86,260 +78,6 @@ struct __align__(1024) SharedStorage {
     float xchg[2][2][2][TILE];   // [tile][parity][column half][row]: row-max / row-sum exchange
 };
 
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug traps (the launch fails with an error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag)
-{
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("sdpa_b200: mbarrier timeout tag=%d block=(%d,%d) thread=%d parity=%u\n", tag, blockIdx.x, blockIdx.y,
-                   threadIdx.x, parity);
-            __trap();
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// One lane of a converged warp (the instruction is warp-uniform, so everything around it can
-// stay on the uniform datapath; a divergent `lane == 0` branch forces R2UR/ELECT traffic per MMA).
-__device__ __forceinline__ bool elect_one_sync()
-{
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem]
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// mbarrier arrives once every tcgen05 operation issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-#define SDPA_TMEM_LD32(taddr, r)                                                                             \
-    asm volatile(                                                                                            \
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                            \
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                            \
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"            \
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),            \
-          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),          \
-          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),          \
-          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                                                               \
-        : "r"(taddr)                                                                                         \
-        : "memory")
-
-#define SDPA_TMEM_ST32(taddr, r)                                                                             \
-    asm volatile(                                                                                            \
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                      \
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                           \
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"                   \
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),       \
-          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),     \
-          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])      \
-        : "memory")
-
-
-#define SDPA_TMEM_ST8(taddr, r)                                                                              \
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"             \
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),  \
-                   "r"(r[7])                                                                                  \
-                 : "memory")
-
-#define SDPA_TMEM_LD16(taddr, r)                                                                             \
-    asm volatile(                                                                                            \
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                            \
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                     \
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),     \
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),            \
-          "=r"(r[15])                                                                                         \
-        : "r"(taddr)                                                                                         \
-        : "memory")
-
-#define SDPA_TMEM_ST16(taddr, r)                                                                             \
-    asm volatile(                                                                                            \
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                                      \
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"                           \
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
-          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])        \
-        : "memory")
-
-__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi)
-{
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c)
-{
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b)
-{
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-// 2^x for two packed values on the FMA/ALU pipes (no MUFU): x = n + f, n = round(x) taken from the
-// low mantissa bits of x + 1.5*2^23, f in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (max
-// relative error 7.5e-5, far below the bf16 rounding of P), 2^n by an integer multiply-add into the
-// exponent field.  Inputs are clamped at -126 (result ~ 0); callers guarantee x < 64.
-__device__ __forceinline__ void exp2_poly_x2(uint64_t x2, float& p0, float& p1)
-{
-    float x0, x1;
-    unpack_f32x2(x2, x0, x1);
-    x0 = fmaxf(x0, -126.f);
-    x1 = fmaxf(x1, -126.f);
-    const uint64_t xc = pack_f32x2(x0, x1);
-    const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);
-    const uint64_t xr = add_f32x2(xc, magic);                                   // integer part lands in the mantissa
-    const uint64_t n2 = add_f32x2(xr, pack_f32x2(-12582912.f, -12582912.f));    // round(x) as a float
-    const uint64_t f2 = fma_f32x2(n2, pack_f32x2(-1.f, -1.f), xc);              // x - round(x)
-    uint64_t p = fma_f32x2(pack_f32x2(0.0551716685f, 0.0551716685f), f2, pack_f32x2(0.2426111251f, 0.2426111251f));
-    p = fma_f32x2(p, f2, pack_f32x2(0.6932609677f, 0.6932609677f));
-    p = fma_f32x2(p, f2, pack_f32x2(0.9999280572f, 0.9999280572f));
-    float q0, q1, r0, r1;
-    unpack_f32x2(p, q0, q1);
-    unpack_f32x2(xr, r0, r1);
-    p0 = __uint_as_float(__float_as_uint(r0) * 0x800000u + __float_as_uint(q0));   // += n << 23
-    p1 = __uint_as_float(__float_as_uint(r1) * 0x800000u + __float_as_uint(q1));
-}
-
-__device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
-{
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-__device__ __forceinline__ float fast_exp2(float x)
-{
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// ---------------------------------------------------------------- UMMA descriptors
-// Shared-memory matrix descriptor (sm_100): start address [0,14) (>>4), leading byte offset
-// [16,30) (>>4), stride byte offset [32,46) (>>4), version = 1 at [46,48), layout type at
-// [61,64) (2 = 128-byte swizzle).
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// K-major operand tile [128 rows][128 cols] bf16 stored as two [128][64] 128B-swizzled boxes:
-// 8-row groups are 1024 B apart (SBO); the k-th 16-column slice starts (k%4)*32 B into box k/4.
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k16)
-{
-    return make_desc(tile_addr + (uint32_t)(k16 >> 2) * HALF_BYTES + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
-}
-// MN-major operand tile (V: [128 keys][128 dv], dv contiguous) stored as two [128 keys][64 dv]
-// swizzled boxes: 64-column groups are HALF_BYTES apart (LBO), 8-key groups 1024 B apart (SBO);
-// the k-th 16-key slice starts k*16 rows = k*2048 B into the tile.
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int k16)
-{
-    return make_desc(tile_addr + (uint32_t)k16 * 2048u, HALF_BYTES, 1024u);
-}
-// Instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1),
-// b_major at bit 16, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int b_mn_major)
-{
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(m >> 4) << 24);
-}
 
 struct KernelParams {
     int rows;            // valid Q rows
@@ -781,385 +519,9 @@ attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
 }
 
-// =====================================================================================
-// v6: cluster of two CTAs, ONE 128-row Q tile per CTA, chain-free pipeline.
-//
-// v5 (above) keeps two Q tiles per CTA; because P aliases S in TMEM, a tile's next S = Q K^T cannot be
-// issued before its P V has consumed P, so each tile is a serial chain softmax -> PV -> S and the
-// iteration period is their SUM (profiles/r01/timeline_trace_v5_cta00.txt).  Here one Q tile owns the
-// whole TMEM: S and P are double-buffered and separate (S0 S1 O P0 P1 = 128+128+128+64+64 columns), so
-//      tensor pipe :  S(0) S(1) | PV(0) S(2) | PV(1) S(3) | ...      (never waits for the softmax of its own S)
-//      softmax     :  tile 0 | tile 1 | tile 2 | ...                  (S(j+1) is ready before tile j ends)
-// and the period becomes the MAX of the two.  Halving the rows per CTA would double the L2->SM traffic of
-// K/V (beyond the ~6.3 KB/clk L2 limit), so the two CTAs of a cluster take neighbouring Q tiles and the
-// SAME key range: each TMA-loads one 64-column half of every K/V tile and multicasts it into both CTAs'
-// shared memory; a stage is recycled when both CTAs' MMAs have committed (tcgen05.commit multicast).
-// Only the fast variant exists here; the overflow guard hands the launch to the v5 SAFE kernel.
-// =====================================================================================
-
-constexpr int V6_KSTAGES = 3, V6_VSTAGES = 2;
-constexpr uint32_t V6_S = 0, V6_O = 256, V6_P = 384;
-
-struct __align__(1024) SharedV6 {
-    uint8_t q[TILE_BYTES];
-    uint8_t k[V6_KSTAGES][TILE_BYTES];
-    uint8_t v[V6_VSTAGES][TILE_BYTES];
-    uint64_t q_full;
-    uint64_t k_full[V6_KSTAGES], k_empty[V6_KSTAGES];
-    uint64_t v_full[V6_VSTAGES], v_empty[V6_VSTAGES];
-    uint64_t s_full[2], p_ready[2], pv_done[2], o_done;
-    uint32_t tmem_base;
-    float xchg[2][4][TILE];   // [first-tile max | final sum][column part][row]
-};
-
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                                      uint16_t cta_mask)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-        " [%0], [%1, {%4, %5}], [%2], %3;"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1)
-        : "memory");
-}
-// arrive (once the MMAs issued so far complete) on the barrier at this offset in every CTA of the mask
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_cta_rank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-
-// NPARTS = softmax warpgroups per tile (2 or 4): a thread owns one row and 128/NPARTS of its keys.
-template <bool TRACE, int POLY, int NPARTS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * NPARTS, 1)
-attn_umma_kernel_v6(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                    const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
-{
-    extern __shared__ uint8_t smem_raw[];
-    SharedV6& sm = *reinterpret_cast<SharedV6*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
-    const int lane = threadIdx.x & 31;
-    const int row_block = blockIdx.x;             // 128 rows; blockIdx.x = 2*cluster + rank
-    const int split = blockIdx.y;
-    const uint32_t rank = cluster_cta_rank();      // 0 or 1: which 64-column half of every K/V tile this CTA loads
-
-    const int tq = prm.tiles_total / prm.splits, tr = prm.tiles_total % prm.splits;
-    const int tile_begin = split * tq + min(split, tr);
-    const int num_tiles = tq + (split < tr ? 1 : 0);   // identical in both CTAs of the cluster
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&map_q);
-        prefetch_tensormap(&map_k);
-        prefetch_tensormap(&map_v);
-        mbar_init(&sm.q_full, 1);
-        mbar_init(&sm.o_done, 1);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.s_full[i], 1);
-            mbar_init(&sm.p_ready[i], 128 * NPARTS);
-            mbar_init(&sm.pv_done[i], 1);
-        }
-        for (int i = 0; i < V6_KSTAGES; ++i) {
-            mbar_init(&sm.k_full[i], 1);
-            mbar_init(&sm.k_empty[i], 2);   // both CTAs of the cluster must have consumed the stage
-        }
-        for (int i = 0; i < V6_VSTAGES; ++i) {
-            mbar_init(&sm.v_full[i], 1);
-            mbar_init(&sm.v_empty[i], 2);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
-    tcgen05_fence_after();
-    const uint32_t tmem = sm.tmem_base;
-    auto stamp = [&](int role, int j, int ev) {
-        if constexpr (TRACE) {
-            if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < TRACE_ITERS)
-                prm.trace[(role * TRACE_ITERS + j) * TRACE_EVENTS + ev] = clock64();
-        }
-    };
-
-    if (warp < 4) {
-        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (num_tiles > 0) {
-            if (warp == 0) {
-                // ================================ TMA producer ================================
-                const int qrow = row_block * TILE;
-                const uint16_t both = 0x3;
-                for (int j = 0; j < num_tiles; ++j) {
-                    const int ks = j % V6_KSTAGES, vs = j % V6_VSTAGES;
-                    const uint32_t kph = (uint32_t)(j / V6_KSTAGES) & 1u, vph = (uint32_t)(j / V6_VSTAGES) & 1u;
-                    const int key0 = (tile_begin + j) * TILE;
-                    if (j == 0 && elect_one_sync()) {
-                        mbar_arrive_expect_tx(&sm.q_full, TILE_BYTES);
-                        tma_load_2d(sm.q, &map_q, &sm.q_full, 0, qrow);
-                        tma_load_2d(sm.q + HALF_BYTES, &map_q, &sm.q_full, 64, qrow);
-                    }
-                    mbar_wait(&sm.k_empty[ks], kph ^ 1u, 100 + ks);
-                    stamp(5, j, 0);
-                    if (elect_one_sync()) {
-                        // my barrier will see the whole tile: my half + the half the peer multicasts to me
-                        mbar_arrive_expect_tx(&sm.k_full[ks], TILE_BYTES);
-                        tma_load_2d_multicast(sm.k[ks] + rank * HALF_BYTES, &map_k, &sm.k_full[ks], 64 * (int)rank, key0, both);
-                    }
-                    mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
-                    stamp(5, j, 1);
-                    if (elect_one_sync()) {
-                        mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
-                        tma_load_2d_multicast(sm.v[vs] + rank * HALF_BYTES, &map_v, &sm.v_full[vs], 64 * (int)rank, key0, both);
-                    }
-                    __syncwarp();
-                }
-            } else if (warp == 1) {
-                // ================================ MMA issuer ==================================
-                constexpr uint32_t idesc_qk = make_idesc(TILE, TILE, 0);
-                constexpr uint32_t idesc_pv = make_idesc(TILE, HEAD, 1);
-                const uint64_t dq = desc_kmajor(smem_u32(sm.q), 0);
-                const uint64_t dkk[V6_KSTAGES] = {desc_kmajor(smem_u32(sm.k[0]), 0), desc_kmajor(smem_u32(sm.k[1]), 0),
-                                                  desc_kmajor(smem_u32(sm.k[2]), 0)};
-                const uint64_t dvv[V6_VSTAGES] = {desc_mnmajor(smem_u32(sm.v[0]), 0), desc_mnmajor(smem_u32(sm.v[1]), 0)};
-                const uint16_t both = 0x3;
-
-                auto issue_s = [&](int j) {
-                    const int sb = j & 1, ks = j % V6_KSTAGES;
-                    mbar_wait(&sm.k_full[ks], (uint32_t)(j / V6_KSTAGES) & 1u, 200 + ks);
-                    tcgen05_fence_after();
-                    if (elect_one_sync()) {
-                        const uint64_t b0 = dkk[ks];
-                        const uint32_t d = tmem + V6_S + 128u * sb;
-#pragma unroll
-                        for (int kk = 0; kk < HEAD / 16; ++kk) {
-                            const uint64_t off = (uint64_t)(((kk >> 2) * HALF_BYTES + (kk & 3) * 32u) >> 4);
-                            umma_ss(d, dq + off, b0 + off, idesc_qk, kk > 0 ? 1u : 0u);
-                        }
-                        umma_commit(&sm.s_full[sb]);
-                        umma_commit_multicast(&sm.k_empty[ks], both);
-                    }
-                    __syncwarp();
-                };
-                auto issue_pv = [&](int j, bool last) {
-                    const int pb = j & 1, vs = j % V6_VSTAGES;
-                    mbar_wait(&sm.v_full[vs], (uint32_t)(j / V6_VSTAGES) & 1u, 210 + vs);
-                    mbar_wait(&sm.p_ready[pb], (uint32_t)(j >> 1) & 1u, 212 + pb);
-                    stamp(4, j, 1);
-                    tcgen05_fence_after();
-                    if (elect_one_sync()) {
-                        const uint64_t b0 = dvv[vs];
-                        const uint32_t d = tmem + V6_O;
-                        const uint32_t a = tmem + V6_P + 64u * pb;
-#pragma unroll
-                        for (int kk = 0; kk < TILE / 16; ++kk)
-                            umma_ts(d, a + 8u * kk, b0 + (uint64_t)((kk * 2048u) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                        umma_commit(&sm.pv_done[pb]);
-                        umma_commit_multicast(&sm.v_empty[vs], both);
-                        if (last) umma_commit(&sm.o_done);
-                    }
-                    __syncwarp();
-                };
-
-                mbar_wait(&sm.q_full, 0, 201);
-                issue_s(0);
-                if (num_tiles > 1) issue_s(1);
-                for (int j = 0; j < num_tiles; ++j) {
-                    stamp(4, j, 0);
-                    issue_pv(j, j + 1 == num_tiles);
-                    stamp(4, j, 2);
-                    if (j + 2 < num_tiles) issue_s(j + 2);
-                    stamp(4, j, 3);
-                }
-            }
-        }
-    } else {
-        if constexpr (NPARTS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        constexpr int COLS = TILE / NPARTS;            // keys (S columns) per thread: 64 or 32
-        const int sw = warp - 4;
-        const int half = sw >> 2;                      // which COLS-wide part of the row (0..NPARTS-1)
-        const int quad = warp & 3;                     // TMEM lane quadrant of this warp
-        const int row_in_tile = quad * 32 + lane;
-        const int grow = row_block * TILE + row_in_tile;
-        if (num_tiles > 0) {
-            // ================================ softmax + epilogue ==========================
-            const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-            const uint32_t o_addr = tmem + lane_base + V6_O + (uint32_t)COLS * half;
-            const float scale = prm.scale_log2;
-            const uint64_t scale2 = pack_f32x2(scale, scale);
-            const int bar_id = 1 + quad;               // pair barrier: the two warps that share these 32 rows
-
-            float m_ref = -CUDART_INF_F;
-            float lsum = 0.f;
-
-            auto exp_chunk = [&](const uint32_t* sv, uint64_t neg_ref2, uint64_t& acc0, uint64_t& acc1, uint32_t* pr) {
-#pragma unroll
-                for (int c = 0; c < 16; c += 2) {
-                    const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
-                    const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
-                    float p0, p1;
-                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
-                    if (poly) {
-                        exp2_poly_x2(t2, p0, p1);
-                    } else {
-                        float t0, t1;
-                        unpack_f32x2(t2, t0, t1);
-                        p0 = fast_exp2(t0);
-                        p1 = fast_exp2(t1);
-                    }
-                    const uint64_t p2 = pack_f32x2(p0, p1);
-                    if (c & 4) acc1 = add_f32x2(acc1, p2);
-                    else acc0 = add_f32x2(acc0, p2);
-                    pr[c / 2] = pack_bf16x2(p0, p1);
-                }
-            };
-
-            auto tile_step = [&](int j, auto masked_tag, auto first_tag) {
-                constexpr bool MASKED = decltype(masked_tag)::value;
-                constexpr bool FIRST = decltype(first_tag)::value;
-                const int sb = j & 1;
-                const uint32_t s_addr = tmem + lane_base + V6_S + 128u * sb + (uint32_t)COLS * half;
-                const uint32_t p_addr = tmem + lane_base + V6_P + 64u * sb + (uint32_t)(COLS / 2) * half;
-                mbar_wait(&sm.s_full[sb], (uint32_t)(j >> 1) & 1u, 300 + sb);
-                if (quad == 0 && half < 2) stamp(half, j, 0);
-                tcgen05_fence_after();
-
-                uint32_t sr[COLS];
-                SDPA_TMEM_LD32(s_addr, sr);
-                if constexpr (COLS == 64) SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
-                tmem_wait_ld();
-                if (quad == 0 && half < 2) stamp(half, j, 1);
-                if constexpr (MASKED) {
-                    const int keys_left = prm.n - (tile_begin + j) * TILE - COLS * half;
-#pragma unroll
-                    for (int c = 0; c < COLS; ++c)
-                        if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
-                }
-                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
-#pragma unroll
-                for (int c = 0; c < COLS; c += 8) {
-                    mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1])));
-                    mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
-                    mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
-                    mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
-                }
-                const float my_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if constexpr (FIRST) {
-                    // the reference of the whole key range: the first tile's row max, agreed by the two halves
-                    sm.xchg[0][half][row_in_tile] = my_max;
-                    named_barrier_sync(bar_id, 32 * NPARTS);
-                    m_ref = my_max;
-#pragma unroll
-                    for (int p = 0; p < NPARTS; ++p) m_ref = fmaxf(m_ref, sm.xchg[0][p][row_in_tile]);
-                }
-                // No wait is needed before overwriting P buffer sb: PV(j-2), its last reader, was issued before
-                // S(j), and the commit behind s_full(j) covers every MMA issued before it.
-                if (quad == 0 && half < 2) stamp(half, j, 2);
-
-                const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
-                uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
-#pragma unroll
-                for (int ch = 0; ch < COLS / 16; ++ch) {
-                    uint32_t pr[8];
-                    exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr);
-                    SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
-                }
-                float a0, a1, a2, a3;
-                unpack_f32x2(acc0, a0, a1);
-                unpack_f32x2(acc1, a2, a3);
-                lsum += (a0 + a1) + (a2 + a3);
-                if constexpr (!FIRST) {
-                    // overflow guard, off the critical path (the max chain overlaps the exponentials)
-                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
-                        if (lane == 0) atomicExch(prm.guard, prm.epoch);   // hand the launch to the SAFE kernel
-                    }
-                }
-                if (quad == 0 && half < 2) stamp(half, j, 4);
-                tmem_wait_st();
-                tcgen05_fence_before();
-                mbar_arrive(&sm.p_ready[sb]);
-                if (quad == 0 && half < 2) stamp(half, j, 5);
-            };
-
-            const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
-            const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
-            if (full_tiles > 0) tile_step(0, std::false_type{}, std::true_type{});
-            for (int j = 1; j < full_tiles; ++j) tile_step(j, std::false_type{}, std::false_type{});
-            if (ragged) {
-                if (num_tiles == 1) tile_step(0, std::true_type{}, std::true_type{});
-                else tile_step(num_tiles - 1, std::true_type{}, std::false_type{});
-            }
-
-            // ---------------- epilogue ----------------
-            sm.xchg[1][half][row_in_tile] = lsum;
-            named_barrier_sync(bar_id, 32 * NPARTS);
-            lsum = 0.f;
-#pragma unroll
-            for (int p = 0; p < NPARTS; ++p) lsum += sm.xchg[1][p][row_in_tile];
-            mbar_wait(&sm.o_done, 0, 320);
-            tcgen05_fence_after();
-            const bool valid = grow < prm.rows;
-            const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
-#pragma unroll
-            for (int c0 = 0; c0 < COLS; c0 += 32) {
-                uint32_t orr[32];
-                SDPA_TMEM_LD32(o_addr + c0, orr);
-                tmem_wait_ld();
-                if (valid) {
-                    const int col = COLS * half + c0;
-                    if (prm.out64 != nullptr) {
-                        double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + col);
-#pragma unroll
-                        for (int c = 0; c < 32; c += 2)
-                            dst[c / 2] = make_double2((double)(__uint_as_float(orr[c]) * inv),
-                                                      (double)(__uint_as_float(orr[c + 1]) * inv));
-                    } else {
-                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + col);
-#pragma unroll
-                        for (int c = 0; c < 32; c += 4)
-                            dst[c / 4] = make_float4(__uint_as_float(orr[c]), __uint_as_float(orr[c + 1]),
-                                                     __uint_as_float(orr[c + 2]), __uint_as_float(orr[c + 3]));
-                    }
-                }
-            }
-            if (valid && half == 0 && prm.out64 == nullptr) {
-                prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = m_ref * scale;
-                prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = lsum;
-            }
-        } else if (grow < prm.rows) {
-            // empty key range: the neutral state (0, -inf, 0), mpi.c:172,188
-            if (prm.out64 != nullptr) {
-                for (int c = 0; c < COLS; ++c) prm.out64[(size_t)grow * HEAD + COLS * half + c] = 0.0;
-            } else {
-                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + COLS * half;
-                for (int c = 0; c < COLS; ++c) dst[c] = 0.f;
-                if (half == 0) {
-                    prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
-                    prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
-                }
-            }
-        }
-    }
-
-    tcgen05_fence_before();
-    __syncthreads();
-    cluster_sync_all();   // neither CTA leaves while the other may still multicast into it or arrive on its barriers
-    if (warp == 1) {
-        tcgen05_fence_after();
-        tmem_dealloc(tmem, 512);
-    }
-}
+// (v6 -- the cluster-of-two, multicast stepping stone between v5 and v7 -- was removed in round 2: measured slower than both,
+//  profiles/README.md keeps its numbers.)
+constexpr uint32_t V6_S = 0, V6_O = 256, V6_P = 384;   // TMEM map of the chain-free kernels: S0 S1 | O | P0 P1
 
 // =====================================================================================
 // v7: v6 with the 2-CTA tensor-core instruction (tcgen05.mma.cta_group::2).  The two CTAs of a cluster
@@ -1187,58 +549,6 @@ struct __align__(1024) SharedV7 {
     float mref[TILE];         // the agreed reference, handed from softmax group 0 to the others
 };
 
-// 2-SM TMA load: data into THIS CTA's shared memory, completion bytes on the LEADER CTA's mbarrier
-// (bit 24 of the shared::cluster address selects the CTA of the pair; clearing it addresses rank 0).
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t cta_rank)
-{
-    uint32_t ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(cta_rank));
-    return ra;
-}
-// Remote arrive with the default (CTA-scope release) semantics.  The data handed over is in TMEM / is
-// TMA traffic, ordered by tcgen05.fence / complete_tx; an explicit .release.cluster here costs ~1100
-// cycles per arrive (measured, profiles/r01/timeline_trace_v7_first.txt).
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
-{
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void umma_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
 
 // GROUPS = softmax groups ping-ponged over alternating key tiles (group g owns tiles j = g mod GROUPS and the
 // S/P buffers g): with the reference fixed by the first tile the tiles are independent, so while one
@@ -2119,19 +1429,17 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
     return SDPA_OK;
 }
 
-// Kernel generation: v6 (cluster of two 128-row CTAs, chain-free pipeline) unless SDPA_UMMA_V6=0 asks for v5.
 static bool trace_env_set()
 {
     const char* t = getenv("SDPA_UMMA_TRACE");
     return t && *t;
 }
 
-static bool use_v6()
+// Kernel generation: v7 (cluster of two 128-row CTAs, 2-CTA MMA) unless SDPA_UMMA_V7=0 asks for v5.
+static bool use_v7()
 {
     const char* e7 = getenv("SDPA_UMMA_V7");
-    const char* e = getenv("SDPA_UMMA_V6");
-    if (e7 ? (*e7 == '1') : (e == nullptr)) return true;   // v7 (default) shares v6's grid shape (128-row CTAs in clusters of two)
-    return e ? (*e != '0') : kDefaultV6;
+    return e7 ? (*e7 != '0') : true;
 }
 
 // Persistent kernel (EXPERIMENTAL, SDPA_UMMA_V8=1): its work map for (rows, n) on sm_count SMs, or false when the shape
@@ -2177,7 +1485,7 @@ bool umma_plan_last_v8(const UmmaPlan* plan, WorkMap* wm, int* max_pieces, const
 
 int attn_umma_pick_splits(int rows, int n, int sm_count)
 {
-    const int row_blocks = use_v6() ? 2 * ceil_div(ceil_div(rows, TILE), 2) : ceil_div(rows, BLOCK_ROWS);
+    const int row_blocks = use_v7() ? 2 * ceil_div(ceil_div(rows, TILE), 2) : ceil_div(rows, BLOCK_ROWS);
     const int tiles = ceil_div(n, TILE);
     if (row_blocks <= 0 || tiles <= 1) return 1;
     // choose the split count (<= 64, >= 4 key tiles each) with the best wave efficiency of the
@@ -2234,15 +1542,6 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true, false, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-        const int sb6 = (int)(sizeof(SharedV6) + 1024);
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v6<true, kDefaultPoly, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb6));
         const int sb7 = (int)(sizeof(SharedV7) + 1024);
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
@@ -2272,16 +1571,11 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.epoch = ++plan->epoch;
     if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
     dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);                      // v5 / SAFE: 256 rows per CTA
-    const char* env_v7 = getenv("SDPA_UMMA_V7");   // the 2-CTA kernel is the default; SDPA_UMMA_V7=0 selects v5 (or v6 with SDPA_UMMA_V6=1)
-    const bool v7 = env_v7 ? (*env_v7 == '1') : (getenv("SDPA_UMMA_V6") == nullptr);
+    const bool v7 = use_v7();   // the 2-CTA kernel is the default; SDPA_UMMA_V7=0 selects v5
     const char* env_groups = getenv("SDPA_UMMA_GROUPS");   // v7: softmax groups ping-ponged over key tiles (1 or 2)
     const bool groups2 = env_groups ? (atoi(env_groups) == 2) : true;
-    const bool v6 = use_v6() || v7;
     const size_t smem7 = sizeof(SharedV7) + 1024;
-    const char* env_parts = getenv("SDPA_UMMA_PARTS");   // v6: softmax warpgroups per tile (2 or 4)
-    const bool parts4 = env_parts ? (atoi(env_parts) == 4) : (kDefaultParts == 4);
-    dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v6: 128 rows per CTA, clusters of two along x
-    const size_t smem6 = sizeof(SharedV6) + 1024;
+    dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v7: 128 rows per CTA, clusters of two along x
     // persistent kernel: only when the engine announced that it merges by pieces, no direct fp64 output, and the caller's
     // split count is the map's piece count (the SAFE twin behind it then fills every partial slot the merge may read)
     WorkMap wm8{0, 0, 0};
@@ -2298,8 +1592,6 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         prm.trace = dtrace;
         if (v7 && groups2) attn_umma_kernel_v7<true, 4, 2, 2><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else if (v7) attn_umma_kernel_v7<true, 4, 2, 1><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (v6 && parts4) attn_umma_kernel_v6<true, kDefaultPoly, 4><<<grid6, 640, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (v6) attn_umma_kernel_v6<true, kDefaultPoly, 2><<<grid6, 384, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         else attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
         std::vector<long long> host(count);
@@ -2342,19 +1634,6 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         else if (poly == 8) SDPA_LAUNCH_V7(8, 2);
         else SDPA_LAUNCH_V7(4, 2);
 #undef SDPA_LAUNCH_V7
-        count_launch();
-    } else if (v6) {
-#define SDPA_LAUNCH_V6(P, N) attn_umma_kernel_v6<false, P, N><<<grid6, 128 + 128 * N, smem6, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
-        if (parts4) {
-            if (poly == 0) SDPA_LAUNCH_V6(0, 4);
-            else if (poly == 8) SDPA_LAUNCH_V6(8, 4);
-            else SDPA_LAUNCH_V6(4, 4);
-        } else {
-            if (poly == 0) SDPA_LAUNCH_V6(0, 2);
-            else if (poly == 8) SDPA_LAUNCH_V6(8, 2);
-            else SDPA_LAUNCH_V6(4, 2);
-        }
-#undef SDPA_LAUNCH_V6
         count_launch();
     } else {
         if (!chunked && poly == 0) attn_umma_kernel<false, false, 0, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
