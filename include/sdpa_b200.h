@@ -36,9 +36,12 @@ typedef enum sdpa_status {
 
 /* Arithmetic of the fused QK^T -> softmax -> .V kernel. */
 typedef enum sdpa_precision {
-    SDPA_PREC_AUTO = 0, /* BF16 tensor-core kernel when dk==dv in {64,128}, else F32 */
-    SDPA_PREC_F32 = 1,  /* fp32 CUDA-core kernel: the reference's own arithmetic (mpi.c:168-189) */
-    SDPA_PREC_BF16 = 2  /* bf16 operands, fp32 accumulate, tcgen05 tensor cores   */
+    SDPA_PREC_AUTO = 0,  /* fp32-class accuracy, like the reference (mpi.c:168-189): BF16X3 when dk, dv are multiples of 8
+                            up to 128, else F32.  Never BF16: the reference's 0.02 gate (mpi.c:476) must hold on peaky inputs */
+    SDPA_PREC_F32 = 1,   /* fp32 CUDA-core kernel: the reference's own arithmetic; any dk, dv <= 256                        */
+    SDPA_PREC_BF16 = 2,  /* opt-in: bf16 operands, fp32 accumulate, tcgen05; dk, dv multiples of 8 up to 256                */
+    SDPA_PREC_BF16X3 = 3 /* fp32 operands split into bf16 hi + lo, three tcgen05.mma per contraction into one fp32
+                            accumulator (<= 1e-5 on N(0,1) inputs); dk, dv multiples of 8 up to 128                         */
 } sdpa_precision;
 
 /* How the per-shard softmax states are merged across GPUs (mpi.c:340-380). */
@@ -87,7 +90,7 @@ typedef struct sdpa_ctx sdpa_ctx;
  *                    from sdpa_set_bootstrap_id() (a launcher with MPI broadcasts
  *                    the id) or, failing that, from the file
  *                    named by env SDPA_NCCL_ID_FILE.  Rank 0 scatters the shards.
- *    Precision / batch come from env SDPA_PRECISION (auto|f32|bf16), SDPA_Q_BATCH.
+ *    Precision / batch come from env SDPA_PRECISION (auto|f32|bf16|bf16x3), SDPA_Q_BATCH.
  *    Fatal errors: message on stderr, exit(1).
  * ------------------------------------------------------------------------- */
 void attention(double* Q, double* K, double* V, double* result,
@@ -185,7 +188,7 @@ sdpa_status sdpa_last_timings(sdpa_ctx* ctx, float* out6);
 /* The same stage times summed over every sdpa_attention_* call since the last reset; the event queries happen
  * here, not inside the calls.  out6: [0] total, [1] casts, [2] fused, [3] merge (ms), [4] fused launches, [5] calls. */
 sdpa_status sdpa_accumulated_timings(sdpa_ctx* ctx, double* out6, int reset);
-/* Which kernel the last call used: "f32_simt" | "bf16_umma". */
+/* Which kernel the last call used: "f32_simt" | "bf16_umma" | "bf16_umma_v8" | "bf16_umma_general" | "bf16x3_umma". */
 const char* sdpa_last_kernel(sdpa_ctx* ctx);
 
 /* ---------------------------------------------------------------------------
@@ -196,6 +199,8 @@ const char* sdpa_last_kernel(sdpa_ctx* ctx);
 sdpa_status sdpa_cvt_d2f(float* dst_dev, const double* src_dev, size_t count, void* stream);
 sdpa_status sdpa_cvt_f2d(double* dst_dev, const float* src_dev, size_t count, void* stream);
 sdpa_status sdpa_cvt_d2bf16(uint16_t* dst_dev, const double* src_dev, size_t count, void* stream);
+/* The operand split of SDPA_PREC_BF16X3: hi = bf16(fp32(x)), lo = bf16(fp32(x) - hi), both round-to-nearest-even. */
+sdpa_status sdpa_cvt_d2bf16x2(uint16_t* hi_dev, uint16_t* lo_dev, const double* src_dev, size_t count, void* stream);
 
 /* ---------------------------------------------------------------------------
  * 5. Diagnostics.

@@ -44,6 +44,7 @@
 // Roofline: tensor pipe, 4*128^3 flops per tile pair; algorithmic HBM bytes are the bf16
 // Q/K/V and the fp32 partial outputs.
 #include "umma_ptx.cuh"
+#include "umma_general.h"
 
 #include <type_traits>
 #include <vector>
@@ -1342,23 +1343,24 @@ PFN_encodeTiled get_encode()
     return fn;
 }
 
-// 2-D bf16 row-major [rows][128] tensor, box = 64 columns x 128 rows, 128-byte swizzle, OOB rows -> 0.
-sdpa_status encode_map(CUtensorMap* map, const void* base, int rows, int box_rows = TILE)
+// 2-D bf16 row-major [rows][cols] tensor, box = 64 columns x box_rows rows, 128-byte swizzle; rows and columns of a box that
+// lie outside the tensor are filled with zeros (this is what replaces the reference's masked vector tails, mpi.c:115-119).
+sdpa_status encode_map(CUtensorMap* map, const void* base, int rows, int box_rows = TILE, int cols = HEAD)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");
         return SDPA_ERR_CUDA;
     }
-    const cuuint64_t dims[2] = {(cuuint64_t)HEAD, (cuuint64_t)(rows > 0 ? rows : 1)};
-    const cuuint64_t strides[1] = {(cuuint64_t)HEAD * 2};
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)(rows > 0 ? rows : 1)};
+    const cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (base=%p rows=%d)", (int)r, base, rows);
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (base=%p rows=%d cols=%d)", (int)r, base, rows, cols);
         return SDPA_ERR_CUDA;
     }
     return SDPA_OK;
@@ -1367,6 +1369,9 @@ sdpa_status encode_map(CUtensorMap* map, const void* base, int rows, int box_row
 }  // namespace
 
 struct UmmaPlan {
+    int dk = 0, dv = 0, hl = 1;      // operand widths; hl = 2: hi/lo split operands (lo arrays lo_off elements behind hi)
+    bool general = false;            // the shape goes to attn_umma_general_kernel (anything but dk = dv = 128 bf16)
+    CUtensorMap gmaps[2][6];         // general kernel, per Q slot: q_hi q_lo k_hi k_lo v_hi v_lo
     CUtensorMap map_k, map_v, map_q[2];
     CUtensorMap map_khalf;   // K with 64-row boxes (v7: each CTA of a pair keeps 64 keys of a tile)
     int n = 0;
@@ -1396,18 +1401,41 @@ void umma_plan_destroy(UmmaPlan* plan)
     delete plan;
 }
 
-bool attn_umma_supported(int dk, int dv) { return dk == HEAD && dv == HEAD; }
+bool attn_umma_supported(int dk, int dv, int hl) { return attn_umma_general_shape(dk, dv, hl, nullptr); }
 
-sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv_bfloat16* V, int n, int dk, int dv)
+static bool force_general()
 {
-    if (!attn_umma_supported(dk, dv)) {
-        set_error("bf16 tensor-core kernel supports dk == dv == 128 (got dk=%d dv=%d)", dk, dv);
+    const char* e = getenv("SDPA_UMMA_GENERAL");   // developer knob: run dk = dv = 128 bf16 on the general kernel too
+    return e && *e == '1';
+}
+
+sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv_bfloat16* V, int n, int dk, int dv, int hl,
+                              size_t k_lo_off, size_t v_lo_off)
+{
+    if (!attn_umma_supported(dk, dv, hl)) {
+        set_error("tensor-core kernel: dk, dv must be multiples of 8 up to 256 (split precision: up to 128); got dk=%d dv=%d", dk, dv);
         return SDPA_ERR_UNSUPPORTED;
     }
-    if (plan->kv_bound && plan->k_base == K && plan->v_base == V && plan->n == n) return SDPA_OK;   // descriptors still valid
-    SDPA_TRY(encode_map(&plan->map_k, K, n));
-    SDPA_TRY(encode_map(&plan->map_v, V, n));
-    SDPA_TRY(encode_map(&plan->map_khalf, K, n, 64));
+    if (plan->kv_bound && plan->k_base == K && plan->v_base == V && plan->n == n && plan->dk == dk && plan->dv == dv && plan->hl == hl)
+        return SDPA_OK;   // descriptors still valid
+    if (plan->dk != dk || plan->hl != hl) plan->q_bound[0] = plan->q_bound[1] = false;
+    plan->dk = dk;
+    plan->dv = dv;
+    plan->hl = hl;
+    plan->general = !(dk == HEAD && dv == HEAD && hl == 1) || force_general();
+    if (plan->general) {
+        for (int slot = 0; slot < 2; ++slot) {
+            SDPA_TRY(encode_map(&plan->gmaps[slot][2], K, n, 64, dk));
+            SDPA_TRY(encode_map(&plan->gmaps[slot][3], K + (hl == 2 ? k_lo_off : 0), n, 64, dk));
+            SDPA_TRY(encode_map(&plan->gmaps[slot][4], V, n, TILE, dv));
+            SDPA_TRY(encode_map(&plan->gmaps[slot][5], V + (hl == 2 ? v_lo_off : 0), n, TILE, dv));
+        }
+    }
+    if (dk == HEAD && dv == HEAD && hl == 1) {
+        SDPA_TRY(encode_map(&plan->map_k, K, n));
+        SDPA_TRY(encode_map(&plan->map_v, V, n));
+        SDPA_TRY(encode_map(&plan->map_khalf, K, n, 64));
+    }
     plan->k_base = K;
     plan->v_base = V;
     plan->n = n;
@@ -1415,14 +1443,18 @@ sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv
     return SDPA_OK;
 }
 
-sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, int rows_capacity, int dk)
+sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, int rows_capacity, int dk, int hl, size_t q_lo_off)
 {
-    if (slot < 0 || slot > 1 || dk != HEAD) {
-        set_error("umma_plan_bind_q: bad slot/dk");
+    if (slot < 0 || slot > 1 || dk != plan->dk || hl != plan->hl) {
+        set_error("umma_plan_bind_q: bad slot, or dk / precision differ from the bound K/V shard");
         return SDPA_ERR_INVALID;
     }
     if (plan->q_bound[slot] && plan->q_base[slot] == Q && plan->q_rows[slot] == rows_capacity) return SDPA_OK;
-    SDPA_TRY(encode_map(&plan->map_q[slot], Q, rows_capacity));
+    if (plan->general) {
+        SDPA_TRY(encode_map(&plan->gmaps[slot][0], Q, rows_capacity, TILE, dk));
+        SDPA_TRY(encode_map(&plan->gmaps[slot][1], Q + (hl == 2 ? q_lo_off : 0), rows_capacity, TILE, dk));
+    }
+    if (dk == HEAD && plan->dv == HEAD && hl == 1) SDPA_TRY(encode_map(&plan->map_q[slot], Q, rows_capacity));
     plan->q_bound[slot] = true;
     plan->q_base[slot] = Q;
     plan->q_rows[slot] = rows_capacity;
@@ -1521,6 +1553,37 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     if (out64 != nullptr && splits != 1) {
         set_error("direct fp64 output requires splits == 1");
         return SDPA_ERR_INVALID;
+    }
+    if (plan->general) {
+        // every shape but dk = dv = 128 bf16: the general kernel, then its exact twin (leaves at once unless the guard fired)
+        if (!plan->guard) {
+            SDPA_CUDA_TRY(cudaMalloc(&plan->guard, sizeof(unsigned int)));
+            SDPA_CUDA_TRY(cudaMemset(plan->guard, 0, sizeof(unsigned int)));
+        }
+        GeneralLaunch L;
+        L.rows = rows;
+        L.n = plan->n;
+        L.dk = plan->dk;
+        L.dv = plan->dv;
+        L.hl = plan->hl;
+        L.splits = splits;
+        L.part = part;
+        L.out64 = out64;
+        L.guard = plan->guard;
+        L.epoch = ++plan->epoch;
+        if (plan->epoch == 0) L.epoch = ++plan->epoch;   // 0 is the "never raised" value
+        L.maps = plan->gmaps[q_slot];
+        plan->last_v8 = false;
+        const char* env_safe = getenv("SDPA_UMMA_SAFE");
+        if (env_safe && *env_safe == '1') {   // developer knob: only the exact variant, guard forced
+            SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
+            L.epoch = 0xffffffffu;
+        } else {
+            L.exact = false;
+            SDPA_TRY(launch_attn_umma_general(L, stream));
+        }
+        L.exact = true;
+        return launch_attn_umma_general(L, stream);
     }
     const size_t smem_bytes = sizeof(SharedStorage) + 1024;
     int dev = 0;

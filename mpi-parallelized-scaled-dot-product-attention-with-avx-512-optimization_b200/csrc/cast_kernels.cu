@@ -129,44 +129,101 @@ cvt_d2bf16_scalar_kernel(__nv_bfloat16* __restrict__ dst, const double* __restri
         dst[i] = __float2bfloat16_rn(__double2float_rn(src[i]));
 }
 
+// fp64 -> (hi, lo) bf16 pair of the split precision: x32 = fp32(x) (the reference's own cvt_d2f, mpi.c:31-64), hi = bf16(x32),
+// lo = bf16(x32 - hi): hi + lo carries 16 mantissa bits of x32.  12 B per element like d2f (8 read, 2 + 2 written).
+__device__ __forceinline__ void split_bf16x2(double2 v, uint32_t& hi, uint32_t& lo)
+{
+    const float a = __double2float_rn(v.x), b = __double2float_rn(v.y);
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(kCastThreads)
+cvt_d2bf16x2_vec_kernel(uint32_t* __restrict__ dst_hi, uint32_t* __restrict__ dst_lo, const double2* __restrict__ src, size_t units)
+{
+    const size_t total = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (kUnroll - 1) * total < units; i += kUnroll * total) {
+        double2 v[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream_f64x2(src + i + u * total);
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            uint32_t hi, lo;
+            split_bf16x2(v[u], hi, lo);
+            dst_hi[i + u * total] = hi;
+            dst_lo[i + u * total] = lo;
+        }
+    }
+    for (; i < units; i += total) {
+        uint32_t hi, lo;
+        split_bf16x2(ld_stream_f64x2(src + i), hi, lo);
+        dst_hi[i] = hi;
+        dst_lo[i] = lo;
+    }
+}
+
+__global__ void __launch_bounds__(kCastThreads)
+cvt_d2bf16x2_scalar_kernel(__nv_bfloat16* __restrict__ dst_hi, __nv_bfloat16* __restrict__ dst_lo, const double* __restrict__ src,
+                           size_t begin, size_t count)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float a = __double2float_rn(src[i]);
+        const __nv_bfloat16 h = __float2bfloat16_rn(a);
+        dst_hi[i] = h;
+        dst_lo[i] = __float2bfloat16_rn(a - __bfloat162float(h));
+    }
+}
+
 // Several fp64 -> compute-precision casts in ONE launch (the K shard, the V shard and the first Q batch of a
 // device-resident call): the segments form one virtual array of 2-element units, so the grid-stride loop has a
 // single tail instead of one per operand and two launch gaps disappear from the step.
-template <bool BF16>
+// MODE 0: fp32, 1: bf16, 2: bf16 hi/lo split (lo array cb.lo_off[seg] 2-element units behind the hi array)
+template <int MODE>
 __global__ void __launch_bounds__(kCastThreads) cvt_in_batch_kernel(CastBatch cb)
 {
     const size_t u0 = cb.units[0], u01 = u0 + cb.units[1], all = u01 + cb.units[2];
     const size_t total = (size_t)gridDim.x * blockDim.x;
-    auto locate = [&](size_t g, const double2*& src, void*& dst, size_t& off) {
+    auto locate = [&](size_t g, const double2*& src, void*& dst, size_t& off, size_t& lo) {
         const int seg = g < u0 ? 0 : (g < u01 ? 1 : 2);
         off = g - (seg == 0 ? 0 : (seg == 1 ? u0 : u01));
         src = reinterpret_cast<const double2*>(cb.src[seg]);
         dst = cb.dst[seg];
+        lo = cb.lo_off[seg];
     };
-    auto store = [&](void* dst, size_t off, double2 v) {
-        if (BF16) reinterpret_cast<uint32_t*>(dst)[off] = pack_bf16x2(__double2float_rn(v.x), __double2float_rn(v.y));
-        else reinterpret_cast<float2*>(dst)[off] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+    auto store = [&](void* dst, size_t off, size_t lo, double2 v) {
+        if (MODE == 2) {
+            uint32_t h, l;
+            split_bf16x2(v, h, l);
+            reinterpret_cast<uint32_t*>(dst)[off] = h;
+            reinterpret_cast<uint32_t*>(dst)[off + lo] = l;
+        } else if (MODE == 1) {
+            reinterpret_cast<uint32_t*>(dst)[off] = pack_bf16x2(__double2float_rn(v.x), __double2float_rn(v.y));
+        } else {
+            reinterpret_cast<float2*>(dst)[off] = make_float2(__double2float_rn(v.x), __double2float_rn(v.y));
+        }
     };
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + (kUnroll - 1) * total < all; i += kUnroll * total) {
         double2 v[kUnroll];
         void* d[kUnroll];
-        size_t off[kUnroll];
+        size_t off[kUnroll], lo[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const double2* src;
-            locate(i + u * total, src, d[u], off[u]);
+            locate(i + u * total, src, d[u], off[u], lo[u]);
             v[u] = ld_stream_f64x2(src + off[u]);
         }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) store(d[u], off[u], v[u]);
+        for (int u = 0; u < kUnroll; ++u) store(d[u], off[u], lo[u], v[u]);
     }
     for (; i < all; i += total) {
         const double2* src;
         void* d;
-        size_t off;
-        locate(i, src, d, off);
-        store(d, off, ld_stream_f64x2(src + off));
+        size_t off, lo;
+        locate(i, src, d, off, lo);
+        store(d, off, lo, ld_stream_f64x2(src + off));
     }
 }
 
@@ -240,10 +297,29 @@ sdpa_status launch_cvt_d2bf16(__nv_bfloat16* dst, const double* src, size_t coun
     return SDPA_OK;
 }
 
+sdpa_status launch_cvt_d2bf16x2(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const double* src, size_t count, cudaStream_t stream)
+{
+    if (count == 0) return SDPA_OK;
+    size_t done = 0;
+    if (aligned(dst_hi, 4) && aligned(dst_lo, 4) && aligned(src, 16) && count >= 2) {
+        const size_t units = count / 2;
+        cvt_d2bf16x2_vec_kernel<<<cast_grid(units / kUnroll), kCastThreads, 0, stream>>>(
+            reinterpret_cast<uint32_t*>(dst_hi), reinterpret_cast<uint32_t*>(dst_lo), reinterpret_cast<const double2*>(src), units);
+        count_launch();
+        done = units * 2;
+    }
+    if (done < count) {
+        cvt_d2bf16x2_scalar_kernel<<<cast_grid(count - done), kCastThreads, 0, stream>>>(dst_hi, dst_lo, src, done, count);
+        count_launch();
+    }
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
 // Up to three operands in one launch; falls back to one launch per operand when a pointer is not 16-byte aligned
 // or a count is odd (the batched kernel moves 2-element units only).
-sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, int nseg,
-                                cudaStream_t stream)
+sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, const size_t* lo_off,
+                                int nseg, cudaStream_t stream)
 {
     if (nseg < 0 || nseg > 3) {
         set_error("launch_cvt_in_batch: 0..3 segments");
@@ -256,26 +332,33 @@ sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const*
         cb.dst[k] = nullptr;
         cb.src[k] = nullptr;
         cb.units[k] = 0;
+        cb.lo_off[k] = 0;
     }
+    const bool split = prec == SDPA_PREC_BF16X3;
     for (int k = 0; k < nseg; ++k) {
         if (count[k] == 0) continue;
-        vec_ok = vec_ok && (count[k] % 2 == 0) && aligned(src[k], 16) && aligned(dst[k], 8);
+        vec_ok = vec_ok && (count[k] % 2 == 0) && aligned(src[k], 16) && aligned(dst[k], 8) && (!split || (lo_off && lo_off[k] % 2 == 0));
         cb.dst[k] = dst[k];
         cb.src[k] = src[k];
         cb.units[k] = count[k] / 2;
+        cb.lo_off[k] = split && lo_off ? lo_off[k] / 2 : 0;
         units_total += cb.units[k];
     }
     if (units_total == 0 && vec_ok) return SDPA_OK;
     if (!vec_ok) {
         for (int k = 0; k < nseg; ++k) {
-            if (prec == SDPA_PREC_BF16) SDPA_TRY(launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst[k]), src[k], count[k], stream));
+            if (split) {
+                __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dst[k]);
+                SDPA_TRY(launch_cvt_d2bf16x2(hi, hi + (lo_off ? lo_off[k] : 0), src[k], count[k], stream));
+            } else if (prec == SDPA_PREC_BF16) SDPA_TRY(launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst[k]), src[k], count[k], stream));
             else SDPA_TRY(launch_cvt_d2f(reinterpret_cast<float*>(dst[k]), src[k], count[k], stream));
         }
         return SDPA_OK;
     }
     const int grid = cast_grid(units_total / kUnroll);
-    if (prec == SDPA_PREC_BF16) cvt_in_batch_kernel<true><<<grid, kCastThreads, 0, stream>>>(cb);
-    else cvt_in_batch_kernel<false><<<grid, kCastThreads, 0, stream>>>(cb);
+    if (split) cvt_in_batch_kernel<2><<<grid, kCastThreads, 0, stream>>>(cb);
+    else if (prec == SDPA_PREC_BF16) cvt_in_batch_kernel<1><<<grid, kCastThreads, 0, stream>>>(cb);
+    else cvt_in_batch_kernel<0><<<grid, kCastThreads, 0, stream>>>(cb);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

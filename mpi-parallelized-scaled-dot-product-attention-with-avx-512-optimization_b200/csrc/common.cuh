@@ -57,13 +57,17 @@ struct Partials {
 sdpa_status launch_cvt_d2f(float* dst, const double* src, size_t count, cudaStream_t stream);
 sdpa_status launch_cvt_f2d(double* dst, const float* src, size_t count, cudaStream_t stream);
 sdpa_status launch_cvt_d2bf16(__nv_bfloat16* dst, const double* src, size_t count, cudaStream_t stream);
+// fp64 -> (hi, lo) bf16 pair of the split precision SDPA_PREC_BF16X3: hi = bf16(fp32(x)), lo = bf16(fp32(x) - hi)
+sdpa_status launch_cvt_d2bf16x2(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, const double* src, size_t count, cudaStream_t stream);
 struct CastBatch {
     void* dst[3];
     const double* src[3];
     size_t units[3];   // 2-element units per segment
+    size_t lo_off[3];  // split precision: distance from the hi to the lo array, in 2-element units
 };
-sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, int nseg,
-                                cudaStream_t stream);
+// lo_off (elements, per segment) is read for SDPA_PREC_BF16X3 only and may be NULL otherwise.
+sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, const size_t* lo_off,
+                                int nseg, cudaStream_t stream);
 
 // fp32 CUDA-core fused attention.  Q [rows x dk], K [n x dk], V [n x dv] fp32 row-major.
 // If out64 != nullptr (requires splits == 1) the normalised result is written as fp64
@@ -73,16 +77,19 @@ sdpa_status launch_attn_f32(const float* Q, const float* K, const float* V, int 
 bool attn_f32_supported(int dk, int dv);
 int attn_f32_pick_splits(int rows, int n, int sm_count);
 
-// bf16 tcgen05 fused attention (attn_umma_bf16.cu).  Q, K [.. x dk], V [n x dv] bf16 row-major.
+// tcgen05 fused attention (attn_umma_bf16.cu: dk = dv = 128 bf16; attn_umma_general.cu: every other shape and the
+// split precision).  Q, K [.. x dk], V [n x dv] bf16 row-major.
 struct UmmaPlan;  // holds the TMA descriptors for one (Q buffer, K/V shard) binding
 sdpa_status umma_plan_create(UmmaPlan** plan);
 void umma_plan_destroy(UmmaPlan* plan);
+// hl = 1: bf16 operands; hl = 2: hi/lo split (the lo array of an operand starts *_lo_off ELEMENTS behind its hi array).
 sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv_bfloat16* V, int n,
-                              int dk, int dv);
-sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, int rows_capacity, int dk);
+                              int dk, int dv, int hl, size_t k_lo_off, size_t v_lo_off);
+sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, int rows_capacity, int dk, int hl,
+                             size_t q_lo_off);
 sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part,
                              double* out64, int sm_count, cudaStream_t stream);
-bool attn_umma_supported(int dk, int dv);
+bool attn_umma_supported(int dk, int dv, int hl);
 int attn_umma_pick_splits(int rows, int n, int sm_count);
 // Persistent fused kernel (EXPERIMENTAL, SDPA_UMMA_V8=1): partial slots per row block for (rows, n), 0 = not applicable.
 struct WorkMap;

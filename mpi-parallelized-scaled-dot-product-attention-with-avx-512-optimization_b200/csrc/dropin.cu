@@ -7,6 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <string>
 
 #include <vector>
 
@@ -41,12 +44,35 @@ int env_precision()
     if (!v || !*v || !strcmp(v, "auto")) return SDPA_PREC_AUTO;
     if (!strcmp(v, "f32") || !strcmp(v, "fp32")) return SDPA_PREC_F32;
     if (!strcmp(v, "bf16")) return SDPA_PREC_BF16;
-    fprintf(stderr, "sdpa_b200: SDPA_PRECISION must be auto|f32|bf16 (got %s)\n", v);
+    if (!strcmp(v, "bf16x3") || !strcmp(v, "f32x3")) return SDPA_PREC_BF16X3;
+    fprintf(stderr, "sdpa_b200: SDPA_PRECISION must be auto|f32|bf16|bf16x3 (got %s)\n", v);
     exit(1);
 }
 
-// File rendezvous for the ncclUniqueId when the launcher did not call sdpa_set_bootstrap_id():
-// rank 0 writes <file>.tmp then renames it; the others poll.
+// File rendezvous for the ncclUniqueId when the launcher did not call sdpa_set_bootstrap_id().  Record = magic, a 64-bit
+// launch nonce, the 128-byte id.  Rank 0 removes whatever a previous run left at the path, writes <file>.tmp and renames it
+// into place; the others poll and accept a record only if (a) its nonce equals theirs -- the nonce is a hash of the first of
+// SDPA_NCCL_ID_NONCE / the launcher's job identifiers (PMIX_NAMESPACE, OMPI_MCA_ess_base_jobid, SLURM_JOB_ID + SLURM_STEP_ID,
+// PMI_JOBID) found in the environment, identical on every rank of one launch -- and (b) the file is not older than this
+// process (minus a slack for launch skew), which also covers launchers that export none of those variables.  Rank 0 deletes
+// the file again once its communicator exists (every rank has read the id by then).
+const time_t g_load_time = time(nullptr);
+const char kIdMagic[8] = {'S', 'D', 'P', 'A', 'I', 'D', '0', '2'};
+
+uint64_t launch_nonce()
+{
+    const char* names[] = {"SDPA_NCCL_ID_NONCE", "PMIX_NAMESPACE", "OMPI_MCA_ess_base_jobid", "SLURM_JOB_ID", "SLURM_STEP_ID", "PMI_JOBID"};
+    uint64_t h = 1469598103934665603ull;   // FNV-1a over name=value of every identifier present
+    for (const char* nm : names) {
+        const char* v = getenv(nm);
+        if (!v || !*v) continue;
+        for (const char* p = nm; *p; ++p) h = (h ^ (unsigned char)*p) * 1099511628211ull;
+        for (const char* p = v; *p; ++p) h = (h ^ (unsigned char)*p) * 1099511628211ull;
+        if (nm == names[0]) break;   // an explicit nonce overrides the launcher's variables
+    }
+    return h;
+}
+
 void bootstrap_id_via_file(int rank, unsigned char* id)
 {
     const char* path = getenv("SDPA_NCCL_ID_FILE");
@@ -54,27 +80,41 @@ void bootstrap_id_via_file(int rank, unsigned char* id)
         fprintf(stderr, "sdpa_b200: mpi_size > 1 needs sdpa_set_bootstrap_id() or env SDPA_NCCL_ID_FILE\n");
         exit(1);
     }
+    const uint64_t nonce = launch_nonce();
+    unsigned char rec[8 + 8 + 128];
     if (rank == 0) {
         if (sdpa_get_unique_id(id) != SDPA_OK) die("ncclGetUniqueId");
+        unlink(path);   // a record left by an earlier run must never be readable while this run's is being written
+        memcpy(rec, kIdMagic, 8);
+        memcpy(rec + 8, &nonce, 8);
+        memcpy(rec + 16, id, 128);
         std::string tmp = std::string(path) + ".tmp";
         FILE* f = fopen(tmp.c_str(), "wb");
-        if (!f || fwrite(id, 1, 128, f) != 128) {
+        if (!f || fwrite(rec, 1, sizeof(rec), f) != sizeof(rec)) {
             fprintf(stderr, "sdpa_b200: cannot write %s\n", tmp.c_str());
             exit(1);
         }
         fclose(f);
         rename(tmp.c_str(), path);
     } else {
-        for (int tries = 0; tries < 60000; ++tries) {
+        const int slack_s = env_int("SDPA_NCCL_ID_MAX_SKEW_S", 30);
+        for (int tries = 0; tries < 120000; ++tries) {
+            struct stat sb;
             FILE* f = fopen(path, "rb");
             if (f) {
-                size_t got = fread(id, 1, 128, f);
+                const size_t got = fread(rec, 1, sizeof(rec), f);
+                const bool fresh = fstat(fileno(f), &sb) == 0 && sb.st_mtime + slack_s >= g_load_time;
                 fclose(f);
-                if (got == 128) return;
+                uint64_t theirs = 0;
+                memcpy(&theirs, rec + 8, 8);
+                if (got == sizeof(rec) && !memcmp(rec, kIdMagic, 8) && theirs == nonce && fresh) {
+                    memcpy(id, rec + 16, 128);
+                    return;
+                }
             }
             usleep(1000);
         }
-        fprintf(stderr, "sdpa_b200: timed out waiting for %s\n", path);
+        fprintf(stderr, "sdpa_b200: timed out waiting for a fresh id record in %s (stale file of another launch?)\n", path);
         exit(1);
     }
 }
@@ -119,6 +159,10 @@ sdpa_ctx* get_ctx(int mpi_rank, int mpi_size)
     }
     sdpa_ctx* ctx = nullptr;
     if (sdpa_ctx_create(&ctx, &cfg, id) != SDPA_OK) die("context creation");
+    if (mpi_size > 1 && mpi_rank == 0 && !g_boot_id_set) {   // every rank has joined the communicator: the record is spent
+        const char* path = getenv("SDPA_NCCL_ID_FILE");
+        if (path && *path) unlink(path);
+    }
     g_cached.ctx = ctx;
     g_cached.cfg = cfg;
     g_cached.world = cfg.world_size;

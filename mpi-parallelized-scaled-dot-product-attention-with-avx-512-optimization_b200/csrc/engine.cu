@@ -140,6 +140,7 @@ struct Shard {
 
     // resident shard in compute precision
     DevBuf Kc, Vc;
+    size_t k_lo_off = 0, v_lo_off = 0, q_lo_off = 0;   // split precision: elements from an operand's hi array to its lo array
     int n_local = 0;
     // staging for fp64 uploads of K/V (two chunks in flight)
     DevBuf kv_stage[2];
@@ -298,19 +299,49 @@ static sdpa_status fold_timings(Shard& s)
     return SDPA_OK;
 }
 
+// Resident storage per element: fp32 4 B, bf16 2 B, split precision 2 + 2 B (a hi array and, lo_off elements behind it, a lo array).
 static size_t elem_size(int prec) { return prec == SDPA_PREC_BF16 ? 2 : 4; }
-
-static sdpa_status cast_in(int prec, void* dst, const double* src, size_t count, cudaStream_t st)
+static size_t unit_size(int prec) { return prec == SDPA_PREC_F32 ? 4 : 2; }   // bytes per element of ONE array
+static bool is_umma(int prec) { return prec == SDPA_PREC_BF16 || prec == SDPA_PREC_BF16X3; }
+static int prec_hl(int prec) { return prec == SDPA_PREC_BF16X3 ? 2 : 1; }
+static const char* kernel_name(int prec, int dk, int dv)
 {
-    if (prec == SDPA_PREC_BF16) return launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst), src, count, st);
-    return launch_cvt_d2f(reinterpret_cast<float*>(dst), src, count, st);
+    if (prec == SDPA_PREC_BF16X3) return "bf16x3_umma";
+    if (prec == SDPA_PREC_BF16) return (dk == 128 && dv == 128) ? "bf16_umma" : "bf16_umma_general";
+    return "f32_simt";
 }
 
+// Cast `count` fp64 elements into the operand that starts at `dst` (element offset `at`); lo_off: split precision only.
+static sdpa_status cast_in(int prec, void* dst, size_t lo_off, size_t at, const double* src, size_t count, cudaStream_t st)
+{
+    if (prec == SDPA_PREC_BF16X3) {
+        __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(dst) + at;
+        return launch_cvt_d2bf16x2(hi, hi + lo_off, src, count, st);
+    }
+    if (prec == SDPA_PREC_BF16) return launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst) + at, src, count, st);
+    return launch_cvt_d2f(reinterpret_cast<float*>(dst) + at, src, count, st);
+}
+
+// AUTO keeps the reference's accuracy class (fp32, attention-mpi.c:168-189): the split-precision tensor-core kernel where
+// the shape allows it, else the fp32 CUDA-core kernel.  Plain bf16 is opt-in only: its operand rounding can move peaky
+// scores beyond the reference's own 0.02 acceptance gate (attention-mpi.c:476).
 static int resolve_precision(int requested, int dk, int dv)
 {
-    if (requested == SDPA_PREC_BF16) return SDPA_PREC_BF16;
-    if (requested == SDPA_PREC_F32) return SDPA_PREC_F32;
-    return attn_umma_supported(dk, dv) ? SDPA_PREC_BF16 : SDPA_PREC_F32;
+    if (requested == SDPA_PREC_BF16 || requested == SDPA_PREC_F32 || requested == SDPA_PREC_BF16X3) return requested;
+    return attn_umma_supported(dk, dv, 2) ? SDPA_PREC_BF16X3 : SDPA_PREC_F32;
+}
+static sdpa_status check_precision(int prec, int dk, int dv)
+{
+    if (is_umma(prec) && !attn_umma_supported(dk, dv, prec_hl(prec))) {
+        set_error("%s tensor-core kernel: dk and dv must be multiples of 8 up to %d (got dk=%d dv=%d)",
+                  prec == SDPA_PREC_BF16X3 ? "bf16x3" : "bf16", prec == SDPA_PREC_BF16X3 ? 128 : 256, dk, dv);
+        return SDPA_ERR_UNSUPPORTED;
+    }
+    if (prec == SDPA_PREC_F32 && !attn_f32_supported(dk, dv)) {
+        set_error("fp32 kernel supports 1 <= dk, dv <= 256 (got dk=%d dv=%d)", dk, dv);
+        return SDPA_ERR_UNSUPPORTED;
+    }
+    return SDPA_OK;
 }
 
 static sdpa_status shard_init(Shard& s)
@@ -365,11 +396,10 @@ static void shard_destroy(Shard& s, const NcclApi* api)
 static const size_t kStageElems = (size_t)4 << 20;  // 32 MiB of fp64 per chunk
 
 // Upload (or read in place) one operand of the shard and cast it into `dst`.
-static sdpa_status upload_cast(Shard& s, int prec, void* dst, const double* src, size_t count, bool src_on_device)
+static sdpa_status upload_cast(Shard& s, int prec, void* dst, size_t lo_off, const double* src, size_t count, bool src_on_device)
 {
-    const size_t esz = elem_size(prec);
     if (src_on_device) {
-        SDPA_TRY(cast_in(prec, dst, src, count, s.s_compute));
+        SDPA_TRY(cast_in(prec, dst, lo_off, 0, src, count, s.s_compute));
         return SDPA_OK;
     }
     size_t done = 0;
@@ -382,7 +412,7 @@ static sdpa_status upload_cast(Shard& s, int prec, void* dst, const double* src,
         SDPA_TRY(h2d_any(s.kv_stage[b].p, src + done, len * sizeof(double), s.s_in));   // pinned: direct; pageable: staged
         SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_ready[b], s.s_in));
         SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_stage_ready[b], 0));
-        SDPA_TRY(cast_in(prec, (char*)dst + done * esz, s.kv_stage[b].as<double>(), len, s.s_compute));
+        SDPA_TRY(cast_in(prec, dst, lo_off, done, s.kv_stage[b].as<double>(), len, s.s_compute));
         SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_free[b], s.s_compute));
         done += len;
         ++c;
@@ -398,14 +428,7 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
         return SDPA_ERR_INVALID;
     }
     const int prec = resolve_precision(ctx->cfg.precision, dk, dv);
-    if (prec == SDPA_PREC_BF16 && !attn_umma_supported(dk, dv)) {
-        set_error("bf16 tensor-core kernel supports dk == dv in {64,128} (got dk=%d dv=%d)", dk, dv);
-        return SDPA_ERR_UNSUPPORTED;
-    }
-    if (prec == SDPA_PREC_F32 && !attn_f32_supported(dk, dv)) {
-        set_error("fp32 kernel supports 1 <= dk, dv <= 256 (got dk=%d dv=%d)", dk, dv);
-        return SDPA_ERR_UNSUPPORTED;
-    }
+    SDPA_TRY(check_precision(prec, dk, dv));
     ctx->dk = dk;
     ctx->dv = dv;
     ctx->prec = prec;
@@ -422,6 +445,8 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
         // +128 rows of slack so TMA boxes / vector loads past the last row stay in bounds
         SDPA_TRY(s.Kc.reserve(((size_t)s.n_local + 128) * dk * esz));
         SDPA_TRY(s.Vc.reserve(((size_t)s.n_local + 128) * dv * esz));
+        s.k_lo_off = ((size_t)s.n_local + 128) * dk;
+        s.v_lo_off = ((size_t)s.n_local + 128) * dv;
         s.npend = 0;
         if (s.n_local > 0 && on_device && defer_casts) {
             // sdpa_attention_device_full: the sources stay valid for the whole call, so the casts ride with Q's
@@ -429,12 +454,13 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
             s.pend_dst[1] = s.Vc.p, s.pend_src[1] = V_shards[i], s.pend_cnt[1] = (size_t)s.n_local * dv;
             s.npend = 2;
         } else if (s.n_local > 0) {
-            SDPA_TRY(upload_cast(s, prec, s.Kc.p, K_shards[i], (size_t)s.n_local * dk, on_device));
-            SDPA_TRY(upload_cast(s, prec, s.Vc.p, V_shards[i], (size_t)s.n_local * dv, on_device));
+            SDPA_TRY(upload_cast(s, prec, s.Kc.p, s.k_lo_off, K_shards[i], (size_t)s.n_local * dk, on_device));
+            SDPA_TRY(upload_cast(s, prec, s.Vc.p, s.v_lo_off, V_shards[i], (size_t)s.n_local * dv, on_device));
         }
-        if (prec == SDPA_PREC_BF16) {
+        if (is_umma(prec)) {
             if (!s.plan) SDPA_TRY(umma_plan_create(&s.plan));
-            SDPA_TRY(umma_plan_bind_kv(s.plan, s.Kc.as<__nv_bfloat16>(), s.Vc.as<__nv_bfloat16>(), s.n_local, dk, dv));
+            SDPA_TRY(umma_plan_bind_kv(s.plan, s.Kc.as<__nv_bfloat16>(), s.Vc.as<__nv_bfloat16>(), s.n_local, dk, dv, prec_hl(prec),
+                                       s.k_lo_off, s.v_lo_off));
         }
     }
     // Host sources: block until the uploads have been consumed (the caller may reuse its arrays).
@@ -492,7 +518,7 @@ static sdpa_status reserve_batch_buffers(sdpa_ctx* ctx, Shard& s, int B, int spl
 // The fused kernel for one batch on one shard: fills the split partials, or writes fp64 directly.
 static sdpa_status run_fused(sdpa_ctx* ctx, Shard& s, int slot, int rows, int splits, Partials part, double* direct_out)
 {
-    if (ctx->prec == SDPA_PREC_BF16) {
+    if (is_umma(ctx->prec)) {
         return launch_attn_umma(s.plan, slot, rows, splits, part, direct_out, s.sm_count, s.s_compute);
     }
     return launch_attn_f32(s.qc[slot].as<float>(), s.Kc.as<float>(), s.Vc.as<float>(), rows, s.n_local, ctx->dk,
@@ -670,14 +696,15 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         api = nccl_api();
         if (!api) return SDPA_ERR_NCCL;
     }
-    ctx->last_kernel = ctx->prec == SDPA_PREC_BF16 ? "bf16_umma" : "f32_simt";
+    ctx->last_kernel = kernel_name(ctx->prec, dk, dv);
     for (float& t : ctx->last_timing) t = 0.f;
     if (m == 0) {
         ctx->last_timing_valid = true;   // nothing ran: all-zero stage times
         for (Shard& s : ctx->shards) {   // K/V casts deferred by sdpa_attention_device_full still have to happen
             if (s.npend == 0) continue;
             SDPA_CUDA_TRY(cudaSetDevice(s.dev));
-            SDPA_TRY(launch_cvt_in_batch(ctx->prec, s.pend_dst, s.pend_src, s.pend_cnt, 2, s.s_compute));
+            const size_t lo[2] = {s.k_lo_off, s.v_lo_off};
+            SDPA_TRY(launch_cvt_in_batch(ctx->prec, s.pend_dst, s.pend_src, s.pend_cnt, lo, 2, s.s_compute));
             s.npend = 0;
         }
         return SDPA_OK;
@@ -693,21 +720,21 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     if (splits <= 0) {
         int nmax = 0;
         for (Shard& s : ctx->shards) nmax = std::max(nmax, s.n_local);
-        splits = ctx->prec == SDPA_PREC_BF16 ? attn_umma_pick_splits(B, nmax, ctx->shards[0].sm_count)
-                                             : attn_f32_pick_splits(B, nmax, ctx->shards[0].sm_count);
+        splits = is_umma(ctx->prec) ? attn_umma_pick_splits(B, nmax, ctx->shards[0].sm_count)
+                                    : attn_f32_pick_splits(B, nmax, ctx->shards[0].sm_count);
     }
     splits = std::max(1, std::min(splits, 64));
     // EXPERIMENTAL (SDPA_UMMA_V8=1, single GPU): the persistent fused kernel cuts every row block into pieces; its piece
     // count replaces the split count and the merge reads pieces per row block (launch_merge_pieces).
     bool by_pieces = false;
-    if (world == 1 && ctx->prec == SDPA_PREC_BF16 && ctx->cfg.kv_splits <= 0 && num_iter == 1) {
+    if (world == 1 && ctx->prec == SDPA_PREC_BF16 && dk == 128 && dv == 128 && ctx->cfg.kv_splits <= 0 && num_iter == 1) {
         const int pieces = attn_umma_v8_pieces(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
         if (pieces > 1) {
             splits = pieces;
             by_pieces = true;
         }
     }
-    if (ctx->prec == SDPA_PREC_BF16)
+    if (is_umma(ctx->prec))
         for (Shard& s : ctx->shards)
             if (s.plan) umma_plan_allow_v8(s.plan, by_pieces);
 
@@ -726,9 +753,10 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         }
         for (int w = 0; w < 4; ++w) s.tpair_last[w] = s.tpair[w].size();
         compute_stream_touched(s);   // whatever ran before this call is not part of it
-        if (ctx->prec == SDPA_PREC_BF16)
+        s.q_lo_off = (size_t)(((B + 127) & ~127) + 128) * dk;
+        if (is_umma(ctx->prec))
             for (int b = 0; b < 2; ++b)
-                SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk));
+                SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk, prec_hl(ctx->prec), s.q_lo_off));
         SDPA_TRY(time_begin(s, 3, s.s_compute));
         // the side streams this call uses start after the begin mark, so that "total" brackets everything
         cudaEvent_t begun = s.marks[s.tpair[3].back()];
@@ -776,16 +804,22 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 void* cd[3] = {s.pend_dst[0], s.pend_dst[1], s.qc[b].p};
                 const double* cs[3] = {s.pend_src[0], s.pend_src[1], q_src_dev};
                 const size_t cc[3] = {s.pend_cnt[0], s.pend_cnt[1], (size_t)bs * dk};
-                SDPA_TRY(launch_cvt_in_batch(ctx->prec, cd, cs, cc, have_q ? 3 : 2, s.s_compute));
+                const size_t lo[3] = {s.k_lo_off, s.v_lo_off, s.q_lo_off};
+                SDPA_TRY(launch_cvt_in_batch(ctx->prec, cd, cs, cc, lo, have_q ? 3 : 2, s.s_compute));
                 s.npend = 0;
                 ++all_launches;
             } else if (have_q) {
-                SDPA_TRY(cast_in(ctx->prec, s.qc[b].p, q_src_dev, (size_t)bs * dk, s.s_compute));
+                SDPA_TRY(cast_in(ctx->prec, s.qc[b].p, s.q_lo_off, 0, q_src_dev, (size_t)bs * dk, s.s_compute));
                 ++all_launches;
             }
-            if (q_from_root)  // the Q batch travels in compute precision (mpi.c:305,327: Ibcast of the fp32 batch)
-                SDPA_NCCL_TRY(api->Broadcast(s.qc[b].p, s.qc[b].p, (size_t)bs * dk * elem_size(ctx->prec), ncclUint8, 0,
+            if (q_from_root) {  // the Q batch travels in compute precision (mpi.c:305,327: Ibcast of the fp32 batch)
+                SDPA_NCCL_TRY(api->Broadcast(s.qc[b].p, s.qc[b].p, (size_t)bs * dk * unit_size(ctx->prec), ncclUint8, 0,
                                              s.comm, s.s_compute));
+                if (ctx->prec == SDPA_PREC_BF16X3) {   // ... and the lo half of the split operand
+                    void* lo = s.qc[b].as<__nv_bfloat16>() + s.q_lo_off;
+                    SDPA_NCCL_TRY(api->Broadcast(lo, lo, (size_t)bs * dk * 2, ncclUint8, 0, s.comm, s.s_compute));
+                }
+            }
             SDPA_TRY(time_end(s, 0, s.s_compute));
             if (!on_device && have_q) SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_free[b], s.s_compute));
 
@@ -1108,7 +1142,7 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
     }
     const int dk = ctx->dk, dv = ctx->dv;
     const int L = (int)ctx->shards.size();
-    ctx->last_kernel = ctx->prec == SDPA_PREC_BF16 ? "bf16_umma" : "f32_simt";
+    ctx->last_kernel = kernel_name(ctx->prec, dk, dv);
     for (float& t : ctx->last_timing) t = 0.f;
     ctx->last_timing_valid = true;
     if (m == 0) return SDPA_OK;
@@ -1118,8 +1152,8 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
     const int B = pick_q_batch(ctx, most_rows);
     int splits = ctx->cfg.kv_splits;
     if (splits <= 0)
-        splits = ctx->prec == SDPA_PREC_BF16 ? attn_umma_pick_splits(B, ctx->shards[0].n_local, ctx->shards[0].sm_count)
-                                             : attn_f32_pick_splits(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
+        splits = is_umma(ctx->prec) ? attn_umma_pick_splits(B, ctx->shards[0].n_local, ctx->shards[0].sm_count)
+                                    : attn_f32_pick_splits(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
     splits = std::max(1, std::min(splits, 64));
     const unsigned long long launches_before = launch_count();
     int fused_launches = 0;
@@ -1131,10 +1165,11 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
         if (s.marks_used > 2048) SDPA_TRY(fold_timings(s));
         for (int w = 0; w < 4; ++w) s.tpair_last[w] = s.tpair[w].size();
         compute_stream_touched(s);
-        if (ctx->prec == SDPA_PREC_BF16) {
+        s.q_lo_off = (size_t)(((B + 127) & ~127) + 128) * dk;
+        if (is_umma(ctx->prec)) {
             umma_plan_allow_v8(s.plan, false);   // this path merges by splits
             for (int b = 0; b < 2; ++b)
-                SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk));
+                SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk, prec_hl(ctx->prec), s.q_lo_off));
         }
         SDPA_TRY(time_begin(s, 3, s.s_compute));
         cudaEvent_t begun = s.marks[s.tpair[3].back()];
@@ -1161,7 +1196,7 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
             compute_stream_touched(s);
 
             SDPA_TRY(time_begin(s, 0, s.s_compute));
-            SDPA_TRY(cast_in(ctx->prec, s.qc[b].p, s.q64[b].as<double>(), (size_t)bs * dk, s.s_compute));
+            SDPA_TRY(cast_in(ctx->prec, s.qc[b].p, s.q_lo_off, 0, s.q64[b].as<double>(), (size_t)bs * dk, s.s_compute));
             SDPA_TRY(time_end(s, 0, s.s_compute));
             SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_free[b], s.s_compute));
 
@@ -1213,10 +1248,11 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
 // Rank 0 uploads each destination's rows in fp64 chunks, casts them on its GPU and
 // ncclSend()s the compute-precision chunk; rank r ncclRecv()s straight into its shard.
 // ---------------------------------------------------------------------------
-static sdpa_status scatter_operand(sdpa_ctx* ctx, Shard& s, const NcclApi* api, int prec, void* my_dst,
+static sdpa_status scatter_operand(sdpa_ctx* ctx, Shard& s, const NcclApi* api, int prec, void* my_dst, size_t my_lo_off,
                                    const double* src_full, int n, int width, DevBuf* sendbuf)
 {
-    const size_t esz = elem_size(prec);
+    const size_t usz = unit_size(prec);
+    const bool split = prec == SDPA_PREC_BF16X3;
     const int world = ctx->world;
     if (s.grank == 0) {
         for (int r = 0; r < world; ++r) {
@@ -1232,14 +1268,17 @@ static sdpa_status scatter_operand(sdpa_ctx* ctx, Shard& s, const NcclApi* api, 
                 SDPA_TRY(h2d_any(s.kv_stage[b].p, src + done, len * sizeof(double), s.s_in));   // pinned: direct; pageable: staged
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_ready[b], s.s_in));
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_stage_ready[b], 0));
-                void* dst = (char*)my_dst + done * esz;
-                if (r != 0) {
-                    SDPA_TRY(sendbuf[b].reserve(kStageElems * esz));
-                    dst = sendbuf[b].p;
+                if (r == 0) {
+                    SDPA_TRY(cast_in(prec, my_dst, my_lo_off, done, s.kv_stage[b].as<double>(), len, s.s_compute));
+                } else {
+                    // chunk in compute precision: [hi (or the only) array | lo array of the split precision]
+                    SDPA_TRY(sendbuf[b].reserve(kStageElems * usz * (split ? 2 : 1)));
+                    SDPA_TRY(cast_in(prec, sendbuf[b].p, kStageElems, 0, s.kv_stage[b].as<double>(), len, s.s_compute));
+                    SDPA_NCCL_TRY(api->Send(sendbuf[b].p, len * usz, ncclUint8, r, s.comm, s.s_compute));
+                    if (split)
+                        SDPA_NCCL_TRY(api->Send((char*)sendbuf[b].p + kStageElems * usz, len * usz, ncclUint8, r, s.comm, s.s_compute));
                 }
-                SDPA_TRY(cast_in(prec, dst, s.kv_stage[b].as<double>(), len, s.s_compute));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_stage_free[b], s.s_compute));
-                if (r != 0) SDPA_NCCL_TRY(api->Send(dst, len * esz, ncclUint8, r, s.comm, s.s_compute));
                 done += len;
                 ++c;
             }
@@ -1249,7 +1288,8 @@ static sdpa_status scatter_operand(sdpa_ctx* ctx, Shard& s, const NcclApi* api, 
         size_t done = 0;
         while (done < count) {
             const size_t len = std::min(kStageElems, count - done);
-            SDPA_NCCL_TRY(api->Recv((char*)my_dst + done * esz, len * esz, ncclUint8, 0, s.comm, s.s_compute));
+            SDPA_NCCL_TRY(api->Recv((char*)my_dst + done * usz, len * usz, ncclUint8, 0, s.comm, s.s_compute));
+            if (split) SDPA_NCCL_TRY(api->Recv((char*)my_dst + (my_lo_off + done) * usz, len * usz, ncclUint8, 0, s.comm, s.s_compute));
             done += len;
         }
     }
@@ -1284,10 +1324,7 @@ static sdpa_status scatter_attention_impl(sdpa_ctx* ctx, const double* Q, const 
         return SDPA_ERR_INVALID;
     }
     const int prec = resolve_precision(ctx->cfg.precision, dk, dv);
-    if ((prec == SDPA_PREC_BF16 && !attn_umma_supported(dk, dv)) || (prec == SDPA_PREC_F32 && !attn_f32_supported(dk, dv))) {
-        set_error("no kernel for dk=%d dv=%d at the requested precision", dk, dv);
-        return SDPA_ERR_UNSUPPORTED;
-    }
+    SDPA_TRY(check_precision(prec, dk, dv));
     ctx->dk = dk;
     ctx->dv = dv;
     ctx->prec = prec;
@@ -1295,9 +1332,11 @@ static sdpa_status scatter_attention_impl(sdpa_ctx* ctx, const double* Q, const 
     s.n_local = sdpa_owner_count(n, ctx->world, s.grank);
     SDPA_TRY(s.Kc.reserve(((size_t)s.n_local + 128) * dk * esz));
     SDPA_TRY(s.Vc.reserve(((size_t)s.n_local + 128) * dv * esz));
+    s.k_lo_off = ((size_t)s.n_local + 128) * dk;
+    s.v_lo_off = ((size_t)s.n_local + 128) * dv;
     DevBuf sendbuf[2];
-    sdpa_status st = scatter_operand(ctx, s, api, prec, s.Kc.p, K, n, dk, sendbuf);
-    if (st == SDPA_OK) st = scatter_operand(ctx, s, api, prec, s.Vc.p, V, n, dv, sendbuf);
+    sdpa_status st = scatter_operand(ctx, s, api, prec, s.Kc.p, s.k_lo_off, K, n, dk, sendbuf);
+    if (st == SDPA_OK) st = scatter_operand(ctx, s, api, prec, s.Vc.p, s.v_lo_off, V, n, dv, sendbuf);
     if (st == SDPA_OK && cudaStreamSynchronize(s.s_compute) != cudaSuccess) {
         set_error("K/V scatter failed: %s", cudaGetErrorString(cudaGetLastError()));
         st = SDPA_ERR_CUDA;
@@ -1305,9 +1344,10 @@ static sdpa_status scatter_attention_impl(sdpa_ctx* ctx, const double* Q, const 
     sendbuf[0].release();
     sendbuf[1].release();
     SDPA_TRY(st);
-    if (prec == SDPA_PREC_BF16) {
+    if (is_umma(prec)) {
         if (!s.plan) SDPA_TRY(umma_plan_create(&s.plan));
-        SDPA_TRY(umma_plan_bind_kv(s.plan, s.Kc.as<__nv_bfloat16>(), s.Vc.as<__nv_bfloat16>(), s.n_local, dk, dv));
+        SDPA_TRY(umma_plan_bind_kv(s.plan, s.Kc.as<__nv_bfloat16>(), s.Vc.as<__nv_bfloat16>(), s.n_local, dk, dv, prec_hl(prec),
+                                   s.k_lo_off, s.v_lo_off));
     }
     return attention_impl(ctx, Q, nullptr, result, false, m, /*q_from_root=*/true);
 }
@@ -1681,6 +1721,11 @@ sdpa_status sdpa_cvt_f2d(double* dst_dev, const float* src_dev, size_t count, vo
 sdpa_status sdpa_cvt_d2bf16(uint16_t* dst_dev, const double* src_dev, size_t count, void* stream)
 {
     return launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst_dev), src_dev, count, (cudaStream_t)stream);
+}
+sdpa_status sdpa_cvt_d2bf16x2(uint16_t* hi_dev, uint16_t* lo_dev, const double* src_dev, size_t count, void* stream)
+{
+    return launch_cvt_d2bf16x2(reinterpret_cast<__nv_bfloat16*>(hi_dev), reinterpret_cast<__nv_bfloat16*>(lo_dev), src_dev, count,
+                               (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -28,12 +28,12 @@ import numpy as np
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libsdpa_b200.so"
 
-PREC_AUTO, PREC_F32, PREC_BF16 = 0, 1, 2
+PREC_AUTO, PREC_F32, PREC_BF16, PREC_BF16X3 = 0, 1, 2, 3
 MERGE_NCCL, MERGE_PEER, MERGE_NCCL2 = 0, 1, 2
 _MERGE = {"nccl": MERGE_NCCL2, "nccl2": MERGE_NCCL2, "nccl3": MERGE_NCCL, "peer": MERGE_PEER}
 DIST_KV, DIST_Q, DIST_AUTO = 0, 1, 2
 _DIST = {"kv": DIST_KV, "q": DIST_Q, "auto": DIST_AUTO}
-_PREC = {"auto": PREC_AUTO, "f32": PREC_F32, "fp32": PREC_F32, "bf16": PREC_BF16}
+_PREC = {"auto": PREC_AUTO, "f32": PREC_F32, "fp32": PREC_F32, "bf16": PREC_BF16, "bf16x3": PREC_BF16X3, "f32x3": PREC_BF16X3}
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _fp = ctypes.POINTER(ctypes.c_float)
@@ -92,6 +92,7 @@ ABI = {
     "sdpa_cvt_d2f": (ctypes.c_int, [_V, _V, ctypes.c_size_t, _V]),
     "sdpa_cvt_f2d": (ctypes.c_int, [_V, _V, ctypes.c_size_t, _V]),
     "sdpa_cvt_d2bf16": (ctypes.c_int, [_V, _V, ctypes.c_size_t, _V]),
+    "sdpa_cvt_d2bf16x2": (ctypes.c_int, [_V, _V, _V, ctypes.c_size_t, _V]),
     "sdpa_last_error": (ctypes.c_char_p, []),
     "sdpa_version": (ctypes.c_char_p, []),
     "sdpa_device_count": (ctypes.c_int, []),
@@ -371,6 +372,12 @@ def cvt_d2f(dst_ptr: int, src_ptr: int, count: int, stream: int = 0) -> None:
 
 def cvt_f2d(dst_ptr: int, src_ptr: int, count: int, stream: int = 0) -> None:
     _check(lib().sdpa_cvt_f2d(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(src_ptr), count, ctypes.c_void_p(stream)), "sdpa_cvt_f2d")
+
+
+def cvt_d2bf16x2(hi_ptr: int, lo_ptr: int, src_ptr: int, count: int, stream: int = 0) -> None:
+    """The operand split of the bf16x3 precision: hi = bf16(fp32(x)), lo = bf16(fp32(x) - hi)."""
+    _check(lib().sdpa_cvt_d2bf16x2(ctypes.c_void_p(hi_ptr), ctypes.c_void_p(lo_ptr), ctypes.c_void_p(src_ptr), count,
+                                   ctypes.c_void_p(stream)), "sdpa_cvt_d2bf16x2")
 
 
 def cvt_d2bf16(dst_ptr: int, src_ptr: int, count: int, stream: int = 0) -> None:

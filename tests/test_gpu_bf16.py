@@ -61,22 +61,6 @@ def test_bf16_ping_pong_batches_and_lazy_rescale(sdpa, oracle):
     np.testing.assert_allclose(got, oracle.attention_f64_numpy(Qb, Kb, Vb), rtol=0, atol=1.5e-2)
 
 
-def test_bf16_auto_precision_selects_tensor_cores(sdpa, oracle):
-    Q, K, V = oracle.make_inputs(256, 512, 128, 128, seed=2)
-    with sdpa.Context(precision="auto") as ctx:
-        ctx.load_kv_host_full(K, V)
-        ctx.attention_host(Q)
-        assert ctx.last_kernel() == "bf16_umma"
-    Q, K, V = oracle.make_inputs(64, 128, 80, 80, seed=2)
-    with sdpa.Context(precision="auto") as ctx:
-        ctx.load_kv_host_full(K, V)
-        ctx.attention_host(Q)
-        assert ctx.last_kernel() == "f32_simt"
-    with pytest.raises(sdpa.SdpaError):
-        with sdpa.Context(precision="bf16") as ctx:
-            ctx.load_kv_host_full(K, V)   # dk = 80: no tensor-core kernel, and no silent fallback
-
-
 def test_bf16_full_size_c3_row_subset(sdpa, oracle):
     """BASELINE c3 (m=8192, n=65536, d=128) at full size: seeded row subset vs the fp64 oracle,
     plus key-permutation invariance of the whole output."""
@@ -114,11 +98,10 @@ def test_bf16_overflow_guard_hands_over_to_safe_kernel(sdpa, oracle):
 
 
 @pytest.mark.parametrize("env", [{"SDPA_UMMA_SAFE": "1"}, {"SDPA_UMMA_POLY": "4"}, {"SDPA_UMMA_POLY": "8"}, {"SDPA_UMMA_GROUPS": "1"},
-                                 {"SDPA_UMMA_V7": "0"}, {"SDPA_UMMA_V7": "0", "SDPA_UMMA_POLY": "4"}, {"SDPA_UMMA_V7": "0", "SDPA_UMMA_CHUNK": "0"},
-                                 {"SDPA_UMMA_V6": "1"}, {"SDPA_UMMA_V6": "1", "SDPA_UMMA_PARTS": "4"}])
+                                 {"SDPA_UMMA_V7": "0"}, {"SDPA_UMMA_V7": "0", "SDPA_UMMA_POLY": "4"}, {"SDPA_UMMA_V7": "0", "SDPA_UMMA_CHUNK": "0"}])
 def test_bf16_kernel_variants(sdpa, oracle, monkeypatch, env):
     """Every kernel generation behind the same contract: the default is v7 (2-CTA MMA, two softmax groups);
-    v5 (SDPA_UMMA_V7=0), v6 (SDPA_UMMA_V6=1), the SAFE kernel alone, and the exp2-polynomial variants."""
+    v5 (SDPA_UMMA_V7=0), the SAFE kernel alone, and the exp2-polynomial variants."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     Q, K, V, got = _run(sdpa, oracle, 600, 2500, seed=21)
