@@ -614,7 +614,7 @@ def run_ours(args) -> None:
     avg_ms = st["ms"] / max(1.0, st["launches"])
     achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
-    bound_note = {"bf16_umma": "tcgen05 bf16 dense; peak = cuBLAS bf16 burst",
+    bound_note = {"bf16_umma": "tcgen05 bf16 dense; peak = cuBLAS bf16 burst", "bf16_umma_v8": "tcgen05 bf16 dense (persistent kernel); peak = cuBLAS bf16 burst",
                   "f32_simt": "fp32 CUDA-core kernel reported against the bf16 tensor peak (its own FFMA ceiling is ~72 TFLOP/s)"}.get(
                       kernel_name, "tcgen05, bf16 operands; peak = cuBLAS bf16 burst (split-precision kernels execute 3 MMAs per algorithmic MMA)")
     traffic, traffic_src = None, None

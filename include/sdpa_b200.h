@@ -36,12 +36,13 @@ typedef enum sdpa_status {
 
 /* Arithmetic of the fused QK^T -> softmax -> .V kernel. */
 typedef enum sdpa_precision {
-    SDPA_PREC_AUTO = 0,  /* fp32-class accuracy, like the reference (mpi.c:168-189): BF16X3 when dk, dv are multiples of 8
-                            up to 128, else F32.  Never BF16: the reference's 0.02 gate (mpi.c:476) must hold on peaky inputs */
+    SDPA_PREC_AUTO = 0,  /* fp32-class accuracy, like the reference (mpi.c:168-189): BF16X3 where that kernel takes the shape,
+                            else F32.  Never BF16: the reference's 0.02 gate (mpi.c:476) must hold on peaky inputs           */
     SDPA_PREC_F32 = 1,   /* fp32 CUDA-core kernel: the reference's own arithmetic; any dk, dv <= 256                        */
     SDPA_PREC_BF16 = 2,  /* opt-in: bf16 operands, fp32 accumulate, tcgen05; dk, dv multiples of 8 up to 256                */
     SDPA_PREC_BF16X3 = 3 /* fp32 operands split into bf16 hi + lo, three tcgen05.mma per contraction into one fp32
-                            accumulator (<= 1e-5 on N(0,1) inputs); dk, dv multiples of 8 up to 128                         */
+                            accumulator (<= 1e-5 on N(0,1) inputs); dk, dv multiples of 8 with dk <= 128 and dv <= 128, or
+                            dk <= 64 and dv <= 256 (what fits the 227 KiB of shared memory)                                */
 } sdpa_precision;
 
 /* How the per-shard softmax states are merged across GPUs (mpi.c:340-380). */

@@ -1,48 +1,23 @@
-// attn_umma_bf16.cu -- fused QK^T -> online softmax -> .V on the 5th-generation tensor cores
-// (tcgen05.mma, accumulators in TMEM, operands staged by TMA), bf16 operands / fp32 accumulate.
+// attn_umma_bf16.cu -- fused QK^T -> online softmax -> .V on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM, operands staged by TMA) for the headline shape dk = dv = 128, bf16 operands / fp32 accumulate.
 //
-// Three kernel generations live here behind one launcher (launch_attn_umma); all produce the same
-// partial softmax state and pass the same parity tests:
-//   attn_umma_kernel_v7  DEFAULT.  Cluster of two CTAs forming one M=256 tcgen05.mma.cta_group::2 (each CTA keeps
-//                        half of every K/V tile), S and P double-buffered in TMEM (no MMA waits for the softmax of
-//                        its own S), two softmax groups ping-ponged over alternating key tiles.  See its banner.
-//   attn_umma_kernel     v5 (SDPA_UMMA_V7=0): one CTA, two Q tiles ping-ponged, P aliases S.  Its SAFE variant is
-//                        the overflow-guard fallback of every generation.  Described right below.
-//   attn_umma_kernel_v8  (SDPA_UMMA_V8=1, EXPERIMENTAL, single GPU) v7 made persistent: one cluster per SM pair walks a
-//                        contiguous range of (row block, key tile) units; written after the round's GPU budget was
-//                        spent -- its barrier protocol is checked by tools/v8_protocol_sim.py, not yet by hardware.
+// The B200 counterpart of online_softmax_attention (attention-mpi.c:168-189): where the reference does one AVX-512 dot
+// (dot_avx512, :103-121) and one axpy (axpy_avx512, :123-140) per (query, key) pair, these kernels do two 256x128x128
+// tensor-core GEMMs per (256-query block, 128-key tile) pair; the running max / running sum of mpi.c:177-180 live in
+// registers, one (query row, 64-key half) per thread.
 //
-// The B200 counterpart of online_softmax_attention (attention-mpi.c:168-189): where the
-// reference does one AVX-512 dot (dot_avx512, :103-121) and one axpy (axpy_avx512, :123-140)
-// per (query, key) pair, this kernel does two 128x128x128 tensor-core GEMMs per
-// (128-query tile, 128-key tile) pair; the running max / running sum of mpi.c:177-180 live in
-// registers, one query row per thread.
-//
-// CTA = 256 query rows (two 128-row tiles A and B, ping-ponged) x one contiguous range of
-// 128-key tiles (split-KV over blockIdx.y).  20 warps:
-//   warp 0      TMA producer   : Q tiles once, then K/V tiles through 2-stage mbarrier rings
-//                                (cp.async.bulk.tensor, 128-byte swizzle)
-//   warp 1      MMA issuer     : one thread issues   S_t = Q_t K^T   (SS, both K-major)
-//                                and                 O_t += P_t V    (TS: P from TMEM, V MN-major)
-//                                order  S_A(0) S_B(0) | PV_A(j) S_A(j+1) PV_B(j) S_B(j+1) | ...
-//                                so the softmax of one tile overlaps the MMAs of the other
-//   warps 2-3   idle (keep the softmax warpgroups aligned to the TMEM lane quadrants)
-//   warps 4-11  softmax of tile A, warps 12-19 softmax of tile B.  A tile has TWO warpgroups:
-//               a thread owns one query row and one 64-key half of it, so every SM sub-partition
-//               runs two warps of the same tile and the MUFU (ex2) pipe of one is fed while the
-//               other issues its FFMA2/FADD2/F2FP (measured on v1: one warp per sub-partition
-//               reaches only ~0.3 IPC and the per-tile chain softmax -> PV -> next S is serial,
-//               see profiles/r01).  Per tile: tcgen05.ld the half row, 8-chain FMNMX3 max, the two
-//               halves' maxima are exchanged through shared memory (named barrier, 256 threads),
-//               lazy rescale of O (only when the max grew by > 2^8, warp vote), exp2 with the
-//               1/sqrt(dk)*log2(e) scale folded into packed FFMA2, packed FADD2 row sums, bf16 P
-//               written back into the TMEM columns of S (tcgen05.st); finally the epilogue.
-// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P_t aliases the
-// first 64 columns of S_t (the tensor pipe executes MMAs in issue order, so S_t(j+1) cannot
-// overwrite P_t(j) before PV_t(j) has consumed it).
-// Shared memory: Q_A, Q_B, 2 x K, 2 x V tiles of 32 KiB = 192 KiB.
-// Roofline: tensor pipe, 4*128^3 flops per tile pair; algorithmic HBM bytes are the bf16
-// Q/K/V and the fp32 partial outputs.
+// Two kernels behind one launcher (launch_attn_umma); both produce the same partial softmax state:
+//   attn_umma_kernel_v8  the PERSISTENT kernel: one cluster per SM pair walks a contiguous range of (row block, key tile)
+//                        units ("stream-K" over the key axis): no wave quantisation, one prologue per SM, 3-4 partial
+//                        states per row block instead of 9.  Used whenever the caller merges by pieces (see its banner).
+//   attn_umma_kernel_v7  the same pipeline as a plain grid (row block x split): small problems, explicit split counts.
+// Common design (v7 banner): a cluster of two CTAs forms one M=256 tcgen05.mma.cta_group::2, each CTA keeps half of every
+// K/V tile, S and P are double-buffered in TMEM (no MMA waits for the softmax of its own S), two softmax groups ping-pong
+// over alternating key tiles.  The softmax reference is fixed by the first key tile of a range; scores that outgrow it by
+// more than 2^64 raise a guard and the exact two-phase variant of the general kernel (attn_umma_general.cu) -- launched
+// behind every fast launch, leaving at once unless the guard fired -- recomputes the launch.
+// Every other shape (dk, dv multiples of 8 up to 256) and the fp32-accurate split precision: attn_umma_general.cu.
+// History of the kernel generations (v1 ... v7, with measurements): profiles/README.md.
 #include "umma_ptx.cuh"
 #include "umma_general.h"
 
@@ -57,28 +32,10 @@ namespace {
 using namespace umma;
 
 constexpr int HEAD = 128;            // dk == dv
-constexpr int BLOCK_ROWS = 2 * TILE; // Q rows per CTA
-constexpr int NTHREADS = 640;
-constexpr int STAGES = 2;
-constexpr float kLazyThreshold = 8.0f;                // safe mode: rescale O only if the max grew by > 2^8
 constexpr float kGuardThreshold = 64.0f;              // fast mode: exponents beyond 2^64 hand the launch to the safe kernel
+constexpr int kDefaultV8Opt = 0;                      // persistent kernel: bit 0 = V producer warp, bit 1 = progressive P stores
+constexpr int kDefaultV8Poly = 0;
 constexpr int kDefaultPoly = 0;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
-
-constexpr uint32_t TMEM_S = 0;    // + 128 * tile
-constexpr uint32_t TMEM_O = 256;  // + 128 * tile
-
-struct __align__(1024) SharedStorage {
-    uint8_t q[2][TILE_BYTES];
-    uint8_t k[STAGES][TILE_BYTES];
-    uint8_t v[STAGES][TILE_BYTES];
-    uint64_t q_full[2];
-    uint64_t k_full[STAGES], k_empty[STAGES];
-    uint64_t v_full[STAGES], v_empty[STAGES];
-    uint64_t s_full[2], p_ready[2], o_done[2];
-    uint32_t tmem_base;
-    float xchg[2][2][2][TILE];   // [tile][parity][column half][row]: row-max / row-sum exchange
-};
-
 
 struct KernelParams {
     int rows;            // valid Q rows
@@ -98,427 +55,6 @@ struct KernelParams {
 };
 
 constexpr int TRACE_ITERS = 24, TRACE_EVENTS = 8, TRACE_ROLES = 6;
-
-// SAFE = the always-correct variant (row max agreed every tile, lazy rescale).  The default launch is
-// the fast variant (reference fixed after the first tile) followed by the SAFE variant, which exits
-// immediately unless the fast one raised the overflow guard.  POLY: see kDefaultPoly.
-template <bool TRACE, bool SAFE, int POLY, bool CHUNKED = true>
-__global__ void __launch_bounds__(NTHREADS, 1)
-attn_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                 const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
-{
-    if constexpr (SAFE) {
-        if (*prm.guard != prm.epoch) return;   // nothing overflowed in the fast pass: the whole grid leaves at once
-    }
-    extern __shared__ uint8_t smem_raw[];
-    SharedStorage& sm = *reinterpret_cast<SharedStorage*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
-    const int lane = threadIdx.x & 31;
-    const int row_block = blockIdx.x;
-    const int split = blockIdx.y;
-
-    // balanced contiguous partition of the key tiles over the splits (same rule as owner_count/owner_disp)
-    const int tq = prm.tiles_total / prm.splits, tr = prm.tiles_total % prm.splits;
-    const int tile_begin = split * tq + min(split, tr);
-    const int num_tiles = tq + (split < tr ? 1 : 0);
-
-    if (warp == 0 && lane == 0) {
-        prefetch_tensormap(&map_q);
-        prefetch_tensormap(&map_k);
-        prefetch_tensormap(&map_v);
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.q_full[i], 1);
-            mbar_init(&sm.s_full[i], 1);
-            mbar_init(&sm.p_ready[i], 256);
-            mbar_init(&sm.o_done[i], 1);
-        }
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&sm.k_full[i], 1);
-            mbar_init(&sm.k_empty[i], 1);
-            mbar_init(&sm.v_full[i], 1);
-            mbar_init(&sm.v_empty[i], 1);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) tmem_alloc(&sm.tmem_base, 512);
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem = sm.tmem_base;
-    auto stamp = [&](int role, int j, int ev) {
-        if constexpr (TRACE) {
-            if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && j < TRACE_ITERS)
-                prm.trace[(role * TRACE_ITERS + j) * TRACE_EVENTS + ev] = clock64();
-        }
-    };
-
-    // Register re-allocation between the warpgroups (each branch is dominated by its own
-    // setmaxnreg, so ptxas budgets it separately): the producer / MMA warpgroup needs few
-    // registers, each softmax thread holds a 64-column half of an S row (128*64 + 512*104 = 640*96).
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (num_tiles > 0) {
-        if (warp == 0) {
-            // ================================ TMA producer ================================
-            // all 32 lanes walk the loop (uniform control flow); one elected lane issues
-            const int qrow = row_block * BLOCK_ROWS;
-            for (int j = 0; j < num_tiles; ++j) {
-                const int stage = j % STAGES;
-                const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-                const int key0 = (tile_begin + j) * TILE;
-                if (j == 0 && elect_one_sync()) {
-                    mbar_arrive_expect_tx(&sm.q_full[0], TILE_BYTES);
-                    tma_load_2d(sm.q[0], &map_q, &sm.q_full[0], 0, qrow);
-                    tma_load_2d(sm.q[0] + HALF_BYTES, &map_q, &sm.q_full[0], 64, qrow);
-                }
-                mbar_wait(&sm.k_empty[stage], ph ^ 1u, 100 + stage);
-                stamp(5, j, 0);
-                if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(&sm.k_full[stage], TILE_BYTES);
-                    tma_load_2d(sm.k[stage], &map_k, &sm.k_full[stage], 0, key0);
-                    tma_load_2d(sm.k[stage] + HALF_BYTES, &map_k, &sm.k_full[stage], 64, key0);
-                }
-                if (j == 0 && elect_one_sync()) {
-                    mbar_arrive_expect_tx(&sm.q_full[1], TILE_BYTES);
-                    tma_load_2d(sm.q[1], &map_q, &sm.q_full[1], 0, qrow + TILE);
-                    tma_load_2d(sm.q[1] + HALF_BYTES, &map_q, &sm.q_full[1], 64, qrow + TILE);
-                }
-                mbar_wait(&sm.v_empty[stage], ph ^ 1u, 110 + stage);
-                stamp(5, j, 1);
-                if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(&sm.v_full[stage], TILE_BYTES);
-                    tma_load_2d(sm.v[stage], &map_v, &sm.v_full[stage], 0, key0);
-                    tma_load_2d(sm.v[stage] + HALF_BYTES, &map_v, &sm.v_full[stage], 64, key0);
-                }
-                __syncwarp();
-            }
-        } else if (warp == 1) {
-            // ================================ MMA issuer ==================================
-            // Uniform control flow for the whole warp; descriptors are base + constant, the
-            // tcgen05.mma / tcgen05.commit instructions sit under elect_one_sync().
-            constexpr uint32_t idesc_qk = make_idesc(TILE, TILE, 0);
-            constexpr uint32_t idesc_pv = make_idesc(TILE, HEAD, 1);
-            const uint64_t dq[2] = {desc_kmajor(smem_u32(sm.q[0]), 0), desc_kmajor(smem_u32(sm.q[1]), 0)};
-            const uint64_t dkk[STAGES] = {desc_kmajor(smem_u32(sm.k[0]), 0), desc_kmajor(smem_u32(sm.k[1]), 0)};
-            const uint64_t dvv[STAGES] = {desc_mnmajor(smem_u32(sm.v[0]), 0), desc_mnmajor(smem_u32(sm.v[1]), 0)};
-
-            // S_t = Q_t K(stage)^T ; commit -> s_full[t]  (+ optionally release the K stage)
-            auto issue_s = [&](int t, int stage, bool release_k) {
-                if (elect_one_sync()) {
-                    const uint64_t a0 = dq[t], b0 = dkk[stage];
-                    const uint32_t d = tmem + TMEM_S + 128u * t;
-#pragma unroll
-                    for (int kk = 0; kk < HEAD / 16; ++kk) {
-                        // 16-column slice kk: (kk%4)*32 B into box kk/4 -> +((kk>>2)*HALF_BYTES + (kk&3)*32) >> 4
-                        const uint64_t off = (uint64_t)(((kk >> 2) * HALF_BYTES + (kk & 3) * 32u) >> 4);
-                        umma_ss(d, a0 + off, b0 + off, idesc_qk, kk > 0 ? 1u : 0u);
-                    }
-                    umma_commit(&sm.s_full[t]);
-                    if (release_k) umma_commit(&sm.k_empty[stage]);
-                }
-                __syncwarp();
-            };
-            // O_t (+)= P_t V(stage) ; optionally release the V stage / signal o_done
-            auto issue_pv = [&](int t, int stage, bool accumulate_first, bool release_v, bool last) {
-                if (elect_one_sync()) {
-                    const uint64_t b0 = dvv[stage];
-                    const uint32_t d = tmem + TMEM_O + 128u * t;
-                    const uint32_t a = tmem + TMEM_S + 128u * t;
-#pragma unroll
-                    for (int kk = 0; kk < TILE / 16; ++kk)   // P of keys 0-63 at S+0.., of keys 64-127 at S+64..
-                        umma_ts(d, a + (kk < 4 ? 8u * kk : 64u + 8u * (kk - 4)), b0 + (uint64_t)((kk * 2048u) >> 4),
-                                idesc_pv, (accumulate_first || kk > 0) ? 1u : 0u);
-                    if (release_v) umma_commit(&sm.v_empty[stage]);
-                    if (last) umma_commit(&sm.o_done[t]);
-                }
-                __syncwarp();
-            };
-
-            // prologue: S_A(0), S_B(0)
-            mbar_wait(&sm.k_full[0], 0, 200);
-            mbar_wait(&sm.q_full[0], 0, 201);
-            tcgen05_fence_after();
-            issue_s(0, 0, false);
-            mbar_wait(&sm.q_full[1], 0, 202);
-            tcgen05_fence_after();
-            issue_s(1, 0, true);   // K(0) is free once S_A(0), S_B(0) have completed
-
-            for (int j = 0; j < num_tiles; ++j) {
-                const int stage = j % STAGES;
-                const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-                const int nstage = (j + 1) % STAGES;
-                const uint32_t nph = (uint32_t)((j + 1) / STAGES) & 1u;
-                const bool more = (j + 1) < num_tiles;
-
-                mbar_wait(&sm.v_full[stage], ph, 210);
-                stamp(4, j, 0);
-                // ---- tile A ----
-                mbar_wait(&sm.p_ready[0], (uint32_t)j & 1u, 211);
-                stamp(4, j, 1);
-                tcgen05_fence_after();
-                issue_pv(0, stage, j > 0, false, !more);
-                stamp(4, j, 2);
-                if (more) {
-                    mbar_wait(&sm.k_full[nstage], nph, 212);
-                    tcgen05_fence_after();
-                    issue_s(0, nstage, false);
-                }
-                stamp(4, j, 3);
-                // ---- tile B ----
-                mbar_wait(&sm.p_ready[1], (uint32_t)j & 1u, 213);
-                stamp(4, j, 4);
-                tcgen05_fence_after();
-                issue_pv(1, stage, j > 0, true, !more);
-                if (more) issue_s(1, nstage, true);
-                stamp(4, j, 5);
-            }
-        }
-        }
-    } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-        if (num_tiles > 0) {
-            // ================================ softmax + epilogue ==========================
-            const int sw = warp - 4;                       // 0..15
-            const int t = sw >> 3;                         // which Q tile
-            const int half = (sw >> 2) & 1;                // which 64-key half of the row
-            const int quad = warp & 3;                     // TMEM lane quadrant of this warp
-            const int row_in_tile = quad * 32 + lane;
-            const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-            const uint32_t s_addr = tmem + lane_base + TMEM_S + 128u * t + 64u * half;   // my 64 S columns;
-            const uint32_t p_addr = s_addr;   // my bf16 P (32 packed columns) overwrites the start of my own S columns
-            const uint32_t o_addr = tmem + lane_base + TMEM_O + 128u * t + 64u * half;   // my O columns
-            const float scale = prm.scale_log2;
-            const uint64_t scale2 = pack_f32x2(scale, scale);
-            const int bar_id = 1 + 4 * t + quad;           // pair barrier: the two warps that share these 32 rows
-
-            float m_ref = -CUDART_INF_F;   // raw-score reference max used by every exponent so far
-            float lsum = 0.f;
-
-            // exp2(s*scale - ref*scale) of 16 keys: packed FFMA2, 2 x ex2 per pair, packed FADD2 row sum, F2FP pack
-            auto exp_chunk = [&](const uint32_t* sv, uint64_t neg_ref2, uint64_t& acc0, uint64_t& acc1, uint32_t* pr) {
-#pragma unroll
-                for (int c = 0; c < 16; c += 2) {
-                    const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
-                    const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
-                    float p0, p1;
-                    // pairs 1 and 5 (POLY=4) or 1,3,5,7 (POLY=8) of the eight pairs use the polynomial
-                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
-                    if (poly) {
-                        exp2_poly_x2(t2, p0, p1);
-                    } else {
-                        float t0, t1;
-                        unpack_f32x2(t2, t0, t1);
-                        p0 = fast_exp2(t0);
-                        p1 = fast_exp2(t1);
-                    }
-                    const uint64_t p2 = pack_f32x2(p0, p1);
-                    if (c & 4) acc1 = add_f32x2(acc1, p2);
-                    else acc0 = add_f32x2(acc0, p2);
-                    pr[c / 2] = pack_bf16x2(p0, p1);
-                }
-            };
-
-            // One key tile.  The exponentials are SPECULATIVE on the reference max of the previous tiles
-            // so they can start as soon as the first 16 columns arrive from TMEM (the remaining
-            // tcgen05.ld's stream behind the MUFU work); the tile's own max is computed alongside and
-            // exchanged with the other half of the row at the end.  Only if the max grew by more than
-            // 2^kLazyThreshold (or on the very first tile, reference = -inf) is the tile redone with the
-            // new reference and O rescaled -- the lazy rescale, decided per warp with a vote.
-            // MASKED = the last tile of the shard when n is not a multiple of 128.
-            auto tile_step = [&](int j, auto masked_tag, auto first_tag) {
-                constexpr bool MASKED = decltype(masked_tag)::value;
-                constexpr bool AGREE = SAFE || decltype(first_tag)::value;   // exchange the row max on this tile?
-                mbar_wait(&sm.s_full[t], (uint32_t)j & 1u, 300 + t);
-                if (quad == 0) stamp(sw >> 2, j, 0);
-                tcgen05_fence_after();
-
-                uint32_t sr[64];
-                const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
-                uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
-                float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
-                int keys_left = 64;
-                if constexpr (MASKED) keys_left = prm.n - (tile_begin + j) * TILE - 64 * half;   // valid keys in my half
-
-                if constexpr (CHUNKED) {
-                SDPA_TMEM_LD16(s_addr, sr);
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    tmem_wait_ld();
-                    if (ch == 0 && quad == 0) stamp(sw >> 2, j, 1);
-                    if (ch < 3) SDPA_TMEM_LD16(s_addr + 16 * (ch + 1), (sr + 16 * (ch + 1)));   // in flight during this chunk
-                    uint32_t* sv = sr + 16 * ch;
-                    if constexpr (MASKED) {
-#pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            if (16 * ch + c >= keys_left) sv[c] = 0xff800000u;  // -inf
-                    }
-#pragma unroll
-                    for (int c = 0; c < 16; c += 8) {
-                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[c + 0]), __uint_as_float(sv[c + 1])));
-                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3])));
-                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5])));
-                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7])));
-                    }
-                    uint32_t pr[8];
-                    exp_chunk(sv, neg_ref2, acc0, acc1, pr);
-                    SDPA_TMEM_ST8(p_addr + 8 * ch, pr);   // columns [8ch, 8ch+8) of my region: S values already in registers
-                }
-                } else {
-                    // whole half row at once: one wait, no scheduling barriers between the 16-key groups
-                    SDPA_TMEM_LD32(s_addr, sr);
-                    SDPA_TMEM_LD32(s_addr + 32, (sr + 32));
-                    tmem_wait_ld();
-                    if (quad == 0) stamp(sw >> 2, j, 1);
-                    if constexpr (MASKED) {
-#pragma unroll
-                        for (int c = 0; c < 64; ++c)
-                            if (c >= keys_left) sr[c] = 0xff800000u;  // -inf
-                    }
-#pragma unroll
-                    for (int c = 0; c < 64; c += 8) {
-                        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sr[c + 0]), __uint_as_float(sr[c + 1])));
-                        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])));
-                        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5])));
-                        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7])));
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t pr[8];
-                        exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr);
-                        SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
-                    }
-                }
-                if (quad == 0) stamp(sw >> 2, j, 2);
-
-                const float my_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                if constexpr (AGREE) {
-                // agree on the tile max with the thread that owns the other half of this row
-                sm.xchg[t][j & 1][half][row_in_tile] = my_max;
-                named_barrier_sync(bar_id, 64);
-                const float tile_max = fmaxf(my_max, sm.xchg[t][j & 1][half ^ 1][row_in_tile]);
-                if (quad == 0) stamp(sw >> 2, j, 3);
-
-                const bool need = (tile_max - m_ref) * scale > kLazyThreshold;   // first tile: -inf reference -> true
-                if (__any_sync(0xffffffffu, need)) {
-                    // Rare path.  O_t is stable here: PV_t(j-1) completed before s_full(j) fired, and
-                    // PV_t(j) is not issued until all 256 threads of the tile signal p_ready(j).
-                    const float new_ref = need ? tile_max : m_ref;
-                    const float corr = need ? fast_exp2((m_ref - new_ref) * scale) : 1.f;   // -inf reference -> 0
-                    m_ref = new_ref;
-                    lsum *= corr;
-#pragma unroll 1
-                    for (int c0 = 0; c0 < 64; c0 += 16) {   // small chunks: keep this path out of the register budget
-                        uint32_t orr[16];
-                        SDPA_TMEM_LD16(o_addr + c0, orr);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) orr[c] = __float_as_uint(__uint_as_float(orr[c]) * corr);
-                        SDPA_TMEM_ST16(o_addr + c0, orr);
-                    }
-                    const uint64_t neg_new2 = pack_f32x2(-new_ref * scale, -new_ref * scale);
-                    acc0 = pack_f32x2(0.f, 0.f);
-                    acc1 = acc0;
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t pr[8];
-                        exp_chunk(sr + 16 * ch, neg_new2, acc0, acc1, pr);
-                        SDPA_TMEM_ST8(p_addr + 8 * ch, pr);
-                    }
-                }
-                } else {
-                    // Fast mode after the first tile: the reference stays where the first tile put it
-                    // (any reference gives the same quotient o/lsum; fp32 has the range for 2^64 growth).
-                    // If a score outgrows it by more than 2^kGuardThreshold the launch is handed to the
-                    // SAFE kernel, which recomputes everything with per-tile agreement.
-                    if (quad == 0) stamp(sw >> 2, j, 3);
-                    if (__any_sync(0xffffffffu, (my_max - m_ref) * scale > kGuardThreshold)) {
-                        if (lane == 0) atomicExch(prm.guard, prm.epoch);
-                    }
-                }
-                float a0, a1, a2, a3;
-                unpack_f32x2(acc0, a0, a1);
-                unpack_f32x2(acc1, a2, a3);
-                lsum += (a0 + a1) + (a2 + a3);
-
-                if (quad == 0) stamp(sw >> 2, j, 4);
-                tmem_wait_st();
-                tcgen05_fence_before();
-                mbar_arrive(&sm.p_ready[t]);
-                if (quad == 0) stamp(sw >> 2, j, 5);
-            };
-            const bool ragged = (prm.n % TILE) != 0 && (tile_begin + num_tiles) == prm.tiles_total;
-            const int full_tiles = ragged ? num_tiles - 1 : num_tiles;
-            if (full_tiles > 0) tile_step(0, std::false_type{}, std::true_type{});
-            for (int j = 1; j < full_tiles; ++j) tile_step(j, std::false_type{}, std::false_type{});
-            if (ragged) {
-                if (num_tiles == 1) tile_step(0, std::true_type{}, std::true_type{});
-                else tile_step(num_tiles - 1, std::true_type{}, std::false_type{});
-            }
-
-            // ---------------- epilogue: O_t, reference max, row sum ----------------
-            sm.xchg[t][num_tiles & 1][half][row_in_tile] = lsum;
-            named_barrier_sync(bar_id, 64);
-            lsum += sm.xchg[t][num_tiles & 1][half ^ 1][row_in_tile];
-
-            mbar_wait(&sm.o_done[t], 0, 320 + t);
-            tcgen05_fence_after();
-            const int grow = row_block * BLOCK_ROWS + t * TILE + row_in_tile;
-            const bool valid = grow < prm.rows;
-            const float inv = (lsum == 0.f) ? 0.f : 1.f / lsum;
-#pragma unroll
-            for (int c0 = 0; c0 < 64; c0 += 32) {
-                uint32_t orr[32];
-                SDPA_TMEM_LD32(o_addr + c0, orr);
-                tmem_wait_ld();
-                if (valid) {
-                    const int col = 64 * half + c0;
-                    if (prm.out64 != nullptr) {
-                        double2* dst = reinterpret_cast<double2*>(prm.out64 + (size_t)grow * HEAD + col);
-#pragma unroll
-                        for (int c = 0; c < 32; c += 2)
-                            dst[c / 2] = make_double2((double)(__uint_as_float(orr[c]) * inv),
-                                                      (double)(__uint_as_float(orr[c + 1]) * inv));
-                    } else {
-                        float4* dst = reinterpret_cast<float4*>(prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + col);
-#pragma unroll
-                        for (int c = 0; c < 32; c += 4)
-                            dst[c / 4] = make_float4(__uint_as_float(orr[c]), __uint_as_float(orr[c + 1]),
-                                                     __uint_as_float(orr[c + 2]), __uint_as_float(orr[c + 3]));
-                    }
-                }
-            }
-            if (valid && half == 0 && prm.out64 == nullptr) {
-                prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = m_ref * scale;
-                prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = lsum;
-            }
-        } else {
-        // empty key range (n == 0 or more splits than tiles): the neutral state (0, -inf, 0), mpi.c:172,188
-        const int sw = warp - 4;
-        const int t = sw >> 3, half = (sw >> 2) & 1;
-        const int grow = row_block * BLOCK_ROWS + t * TILE + (warp & 3) * 32 + lane;
-        if (grow < prm.rows) {
-            if (prm.out64 != nullptr) {
-                for (int c = 0; c < 64; ++c) prm.out64[(size_t)grow * HEAD + 64 * half + c] = 0.0;
-            } else {
-                float* dst = prm.part_o + ((size_t)split * prm.rows_capacity + grow) * HEAD + 64 * half;
-                for (int c = 0; c < 64; ++c) dst[c] = 0.f;
-                if (half == 0) {
-                    prm.part_tmax[(size_t)split * prm.rows_capacity + grow] = -CUDART_INF_F;
-                    prm.part_lsum[(size_t)split * prm.rows_capacity + grow] = 0.f;
-                }
-            }
-        }
-        }
-    }
-
-    tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tcgen05_fence_after();
-        tmem_dealloc(tmem, 512);
-    }
-}
 
 // (v6 -- the cluster-of-two, multicast stepping stone between v5 and v7 -- was removed in round 2: measured slower than both,
 //  profiles/README.md keeps its numbers.)
@@ -655,11 +191,8 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 constexpr uint32_t idesc_qk = make_idesc(2 * TILE, TILE, 0);   // M = 256 over the CTA pair
                 constexpr uint32_t idesc_pv = make_idesc(2 * TILE, HEAD, 1);
                 const uint64_t dq = desc_kmajor(smem_u32(sm.q), 0);
-                uint64_t dkk[V7_KSTAGES], dvv[V7_VSTAGES];
-#pragma unroll
-                for (int i = 0; i < V7_KSTAGES; ++i) dkk[i] = make_desc(smem_u32(sm.k[i]), 16u, 1024u);
-#pragma unroll
-                for (int i = 0; i < V7_VSTAGES; ++i) dvv[i] = make_desc(smem_u32(sm.v[i]), HALF_TILE_BYTES, 1024u);
+                // stage s of a ring: base descriptor + s * stage bytes (>> 4 in the address field); no indexed local arrays on the issue path
+                const uint64_t dk0 = make_desc(smem_u32(sm.k[0]), 16u, 1024u), dv0 = make_desc(smem_u32(sm.v[0]), HALF_TILE_BYTES, 1024u);
                 const uint16_t both = 0x3;
 
                 auto issue_s = [&](int j) {
@@ -667,7 +200,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                     mbar_wait(&sm.k_full[ks], (uint32_t)(j / V7_KSTAGES) & 1u, 200 + ks);   // (already tested by the scheduler below)
                     tcgen05_fence_after();
                     if (elect_one_sync()) {
-                        const uint64_t b0 = dkk[ks];
+                        const uint64_t b0 = dk0 + (uint64_t)((uint32_t)ks * (HALF_TILE_BYTES >> 4));
                         const uint32_t d = tmem + V6_S + 128u * sb;
 #pragma unroll
                         for (int kk = 0; kk < HEAD / 16; ++kk) {
@@ -687,7 +220,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                     stamp(4, j, 1);
                     tcgen05_fence_after();
                     if (elect_one_sync()) {
-                        const uint64_t b0 = dvv[vs];
+                        const uint64_t b0 = dv0 + (uint64_t)((uint32_t)vs * (HALF_TILE_BYTES >> 4));
                         const uint32_t d = tmem + V6_O;
                         const uint32_t a = tmem + V6_P + 64u * pb;
 #pragma unroll
@@ -739,8 +272,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
             const uint64_t scale2 = pack_f32x2(scale, scale);
             const int bar_id = 1 + quad;               // the warps of ONE group that share these 32 rows
             const int bar_all = 5 + quad;              // the warps of ALL groups that share these 32 rows
-            const uint32_t leader_pready[2] = {map_to_cta(&sm.p_ready[0], 0), map_to_cta(&sm.p_ready[1], 0)};
-            const uint32_t leader_sfree[2] = {map_to_cta(&sm.s_free[0], 0), map_to_cta(&sm.s_free[1], 0)};
+            const uint32_t leader_pready0 = map_to_cta(&sm.p_ready[0], 0), leader_sfree0 = map_to_cta(&sm.s_free[0], 0);   // [1] is 8 bytes further
 
             float m_ref = -CUDART_INF_F;
             float lsum = 0.f;
@@ -783,7 +315,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 tmem_wait_ld();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_sfree[sb]);   // S buffer sb may be overwritten by S(j+2)
+                if (lane == 0) mbar_arrive_cluster(leader_sfree0 + 8u * (uint32_t)sb);   // S buffer sb may be overwritten by S(j+2)
                 if (quad == 0 && half == 0) stamp(group, j, 1);
                 if constexpr (MASKED) {
                     const int keys_left = prm.n - (tile_begin + j) * TILE - COLS * half;
@@ -839,7 +371,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 tmem_wait_st();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_pready[sb]);   // one arrival per warp, on the leader's barrier
+                if (lane == 0) mbar_arrive_cluster(leader_pready0 + 8u * (uint32_t)sb);   // one arrival per warp, on the leader's barrier
                 if (quad == 0 && half == 0) stamp(group, j, 5);
             };
 
@@ -976,7 +508,10 @@ struct SegCursor {
     }
 };
 
-template <int POLY>
+// POLY: of every 16 exponentials, this many run on the FMA pipe (degree-3 polynomial) instead of the MUFU.  VW: the V tiles have
+// their own TMA producer warp (warp 2), so a K load never queues behind a V slot that is still being read.  PS: P is
+// stored chunk by chunk (the wait for PV(g-2) sits after the first two chunks) instead of being held in 32 registers.
+template <int POLY, bool VW, bool PS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
 attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
@@ -1057,6 +592,27 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                             tma_load_2d_2sm(sm.k[ks], &map_khalf, &sm.k_full[ks], 0, key0 + 64 * (int)rank);
                             tma_load_2d_2sm(sm.k[ks] + HALF_TILE_BYTES / 2, &map_khalf, &sm.k_full[ks], 64, key0 + 64 * (int)rank);
                         }
+                        if constexpr (!VW) {
+                            mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
+                            if (elect_one_sync()) {
+                                if (leader) mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
+                                else mbar_arrive_cluster(map_to_cta(&sm.v_full[vs], 0));
+                                tma_load_2d_2sm(sm.v[vs], &map_v, &sm.v_full[vs], 64 * (int)rank, key0);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else if (VW && warp == 2) {
+                // ================================ TMA producer of the V tiles ==================
+                SegCursor cur;
+                cur.init(unit_begin, unit_end, T);
+                int g = 0;
+                while (cur.next()) {
+                    for (int j = 0; j < cur.nt; ++j, ++g) {
+                        const int vs = g % V7_VSTAGES;
+                        const uint32_t vph = (uint32_t)(g / V7_VSTAGES) & 1u;
+                        const int key0 = (cur.t0 + j) * TILE;
                         mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
                         if (elect_one_sync()) {
                             if (leader) mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
@@ -1071,12 +627,9 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 if (leader) {
                 constexpr uint32_t idesc_qk = make_idesc(2 * TILE, TILE, 0);
                 constexpr uint32_t idesc_pv = make_idesc(2 * TILE, HEAD, 1);
-                const uint64_t dq[2] = {desc_kmajor(smem_u32(sm.q[0]), 0), desc_kmajor(smem_u32(sm.q[1]), 0)};
-                uint64_t dkk[V7_KSTAGES], dvv[V7_VSTAGES];
-#pragma unroll
-                for (int i = 0; i < V7_KSTAGES; ++i) dkk[i] = make_desc(smem_u32(sm.k[i]), 16u, 1024u);
-#pragma unroll
-                for (int i = 0; i < V7_VSTAGES; ++i) dvv[i] = make_desc(smem_u32(sm.v[i]), HALF_TILE_BYTES, 1024u);
+                const uint64_t dq0 = desc_kmajor(smem_u32(sm.q[0]), 0);
+                // stage s of a ring: base descriptor + s * stage bytes (>> 4 in the address field); no indexed local arrays on the issue path
+                const uint64_t dk0 = make_desc(smem_u32(sm.k[0]), 16u, 1024u), dv0 = make_desc(smem_u32(sm.v[0]), HALF_TILE_BYTES, 1024u);
                 const uint16_t both = 0x3;
 
                 SegCursor cs, cp;   // the S stream runs two tiles ahead of the PV stream, possibly in the next segment
@@ -1093,7 +646,7 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                     tcgen05_fence_after();
                     const bool last_of_segment = (js == cs.nt - 1);
                     if (elect_one_sync()) {
-                        const uint64_t a0 = dq[qs], b0 = dkk[ks];
+                        const uint64_t a0 = dq0 + (uint64_t)((uint32_t)qs * (TILE_BYTES >> 4)), b0 = dk0 + (uint64_t)((uint32_t)ks * (HALF_TILE_BYTES >> 4));
                         const uint32_t d = tmem + V6_S + 128u * sb;
 #pragma unroll
                         for (int kk = 0; kk < HEAD / 16; ++kk) {
@@ -1120,7 +673,7 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                     mbar_wait(&sm.p_ready[pb], (uint32_t)(g >> 1) & 1u, 214 + pb);
                     tcgen05_fence_after();
                     if (elect_one_sync()) {
-                        const uint64_t b0 = dvv[vs];
+                        const uint64_t b0 = dv0 + (uint64_t)((uint32_t)vs * (HALF_TILE_BYTES >> 4));
                         const uint32_t d = tmem + V6_O;
                         const uint32_t a = tmem + V6_P + 64u * pb;
 #pragma unroll
@@ -1166,8 +719,7 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
             const uint64_t scale2 = pack_f32x2(scale, scale);
             const int bar_id = 1 + quad;
             const int bar_all = 5 + quad;
-            const uint32_t leader_pready[2] = {map_to_cta(&sm.p_ready[0], 0), map_to_cta(&sm.p_ready[1], 0)};
-            const uint32_t leader_sfree[2] = {map_to_cta(&sm.s_free[0], 0), map_to_cta(&sm.s_free[1], 0)};
+            const uint32_t leader_pready0 = map_to_cta(&sm.p_ready[0], 0), leader_sfree0 = map_to_cta(&sm.s_free[0], 0);   // [1] is 8 bytes further
             const uint32_t leader_ofree = map_to_cta(&sm.o_free, 0);
 
             float m_ref = -CUDART_INF_F;
@@ -1179,7 +731,8 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                     const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
                     const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
                     float p0, p1;
-                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
+                    const bool poly = (POLY == 2 && c == 6) || (POLY == 4 && (c == 2 || c == 10)) || (POLY == 6 && (c == 2 || c == 6 || c == 12)) ||
+                                      (POLY == 8 && (c & 2));
                     if (poly) {
                         exp2_poly_x2(t2, p0, p1);
                     } else {
@@ -1211,7 +764,7 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 tmem_wait_ld();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_sfree[sb]);
+                if (lane == 0) mbar_arrive_cluster(leader_sfree0 + 8u * (uint32_t)sb);
                 if constexpr (MASKED) {
                     const int keys_left = prm.n - key_tile * TILE - COLS * half;
 #pragma unroll
@@ -1237,6 +790,23 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 }
                 const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
                 uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
+                if constexpr (PS) {
+                    // P buffer sb is read by PV(g-2), issued two tiles ago: by the time two chunks of exponentials are done it has
+                    // normally completed, so the wait costs nothing and the remaining chunks are stored as they are produced
+                    uint32_t pa[16];
+                    exp_chunk(sr, neg_ref2, acc0, acc1, pa);
+                    exp_chunk(sr + 16, neg_ref2, acc0, acc1, pa + 8);
+                    if (g >= 2) mbar_wait(&sm.pv_done[sb], (uint32_t)((g >> 1) - 1) & 1u, 310 + sb);
+                    tcgen05_fence_after();
+                    SDPA_TMEM_ST8(p_addr, pa);
+                    SDPA_TMEM_ST8(p_addr + 8, (pa + 8));
+                    uint32_t pb[8];
+                    exp_chunk(sr + 32, neg_ref2, acc0, acc1, pb);
+                    SDPA_TMEM_ST8(p_addr + 16, pb);
+                    uint32_t pc[8];
+                    exp_chunk(sr + 48, neg_ref2, acc0, acc1, pc);
+                    SDPA_TMEM_ST8(p_addr + 24, pc);
+                } else {
                 uint32_t pr[COLS / 2];
 #pragma unroll
                 for (int ch = 0; ch < COLS / 16; ++ch) exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr + 8 * ch);
@@ -1244,6 +814,7 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 tcgen05_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < COLS / 16; ++ch) SDPA_TMEM_ST8(p_addr + 8 * ch, (pr + 8 * ch));
+                }
                 float a0, a1, a2, a3;
                 unpack_f32x2(acc0, a0, a1);
                 unpack_f32x2(acc1, a2, a3);
@@ -1256,7 +827,7 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 tmem_wait_st();
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_pready[sb]);
+                if (lane == 0) mbar_arrive_cluster(leader_pready0 + 8u * (uint32_t)sb);
             };
 
             SegCursor cur;
@@ -1423,7 +994,7 @@ sdpa_status umma_plan_bind_kv(UmmaPlan* plan, const __nv_bfloat16* K, const __nv
     plan->dv = dv;
     plan->hl = hl;
     plan->general = !(dk == HEAD && dv == HEAD && hl == 1) || force_general();
-    if (plan->general) {
+    {   // the general kernel's maps are bound for every shape: its exact variant is the repair twin of v7 / v8 too
         for (int slot = 0; slot < 2; ++slot) {
             SDPA_TRY(encode_map(&plan->gmaps[slot][2], K, n, 64, dk));
             SDPA_TRY(encode_map(&plan->gmaps[slot][3], K + (hl == 2 ? k_lo_off : 0), n, 64, dk));
@@ -1450,7 +1021,7 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
         return SDPA_ERR_INVALID;
     }
     if (plan->q_bound[slot] && plan->q_base[slot] == Q && plan->q_rows[slot] == rows_capacity) return SDPA_OK;
-    if (plan->general) {
+    {
         SDPA_TRY(encode_map(&plan->gmaps[slot][0], Q, rows_capacity, TILE, dk));
         SDPA_TRY(encode_map(&plan->gmaps[slot][1], Q + (hl == 2 ? q_lo_off : 0), rows_capacity, TILE, dk));
     }
@@ -1468,18 +1039,13 @@ static bool trace_env_set()
 }
 
 // Kernel generation: v7 (cluster of two 128-row CTAs, 2-CTA MMA) unless SDPA_UMMA_V7=0 asks for v5.
-static bool use_v7()
-{
-    const char* e7 = getenv("SDPA_UMMA_V7");
-    return e7 ? (*e7 != '0') : true;
-}
 
-// Persistent kernel (EXPERIMENTAL, SDPA_UMMA_V8=1): its work map for (rows, n) on sm_count SMs, or false when the shape
+// Persistent kernel: its work map for (rows, n) on sm_count SMs, or false when the shape
 // does not suit it (too little work per cluster, or more pieces per row block than the merge takes).
 static bool v8_work_map(int rows, int n, int sm_count, WorkMap* wm, int* max_pieces)
 {
-    const char* e = getenv("SDPA_UMMA_V8");
-    if (!(e && *e == '1') || rows <= 0 || n <= 0) return false;
+    const char* e = getenv("SDPA_UMMA_V8");   // SDPA_UMMA_V8=0: always the plain-grid kernel (v7)
+    if ((e && *e == '0') || rows <= 0 || n <= 0) return false;
     WorkMap w;
     w.T = ceil_div(n, TILE);
     w.RB = ceil_div(rows, 2 * TILE);
@@ -1517,7 +1083,7 @@ bool umma_plan_last_v8(const UmmaPlan* plan, WorkMap* wm, int* max_pieces, const
 
 int attn_umma_pick_splits(int rows, int n, int sm_count)
 {
-    const int row_blocks = use_v7() ? 2 * ceil_div(ceil_div(rows, TILE), 2) : ceil_div(rows, BLOCK_ROWS);
+    const int row_blocks = 2 * ceil_div(ceil_div(rows, TILE), 2);   // 128-row CTAs in clusters of two
     const int tiles = ceil_div(n, TILE);
     if (row_blocks <= 0 || tiles <= 1) return 1;
     // choose the split count (<= 64, >= 4 key tiles each) with the best wave efficiency of the
@@ -1585,26 +1151,15 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         L.exact = true;
         return launch_attn_umma_general(L, stream);
     }
-    const size_t smem_bytes = sizeof(SharedStorage) + 1024;
     int dev = 0;
     SDPA_CUDA_TRY(cudaGetDevice(&dev));
-    // developer knobs: SDPA_UMMA_POLY=0|4|8 exponentials of every 16 on the FMA pipe; SDPA_UMMA_SAFE=1 forces the safe kernel
+    // developer knobs: SDPA_UMMA_POLY = exponentials of every 16 on the FMA pipe; SDPA_UMMA_SAFE=1 runs the exact variant alone
     const char* env_poly = getenv("SDPA_UMMA_POLY");
     int poly = env_poly ? atoi(env_poly) : kDefaultPoly;
     if (poly != 0 && poly != 4 && poly != 8) poly = kDefaultPoly;
-    const char* env_chunk = getenv("SDPA_UMMA_CHUNK");
-    const bool chunked = !(env_chunk && *env_chunk == '0');
     const char* env_safe = getenv("SDPA_UMMA_SAFE");
     const bool force_safe = env_safe && *env_safe == '1';
     if (dev < 64 && !plan->attr_set[dev]) {
-        const int sb = (int)smem_bytes;
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<false, false, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel<true, false, kDefaultPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb));
         const int sb7 = (int)(sizeof(SharedV7) + 1024);
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
@@ -1633,14 +1188,12 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.guard = plan->guard;
     prm.epoch = ++plan->epoch;
     if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
-    dim3 grid(ceil_div(rows, BLOCK_ROWS), splits);                      // v5 / SAFE: 256 rows per CTA
-    const bool v7 = use_v7();   // the 2-CTA kernel is the default; SDPA_UMMA_V7=0 selects v5
     const char* env_groups = getenv("SDPA_UMMA_GROUPS");   // v7: softmax groups ping-ponged over key tiles (1 or 2)
     const bool groups2 = env_groups ? (atoi(env_groups) == 2) : true;
     const size_t smem7 = sizeof(SharedV7) + 1024;
     dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v7: 128 rows per CTA, clusters of two along x
     // persistent kernel: only when the engine announced that it merges by pieces, no direct fp64 output, and the caller's
-    // split count is the map's piece count (the SAFE twin behind it then fills every partial slot the merge may read)
+    // split count is the map's piece count (the exact twin behind it then fills every partial slot the merge may read)
     WorkMap wm8{0, 0, 0};
     int pieces8 = 0;
     const bool use_v8 = plan->allow_v8 && out64 == nullptr && !force_safe && !(trace_env_set()) &&
@@ -1653,9 +1206,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
         SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
         prm.trace = dtrace;
-        if (v7 && groups2) attn_umma_kernel_v7<true, 4, 2, 2><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (v7) attn_umma_kernel_v7<true, 4, 2, 1><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else attn_umma_kernel<true, false, kDefaultPoly><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        if (groups2) attn_umma_kernel_v7<true, 4, 2, 2><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        else attn_umma_kernel_v7<true, 4, 2, 1><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
         std::vector<long long> host(count);
         SDPA_CUDA_TRY(cudaMemcpyAsync(host.data(), dtrace, count * sizeof(long long), cudaMemcpyDeviceToHost, stream));
@@ -1677,20 +1229,38 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     } else if (use_v8) {
         const int dev8 = dev;
         const size_t smem8 = sizeof(SharedV8) + 1024;
-        if (dev8 < 64 && !plan->attr8_set[dev8]) {
-            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            plan->attr8_set[dev8] = true;
-        }
+        // developer knobs: SDPA_UMMA_POLY (0|2|4|6 of 16 exponentials on the FMA pipe), SDPA_V8_OPT bit 0 = V producer warp,
+        // bit 1 = progressive P stores
+        const char* env_opt = getenv("SDPA_V8_OPT");
+        const int opt = env_opt ? (atoi(env_opt) & 3) : kDefaultV8Opt;
+        const int poly8 = env_poly ? atoi(env_poly) : kDefaultV8Poly;
         prm.wm = wm8;
         const dim3 grid8(2 * wm8.C, 1);
-        if (poly == 4) attn_umma_kernel_v8<4><<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else attn_umma_kernel_v8<0><<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+#define SDPA_V8_CASE(P, VW, PS)                                                                                                 \
+    {                                                                                                                          \
+        static bool attr_done[64] = {};                                                                                        \
+        if (dev8 < 64 && !attr_done[dev8]) {                                                                                   \
+            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8<P, VW, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8)); \
+            attr_done[dev8] = true;                                                                                            \
+        }                                                                                                                      \
+        attn_umma_kernel_v8<P, VW, PS><<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm); \
+    }
+#define SDPA_V8_POLY(VW, PS)                                   \
+    if (poly8 == 2) SDPA_V8_CASE(2, VW, PS)                    \
+    else if (poly8 == 4) SDPA_V8_CASE(4, VW, PS)               \
+    else if (poly8 == 6) SDPA_V8_CASE(6, VW, PS)               \
+    else SDPA_V8_CASE(0, VW, PS)
+        if (opt == 3) { SDPA_V8_POLY(true, true) }
+        else if (opt == 2) { SDPA_V8_POLY(false, true) }
+        else if (opt == 1) { SDPA_V8_POLY(true, false) }
+        else { SDPA_V8_POLY(false, false) }
+#undef SDPA_V8_POLY
+#undef SDPA_V8_CASE
         count_launch();
         plan->last_v8 = true;
         plan->last_wm = wm8;
         plan->last_pieces = pieces8;
-    } else if (v7) {
+    } else {
 #define SDPA_LAUNCH_V7(P, G) attn_umma_kernel_v7<false, P, 2, G><<<grid6, 128 + 256 * G, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
         if (!groups2) SDPA_LAUNCH_V7(4, 1);
         else if (poly == 0) SDPA_LAUNCH_V7(0, 2);
@@ -1698,19 +1268,24 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         else SDPA_LAUNCH_V7(4, 2);
 #undef SDPA_LAUNCH_V7
         count_launch();
-    } else {
-        if (!chunked && poly == 0) attn_umma_kernel<false, false, 0, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (!chunked) attn_umma_kernel<false, false, 4, false><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (poly == 0) attn_umma_kernel<false, false, 0><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else if (poly == 8) attn_umma_kernel<false, false, 8><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else attn_umma_kernel<false, false, 4><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        count_launch();
     }
-    // the safe variant: leaves immediately unless the guard was raised for this epoch
-    attn_umma_kernel<false, true, 0><<<grid, NTHREADS, smem_bytes, stream>>>(plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
-    return SDPA_OK;
+    // the exact variant of the general kernel: leaves immediately unless the guard was raised for this epoch; it writes the
+    // same (split, row) partial slots / the same fp64 rows as the fast kernel it repairs
+    GeneralLaunch L;
+    L.rows = rows;
+    L.n = plan->n;
+    L.dk = HEAD;
+    L.dv = HEAD;
+    L.hl = 1;
+    L.splits = splits;
+    L.exact = true;
+    L.part = part;
+    L.out64 = out64;
+    L.guard = plan->guard;
+    L.epoch = prm.epoch;
+    L.maps = plan->gmaps[q_slot];
+    return launch_attn_umma_general(L, stream);
 }
 
 }  // namespace sdpa

@@ -119,21 +119,24 @@ sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* co
 
 // ---- device-side exchange across processes (CUDA IPC peer memory + flags in device memory) ----------
 // A flag holds the epoch (global batch counter) of the last completed step.
-sdpa_status launch_signal_flag(unsigned int* flag, unsigned int epoch, cudaStream_t stream);       // release-store after prior work
+sdpa_status launch_signal_flag(unsigned int* flag, unsigned int epoch, cudaStream_t stream,
+                               unsigned long long* trace = nullptr);                                // release-store after prior work
 sdpa_status launch_wait_flag(const unsigned int* flag, unsigned int epoch, cudaStream_t stream);   // spin until *flag >= epoch
 struct PeerSync {
     const unsigned int* ready[64];   // per shard: its "state of epoch e is complete" flag (local or IPC-mapped)
     unsigned int* consumed;          // root-local: set to epoch once every block has merged (peers poll it before reuse)
     unsigned int* block_counter;     // root-local scratch
     unsigned int epoch;
+    unsigned long long* trace = nullptr;   // SDPA_EXCHANGE_TRACE: 4 x u64 of this epoch (see merge_kernels.cu)
 };
 // Root GPU: wait for every shard's flag, merge their (contrib,tmax,lsum) read through peer pointers, write fp64.
 sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
                                       const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
                                       const PeerSync& sync, cudaStream_t stream);
 // Split merge behind the persistent fused kernel: per row, wm_pieces(row block) states (all max_pieces if *guard == epoch).
-sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64,
-                                const unsigned int* guard, unsigned int epoch, cudaStream_t stream);
+// out64 != NULL: normalised fp64 rows; else the merged un-normalised state (contrib, tmax, lsum) for the cross-GPU merge.
+sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64, float* contrib,
+                                float* tmax_out, float* lsum_out, const unsigned int* guard, unsigned int epoch, cudaStream_t stream);
 // Sliced merge, source side: merge the split states of `rows` rows and write each row's state into the inbox segment of
 // the rank owning its slice (slice r = rows/world + (r < rows%world) consecutive rows), then raise flag[r] = epoch at every rank.
 struct RouteTargets {

@@ -220,6 +220,9 @@ struct sdpa_ctx {
         std::vector<void*> opened;      // IPC mappings to close
         unsigned int epoch = 0;         // global batch counter, identical on every rank
         unsigned int slot_epoch[2] = {0, 0};
+        DevBuf trace;                   // SDPA_EXCHANGE_TRACE=<path>: kTraceEpochs x 4 u64 %globaltimer stamps, dumped to <path>.rank<r>
+        static constexpr unsigned int kTraceEpochs = 4096;
+        unsigned long long* trace_slot(unsigned int e) { return trace.p ? trace.as<unsigned long long>() + (size_t)(e % kTraceEpochs) * 4 : nullptr; }
     } ipc;
     bool has_root() const { return rank_base == 0; }
 };
@@ -333,8 +336,9 @@ static int resolve_precision(int requested, int dk, int dv)
 static sdpa_status check_precision(int prec, int dk, int dv)
 {
     if (is_umma(prec) && !attn_umma_supported(dk, dv, prec_hl(prec))) {
-        set_error("%s tensor-core kernel: dk and dv must be multiples of 8 up to %d (got dk=%d dv=%d)",
-                  prec == SDPA_PREC_BF16X3 ? "bf16x3" : "bf16", prec == SDPA_PREC_BF16X3 ? 128 : 256, dk, dv);
+        set_error("%s tensor-core kernel: dk and dv must be multiples of 8, %s (got dk=%d dv=%d)",
+                  prec == SDPA_PREC_BF16X3 ? "bf16x3" : "bf16",
+                  prec == SDPA_PREC_BF16X3 ? "dk <= 128 and dv <= 128, or dk <= 64 and dv <= 256" : "up to 256", dk, dv);
         return SDPA_ERR_UNSUPPORTED;
     }
     if (prec == SDPA_PREC_F32 && !attn_f32_supported(dk, dv)) {
@@ -564,6 +568,12 @@ static sdpa_status drain_exchange(sdpa_ctx* ctx)
     return SDPA_OK;
 }
 
+static bool ipc_sliced_requested()
+{
+    const char* mode = getenv("SDPA_IPC_MERGE");
+    return mode && !strcmp(mode, "sliced");
+}
+
 static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
 {
     sdpa_ctx::Ipc& x = ctx->ipc;
@@ -593,13 +603,16 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
     if (!x.flags.p) {
         SDPA_TRY(x.flags.reserve(4096));
         SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 4096));
+        if (const char* tp = getenv("SDPA_EXCHANGE_TRACE"); tp && *tp) {
+            SDPA_TRY(x.trace.reserve((size_t)sdpa_ctx::Ipc::kTraceEpochs * 4 * sizeof(unsigned long long)));
+            SDPA_CUDA_TRY(cudaMemset(x.trace.p, 0, x.trace.bytes));
+        }
         x.epoch = 0;
         x.slot_epoch[0] = x.slot_epoch[1] = 0;
         // "root" (default): the root GPU merges every row, reading the states over NVLink; "sliced": every rank merges its
         // share of the rows from an inbox the others push into.  Measured equal at 8 GPUs (0.354 vs 0.356 ms per c3 step) and
         // the root form ahead at 2 (0.308 vs 0.331 ms): the exchange is bound by its flag hops, not by the root's ingress.
-        const char* mode = getenv("SDPA_IPC_MERGE");
-        x.sliced = mode && !strcmp(mode, "sliced");
+        x.sliced = ipc_sliced_requested();
     }
     struct Handles { cudaIpcMemHandle_t x0, x1, fl, s0, s1; };
     Handles mine;
@@ -724,10 +737,13 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                     : attn_f32_pick_splits(B, nmax, ctx->shards[0].sm_count);
     }
     splits = std::max(1, std::min(splits, 64));
-    // EXPERIMENTAL (SDPA_UMMA_V8=1, single GPU): the persistent fused kernel cuts every row block into pieces; its piece
-    // count replaces the split count and the merge reads pieces per row block (launch_merge_pieces).
+    // The persistent fused kernel (dk = dv = 128 bf16, enough work per SM pair) cuts every row block into pieces; its piece
+    // count replaces the split count and the split merge reads pieces per row block (launch_merge_pieces).  Every shard must
+    // own the same number of keys (the partial buffers and the piece count are shared); the sliced exchange routes by splits.
     bool by_pieces = false;
-    if (world == 1 && ctx->prec == SDPA_PREC_BF16 && dk == 128 && dv == 128 && ctx->cfg.kv_splits <= 0 && num_iter == 1) {
+    bool same_n = true;
+    for (Shard& s : ctx->shards) same_n = same_n && s.n_local == ctx->shards[0].n_local;
+    if (ctx->prec == SDPA_PREC_BF16 && dk == 128 && dv == 128 && ctx->cfg.kv_splits <= 0 && same_n && !(use_ipc && ipc_sliced_requested())) {
         const int pieces = attn_umma_v8_pieces(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
         if (pieces > 1) {
             splits = pieces;
@@ -839,11 +855,15 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 int max_pieces = 0;
                 const unsigned int* guard = nullptr;
                 unsigned int guard_epoch = 0;
-                if (single && by_pieces && umma_plan_last_v8(s.plan, &wm, &max_pieces, &guard, &guard_epoch)) {
-                    SDPA_TRY(launch_merge_pieces(part, wm, max_pieces, bs, dv, final_dst, guard, guard_epoch, s.s_compute));
-                    ctx->last_kernel = "bf16_umma_v8";
-                } else if (single) {
-                    SDPA_TRY(launch_merge_splits(part, bs, dv, final_dst, nullptr, nullptr, nullptr, false, s.s_compute));
+                const bool pieces = by_pieces && umma_plan_last_v8(s.plan, &wm, &max_pieces, &guard, &guard_epoch);
+                if (pieces) ctx->last_kernel = "bf16_umma_v8";
+                // the shard's own partial states -> one state: normalised fp64 rows (single GPU) or (contrib, tmax, lsum)
+                auto merge_local = [&](double* out64, float* c, float* t, float* l) -> sdpa_status {
+                    if (pieces) return launch_merge_pieces(part, wm, max_pieces, bs, dv, out64, c, t, l, guard, guard_epoch, s.s_compute);
+                    return launch_merge_splits(part, bs, dv, out64, c, t, l, false, s.s_compute);
+                };
+                if (single) {
+                    SDPA_TRY(merge_local(final_dst, nullptr, nullptr, nullptr));
                 } else {
                     if (use_ipc) {
                         // publish this shard's state in its IPC-shared slot, then raise the epoch flag
@@ -870,14 +890,13 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                             to.world = world;
                             SDPA_TRY(launch_merge_splits_routed(part, bs, dv, to, s.s_compute));
                         } else {
-                            SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, xc, xt, xl, false, s.s_compute));
-                            SDPA_TRY(launch_signal_flag(x.flags.as<unsigned int>() + b, x.epoch, s.s_compute));
+                            SDPA_TRY(merge_local(nullptr, xc, xt, xl));
+                            SDPA_TRY(launch_signal_flag(x.flags.as<unsigned int>() + b, x.epoch, s.s_compute, x.trace_slot(x.epoch)));
                         }
                         x.slot_epoch[b] = x.epoch;
                     } else {
                     float* lsum_dst = (two_coll && !use_peer) ? s.contrib[b].as<float>() + (size_t)bs * dv : s.lsum[b].as<float>();
-                    SDPA_TRY(launch_merge_splits(part, bs, dv, nullptr, s.contrib[b].as<float>(), s.tmax[b].as<float>(),
-                                                 lsum_dst, false, s.s_compute));
+                    SDPA_TRY(merge_local(nullptr, s.contrib[b].as<float>(), s.tmax[b].as<float>(), lsum_dst));
                     }
                 }
                 SDPA_TRY(time_end(s, 2, s.s_compute));
@@ -945,6 +964,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 sync.consumed = x.flags.as<unsigned int>() + 2 + b;
                 sync.block_counter = x.flags.as<unsigned int>() + 4 + b;
                 sync.epoch = x.epoch;
+                sync.trace = x.trace_slot(x.epoch);
                 double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
                 SDPA_TRY(time_begin(s, 2, s.s_comm));
                 SDPA_TRY(launch_merge_peers_synced(cp, tp, lp, world, bs, dv, dst, sync, s.s_comm));
@@ -1514,6 +1534,22 @@ sdpa_status sdpa_ctx_destroy(sdpa_ctx* ctx)
         drain_exchange(ctx);
         cudaSetDevice(ctx->shards[0].dev);
         cudaDeviceSynchronize();
+        if (ctx->ipc.trace.p) {   // developer aid: dump the exchange timeline of this rank
+            const char* tp = getenv("SDPA_EXCHANGE_TRACE");
+            std::vector<unsigned long long> host((size_t)sdpa_ctx::Ipc::kTraceEpochs * 4);
+            if (tp && cudaMemcpy(host.data(), ctx->ipc.trace.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+                char path[1024];
+                snprintf(path, sizeof(path), "%s.rank%d", tp, ctx->rank_base);
+                if (FILE* f = fopen(path, "w")) {
+                    fprintf(f, "epoch published_ns merge_begin_ns flags_seen_ns merge_done_ns   (last epoch %u)\n", ctx->ipc.epoch);
+                    for (unsigned int e = 0; e < sdpa_ctx::Ipc::kTraceEpochs; ++e)
+                        if (host[e * 4] || host[e * 4 + 1])
+                            fprintf(f, "%u %llu %llu %llu %llu\n", e, host[e * 4], host[e * 4 + 1], host[e * 4 + 2], host[e * 4 + 3]);
+                    fclose(f);
+                }
+            }
+            ctx->ipc.trace.release();
+        }
         ipc_close(ctx);
         ctx->ipc.xbuf[0].release();
         ctx->ipc.xbuf[1].release();

@@ -50,10 +50,19 @@ __device__ __forceinline__ void spin_until(const unsigned int* flag, unsigned in
     }
 }
 
-__global__ void signal_flag_kernel(unsigned int* flag, unsigned int epoch)
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// trace (SDPA_EXCHANGE_TRACE, developer aid): 4 x u64 per epoch -- [0] this rank published its state, and on the root
+// [1] the merge kernel started, [2] every rank's flag had been seen, [3] the merge was complete (%globaltimer, ns).
+__global__ void signal_flag_kernel(unsigned int* flag, unsigned int epoch, unsigned long long* trace)
 {
     __threadfence_system();   // everything this GPU wrote before (earlier kernels on the stream) is visible system-wide
     st_release_sys(flag, epoch);
+    if (trace) trace[0] = global_ns();
 }
 __global__ void wait_flag_kernel(const unsigned int* flag, unsigned int epoch) { spin_until(flag, epoch, 1); }
 
@@ -72,6 +81,7 @@ struct SyncArgs {
     unsigned int* block_counter;
     unsigned int epoch;
     int enabled;
+    unsigned long long* trace;
 };
 
 template <bool FINAL>
@@ -82,8 +92,10 @@ merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restric
 {
     if (sync.enabled) {
         // fused exchange: the states live on other GPUs; wait until each of them has published this epoch
+        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[1] = global_ns();
         if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.epoch, 2);
         __syncthreads();
+        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[2] = global_ns();
     }
     merge_rows<FINAL>(st, count, rows, dv, out64, contrib, tmax_out, lsum_out, max_unit, vec_ok);
     if (sync.enabled) {
@@ -96,6 +108,7 @@ merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restric
                 // root merge: every block has read the peers' buffers, they may be reused;
                 // sliced merge: this rank's rows of the result are in the root's staging buffer
                 st_release_sys(sync.consumed, sync.epoch);
+                if (sync.trace) sync.trace[3] = global_ns();
             }
         }
     }
@@ -260,14 +273,17 @@ merge_route_kernel(StatePtrs st, int count, int rows, int dv, RouteArgs rt, bool
 // Split merge behind the persistent fused kernel (attn_umma_kernel_v8): the number of partial states of a row is the
 // number of pieces its row block was cut into (wm_pieces), unless the overflow guard handed the launch to the SAFE
 // kernel, which fills all `max_pieces` slots with equal splits.
+template <bool FINAL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-merge_pieces_kernel(StatePtrs st, WorkMap wm, int max_pieces, int rows, int dv, double* __restrict__ out64, bool vec_ok,
-                    const unsigned int* __restrict__ guard, unsigned int epoch)
+merge_pieces_kernel(StatePtrs st, WorkMap wm, int max_pieces, int rows, int dv, double* __restrict__ out64, float* __restrict__ contrib,
+                    float* __restrict__ tmax_out, float* __restrict__ lsum_out, bool vec_ok, const unsigned int* __restrict__ guard,
+                    unsigned int epoch)
 {
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int count = (*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256);
-    merge_one_row<true>(st, count, row, dv, out64 + (size_t)row * dv, nullptr, nullptr, nullptr, 1.f, vec_ok);
+    merge_one_row<FINAL>(st, count, row, dv, FINAL ? out64 + (size_t)row * dv : nullptr, FINAL ? nullptr : contrib + (size_t)row * dv,
+                         FINAL ? nullptr : tmax_out + row, FINAL ? nullptr : lsum_out + row, 1.f, vec_ok);
 }
 
 // Root GPU, sliced merge: wait until every rank has delivered its rows of the batch into the staging buffer,
@@ -378,6 +394,7 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     sa.block_counter = sync.block_counter;
     sa.epoch = sync.epoch;
     sa.enabled = 1;
+    sa.trace = sync.trace;
     const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     bool vec_ok = al16(out64);
     for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
@@ -388,24 +405,27 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     return SDPA_OK;
 }
 
-sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64,
-                                const unsigned int* guard, unsigned int epoch, cudaStream_t stream)
+sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64, float* contrib,
+                                float* tmax_out, float* lsum_out, const unsigned int* guard, unsigned int epoch, cudaStream_t stream)
 {
     if (rows <= 0) return SDPA_OK;
-    if (max_pieces < 1 || max_pieces > 64 || max_pieces > part.splits || !out64 || !guard) {
+    if (max_pieces < 1 || max_pieces > 64 || max_pieces > part.splits || !guard || (!out64 && !(contrib && tmax_out && lsum_out))) {
         set_error("merge_pieces: bad arguments (pieces=%d, partial slots=%d)", max_pieces, part.splits);
         return SDPA_ERR_INVALID;
     }
     StatePtrs st;
-    bool vec_ok = al16(out64);
+    bool vec_ok = al16(out64) && al16(contrib);
     for (int s = 0; s < max_pieces; ++s) {
         st.o[s] = part.o + (size_t)s * part.rows_capacity * dv;
         st.tmax[s] = part.tmax + (size_t)s * part.rows_capacity;
         st.lsum[s] = part.lsum + (size_t)s * part.rows_capacity;
         vec_ok = vec_ok && al16(st.o[s]);
     }
-    merge_pieces_kernel<<<ceil_div(rows, kWarpsPerBlock), kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, vec_ok,
-                                                                                          guard, epoch);
+    const int blocks = ceil_div(rows, kWarpsPerBlock);
+    if (out64) merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr,
+                                                                                    vec_ok, guard, epoch);
+    else merge_pieces_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, nullptr, contrib, tmax_out, lsum_out,
+                                                                               vec_ok, guard, epoch);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
@@ -472,9 +492,9 @@ sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, i
     return SDPA_OK;
 }
 
-sdpa_status launch_signal_flag(unsigned int* flag, unsigned int epoch, cudaStream_t stream)
+sdpa_status launch_signal_flag(unsigned int* flag, unsigned int epoch, cudaStream_t stream, unsigned long long* trace)
 {
-    signal_flag_kernel<<<1, 1, 0, stream>>>(flag, epoch);
+    signal_flag_kernel<<<1, 1, 0, stream>>>(flag, epoch, trace);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;

@@ -99,8 +99,8 @@ def test_golden_cases_on_tensor_cores(sdpa, oracle, golden):
 
 def test_auto_precision_keeps_the_reference_accuracy(sdpa, oracle):
     """AUTO never selects plain bf16: split precision on tensor cores where the shape allows, else the fp32 kernel."""
-    for (dk, dv), kernel in (((128, 128), "bf16x3_umma"), ((80, 80), "bf16x3_umma"), ((200, 64), "f32_simt"), ((100, 100), "f32_simt"),
-                             ((64, 256), "f32_simt")):
+    for (dk, dv), kernel in (((128, 128), "bf16x3_umma"), ((80, 80), "bf16x3_umma"), ((64, 256), "bf16x3_umma"), ((200, 64), "f32_simt"),
+                             ((100, 100), "f32_simt"), ((128, 256), "f32_simt")):
         Q, K, V = oracle.make_inputs(64, 200, dk, dv, seed=dk + dv)
         got = _run(sdpa, Q, K, V, "auto", kernel)
         np.testing.assert_allclose(got, oracle.attention_f64_numpy(Q, K, V), rtol=0, atol=X3_ATOL)
@@ -110,7 +110,7 @@ def test_auto_precision_keeps_the_reference_accuracy(sdpa, oracle):
             _run(sdpa, Q, K, V, prec)          # dk = 100: no tensor-core kernel, and no silent fallback
     Q, K, V = oracle.make_inputs(64, 128, 200, 64, seed=2)
     with pytest.raises(sdpa.SdpaError):
-        _run(sdpa, Q, K, V, "bf16x3")          # split precision stops at 128
+        _run(sdpa, Q, K, V, "bf16x3")          # split precision: dk <= 128 (and dv <= 128, or dk <= 64 with dv <= 256)
     _run(sdpa, Q, K, V, "bf16", "bf16_umma_general")
 
 
