@@ -102,6 +102,9 @@ void attention(double* Q, double* K, double* V, double* result,
  * keeps outside its timed region (mpi.c:519-522).  Optional. */
 sdpa_status sdpa_runtime_init(int mpi_rank, int mpi_size);
 void sdpa_runtime_shutdown(void);
+/* MAX over all ranks of *value, in place on every rank: the reference reports the slowest rank's elapsed time
+ * (MPI_Reduce(MAX), mpi.c:524).  Uses the communicator of the runtime context; identity when mpi_size == 1. */
+sdpa_status sdpa_runtime_max(double* value);
 
 /* ---------------------------------------------------------------------------
  * 2. Shard map (replaces owner_count / owner_disp, mpi.c:19-27): balanced

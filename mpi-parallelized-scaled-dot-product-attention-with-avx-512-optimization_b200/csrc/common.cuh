@@ -122,6 +122,7 @@ sdpa_status launch_merge_peers(const float* const* contrib_ptrs, const float* co
 sdpa_status launch_signal_flag(unsigned int* flag, unsigned int epoch, cudaStream_t stream,
                                unsigned long long* trace = nullptr);                                // release-store after prior work
 sdpa_status launch_wait_flag(const unsigned int* flag, unsigned int epoch, cudaStream_t stream);   // spin until *flag >= epoch
+sdpa_status set_flag_timeout_seconds(double seconds);   // bound of those spins on the current device (default 120 s)
 struct PeerSync {
     const unsigned int* ready[64];   // per shard: its "state of epoch e is complete" flag (local or IPC-mapped)
     unsigned int* consumed;          // root-local: set to epoch once every block has merged (peers poll it before reuse)

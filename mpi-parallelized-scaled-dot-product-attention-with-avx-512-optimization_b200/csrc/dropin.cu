@@ -194,6 +194,17 @@ sdpa_status sdpa_runtime_init(int mpi_rank, int mpi_size)
     return SDPA_OK;
 }
 
+sdpa_status sdpa_ctx_max(sdpa_ctx* ctx, double* value);
+
+sdpa_status sdpa_runtime_max(double* value)
+{
+    if (!g_cached.ctx) {
+        set_error("sdpa_runtime_max: no runtime context (call sdpa_runtime_init or attention first)");
+        return SDPA_ERR_INVALID;
+    }
+    return sdpa_ctx_max(g_cached.ctx, value);
+}
+
 void sdpa_runtime_shutdown(void)
 {
     if (g_cached.ctx) sdpa_ctx_destroy(g_cached.ctx);

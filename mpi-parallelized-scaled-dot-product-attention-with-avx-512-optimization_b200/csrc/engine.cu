@@ -603,6 +603,7 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
     if (!x.flags.p) {
         SDPA_TRY(x.flags.reserve(4096));
         SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 4096));
+        if (const char* ts = getenv("SDPA_FLAG_TIMEOUT_S"); ts && atof(ts) > 0.0) SDPA_TRY(set_flag_timeout_seconds(atof(ts)));
         if (const char* tp = getenv("SDPA_EXCHANGE_TRACE"); tp && *tp) {
             SDPA_TRY(x.trace.reserve((size_t)sdpa_ctx::Ipc::kTraceEpochs * 4 * sizeof(unsigned long long)));
             SDPA_CUDA_TRY(cudaMemset(x.trace.p, 0, x.trace.bytes));
@@ -1327,20 +1328,18 @@ static sdpa_status scatter_attention_impl(sdpa_ctx* ctx, const double* Q, const 
     if (!api) return SDPA_ERR_NCCL;
     Shard& s = ctx->shards[0];
     SDPA_CUDA_TRY(cudaSetDevice(s.dev));
-    // dims from rank 0 (mpi.c:193-197)
-    int dims[4] = {m, n, dk, dv};
+    // dims from rank 0 (mpi.c:193-197), together with rank 0's verdict on its own arguments: every rank leaves with the same
+    // error instead of the others blocking in a receive that rank 0 never posts
+    int dims[5] = {m, n, dk, dv, 1};
+    if (s.grank == 0 && (m < 0 || n < 0 || dk < 1 || dv < 1 || (n > 0 && (!K || !V)) || (m > 0 && (!Q || !result)))) dims[4] = 0;
     SDPA_TRY(s.gmax[0].reserve(256));
     if (s.grank == 0) SDPA_CUDA_TRY(cudaMemcpyAsync(s.gmax[0].p, dims, sizeof(dims), cudaMemcpyHostToDevice, s.s_compute));
-    SDPA_NCCL_TRY(api->Broadcast(s.gmax[0].p, s.gmax[0].p, 4, ncclInt32, 0, s.comm, s.s_compute));
+    SDPA_NCCL_TRY(api->Broadcast(s.gmax[0].p, s.gmax[0].p, 5, ncclInt32, 0, s.comm, s.s_compute));
     SDPA_CUDA_TRY(cudaMemcpyAsync(dims, s.gmax[0].p, sizeof(dims), cudaMemcpyDeviceToHost, s.s_compute));
     SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
     m = dims[0]; n = dims[1]; dk = dims[2]; dv = dims[3];
-    if (m < 0 || n < 0 || dk < 1 || dv < 1) {
-        set_error("attention(): bad dimensions m=%d n=%d dk=%d dv=%d", m, n, dk, dv);
-        return SDPA_ERR_INVALID;
-    }
-    if (s.grank == 0 && ((n > 0 && (!K || !V)) || (m > 0 && (!Q || !result)))) {
-        set_error("attention(): NULL input on rank 0");
+    if (!dims[4]) {
+        set_error("attention(): bad dimensions or NULL input on rank 0 (m=%d n=%d dk=%d dv=%d)", m, n, dk, dv);
         return SDPA_ERR_INVALID;
     }
     const int prec = resolve_precision(ctx->cfg.precision, dk, dv);
@@ -1743,6 +1742,30 @@ sdpa_status sdpa_accumulated_timings(sdpa_ctx* ctx, double* out6, int reset)
 }
 
 const char* sdpa_last_kernel(sdpa_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+
+/* MAX of a double over every process of the context (mpi.c:524); collective. */
+sdpa_status sdpa_ctx_max(sdpa_ctx* ctx, double* value)
+{
+    if (!ctx || !value) {
+        set_error("sdpa_ctx_max: bad arguments");
+        return SDPA_ERR_INVALID;
+    }
+    if (ctx->world == (int)ctx->shards.size()) return SDPA_OK;   // one process: nothing to reduce over
+    const NcclApi* api = nccl_api();
+    if (!api) return SDPA_ERR_NCCL;
+    Shard& s = ctx->shards[0];
+    if (!s.comm) {
+        set_error("sdpa_ctx_max: the context has no communicator");
+        return SDPA_ERR_INVALID;
+    }
+    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    SDPA_TRY(s.gsum[0].reserve(256));
+    SDPA_CUDA_TRY(cudaMemcpyAsync(s.gsum[0].p, value, sizeof(double), cudaMemcpyHostToDevice, s.s_comm));
+    SDPA_NCCL_TRY(api->AllReduce(s.gsum[0].p, s.gsum[0].p, 1, ncclFloat64, ncclMax, s.comm, s.s_comm));
+    SDPA_CUDA_TRY(cudaMemcpyAsync(value, s.gsum[0].p, sizeof(double), cudaMemcpyDeviceToHost, s.s_comm));
+    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_comm));
+    return SDPA_OK;
+}
 
 unsigned long long sdpa_launch_count(void) { return sdpa::launch_count(); }
 

@@ -122,7 +122,11 @@ int main(int argc, char** argv)
     clock_gettime(CLOCK_MONOTONIC, &t0);
     attention(Q, K, V, result, m, n, dk, dv, rank, size);
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    const double us = (double)(t1.tv_sec - t0.tv_sec) * 1e6 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-3;
+    double us = (double)(t1.tv_sec - t0.tv_sec) * 1e6 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-3;
+    if (size > 1 && sdpa_runtime_max(&us) != SDPA_OK) {   /* the slowest rank's time, as MPI_Reduce(MAX) at mpi.c:524 */
+        fprintf(stderr, "sdpa_b200: %s\n", sdpa_last_error());
+        return 1;
+    }
 
     int rc = 0;
     if (rank == 0) {

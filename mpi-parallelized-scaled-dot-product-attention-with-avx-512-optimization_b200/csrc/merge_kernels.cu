@@ -37,13 +37,16 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // Bounded spin (a protocol bug traps instead of hanging the GPU).  Epochs only grow; the signed
-// difference tolerates wrap-around.
+// difference tolerates wrap-around.  The bound is generous (default 120 s, SDPA_FLAG_TIMEOUT_S): ranks of one job may be
+// seconds apart (a paused process, a first-call module load, a slow pageable upload on one rank) without that being an error.
+__device__ long long g_flag_timeout_cycles = 240000000000LL;
+
 __device__ __forceinline__ void spin_until(const unsigned int* flag, unsigned int epoch, int tag)
 {
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
         __nanosleep(200);
-        if (clock64() - t0 > 8000000000LL) {
+        if (clock64() - t0 > g_flag_timeout_cycles) {
             printf("sdpa_b200: peer flag timeout tag=%d block=%d want=%u have=%u\n", tag, blockIdx.x, epoch, ld_acquire_sys(flag));
             __trap();
         }
@@ -489,6 +492,14 @@ sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, i
                                                       units, sa, ranks);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+// Sets the spin bound of the flag waits on the current device (seconds at a nominal 2 GHz).
+sdpa_status set_flag_timeout_seconds(double seconds)
+{
+    const long long cycles = (long long)(seconds * 2.0e9);
+    SDPA_CUDA_TRY(cudaMemcpyToSymbol(g_flag_timeout_cycles, &cycles, sizeof(cycles)));
     return SDPA_OK;
 }
 

@@ -66,6 +66,7 @@ ABI = {
     "attention": (None, [_V, _V, _V, _V] + [ctypes.c_int] * 6),
     "sdpa_runtime_init": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "sdpa_runtime_shutdown": (None, []),
+    "sdpa_runtime_max": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double)]),
     "sdpa_owner_count": (ctypes.c_int, [ctypes.c_int] * 3),
     "sdpa_owner_disp": (ctypes.c_int, [ctypes.c_int] * 3),
     "sdpa_config_init": (None, [ctypes.POINTER(Config)]),

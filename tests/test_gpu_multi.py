@@ -21,7 +21,8 @@ def _need_gpus(sdpa, n):
 
 @pytest.mark.parametrize("merge", ["nccl2", "nccl3", "peer"])
 @pytest.mark.parametrize("prec,m,n,d,atol", [("f32", 300, 1001, 64, 1e-5), ("f32", 129, 3, 80, 1e-5),
-                                             ("bf16", 700, 5000, 128, 1e-2), ("bf16", 9000, 4100, 128, 1e-2)])
+                                             ("bf16", 700, 5000, 128, 1e-2), ("bf16", 9000, 4100, 128, 1e-2),
+                                             ("bf16x3", 700, 5000, 128, 1e-5), ("auto", 300, 1001, 80, 1e-5), ("bf16", 8300, 40000, 128, 1e-2)])
 def test_single_process_two_gpus(sdpa, oracle, merge, prec, m, n, d, atol):
     _need_gpus(sdpa, 2)
     Q, K, V = oracle.make_inputs(m, n, d, d, seed=m + n)
@@ -121,7 +122,7 @@ def _rank_worker(rank, world, port, out_dir, id_file):
     ref = o.attention_f64_numpy(Q, K, V) if rank == 0 else None
     first, count = parallel.shard_rows(n, world, rank)
     for prec, atol, merge in (("f32", 1e-5, "nccl2"), ("bf16", 1e-2, "nccl3"), ("bf16", 1e-2, "peer"), ("f32", 1e-5, "peer"),
-                              ("bf16", 1e-2, "peer-sliced"), ("f32", 1e-5, "peer-sliced")):
+                              ("bf16", 1e-2, "peer-sliced"), ("f32", 1e-5, "peer-sliced"), ("bf16x3", 1e-5, "peer"), ("auto", 1e-5, "nccl2")):
         # (1) pre-sharded inputs, one context per rank (bench.py's model); merge="peer" = CUDA-IPC device-side exchange
         # (the root GPU merges all rows; "peer-sliced" = every rank merges its share of the rows from a pushed inbox)
         os.environ["SDPA_IPC_MERGE"] = "sliced" if merge == "peer-sliced" else "root"
@@ -171,7 +172,6 @@ def test_one_process_per_gpu(sdpa, oracle, tmp_path):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.skipif(os.environ.get("SDPA_TEST_EXPERIMENTAL") != "1", reason="experimental path: set SDPA_TEST_EXPERIMENTAL=1")
 def test_overlapped_queued_passes(sdpa, oracle, tmp_path):
     _need_gpus(sdpa, 2)
     import torch.multiprocessing as mp

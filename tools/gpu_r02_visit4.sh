@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round-2 visit 4 (TWO GPUs): every cross-GPU test incl. the overlapped passes and the Q-sharded distribution, the bench with
+# its oracle parity check, the exchange timeline with and without pass overlap, c4's shape (m > q_batch: ping-pong batches with
+# an exchange per batch) on two GPUs.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+OUT=gpurun_out
+S=$OUT/summary_v4.log; rm -f $S $OUT/xtrace_*
+timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider --durations=5 > $OUT/v4_pytest_multi.log 2>&1
+echo "pytest multi rc=$?" >> $S
+run() { # name, env..., then bench args after --
+  local name=$1; shift
+  local envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" NCCL_DEBUG=WARN timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus 2 "$@" > $OUT/v4_$name.json 2> $OUT/v4_$name.err
+  echo "bench $name rc=$?" >> $S
+}
+run g2_default SDPA_EXCHANGE_TRACE=$OUT/xtrace_default -- --steps 20 --warmup 3
+run g2_overlap SDPA_OVERLAP_PASSES=1 SDPA_EXCHANGE_TRACE=$OUT/xtrace_overlap -- --steps 20 --warmup 3
+run g2_v7 SDPA_UMMA_V8=0 -- --steps 20 --warmup 3
+run g2_c4 X=1 -- --steps 5 --warmup 3 --extra c4
+run g2_c4_overlap SDPA_OVERLAP_PASSES=1 -- --steps 5 --warmup 3 --extra c4
+cat $S; grep -E "passed|failed" $OUT/v4_pytest_multi.log | tail -2; grep -E "^FAILED|^ERROR" $OUT/v4_pytest_multi.log | head -20
+python tools/exchange_digest.py $OUT/xtrace_default; python tools/exchange_digest.py $OUT/xtrace_overlap
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/v4_g2_*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split("/")[-1], "value", round(d["value"],1), "ms", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"],1), {k:round(v,4) for k,v in d["stage_ms_per_step"].items()}, d["impl_detail"]["kernel"], "parity", d["parity_check"]["ok"], d["parity_check"]["max_abs_err"])
+        for k,v in d.get("configs",{}).items(): print("    ", k, "value", round(v["value"],1), "ms", round(v["ms_per_step"],4), "e2e", round(v["e2e"]["value"],1), v["stage_ms_per_step"], "parity", v["parity_check"]["ok"], v["parity_check"]["max_abs_err"], "batches", v["q_batches_per_step"])
+    except Exception as e:
+        print(f, "unreadable", e); print(open(f.replace(".json",".err")).read()[-1500:])
+PY
