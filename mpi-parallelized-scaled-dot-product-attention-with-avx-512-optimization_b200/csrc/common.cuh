@@ -101,9 +101,19 @@ bool umma_plan_last_v8(const UmmaPlan* plan, WorkMap* wm, int* max_pieces, const
 //   mode FINAL   : out64[row][d] = sum_s o_s w_s / sum_s lsum_s w_s     (gsum==0 -> 0)
 //   mode PARTIAL : contrib/tmax/lsum of the merged state, un-normalised (feeds the cross-GPU merge)
 //   mode PUBLIC  : like PARTIAL but lmax is converted to the reference's natural-log units
+// Exchange-slot hand-over of one shard, fused into its split merge: wait until *wait_flag >= wait_epoch (the root has
+// consumed what the slot held; NULL = nothing to wait for), merge into the slot, release *flag = epoch (state published).
+struct PublishSync {
+    const unsigned int* wait_flag = nullptr;
+    unsigned int wait_epoch = 0;
+    unsigned int* flag = nullptr;
+    unsigned int epoch = 0;
+    unsigned int* block_counter = nullptr;   // local scratch word
+    unsigned long long* trace = nullptr;
+};
 sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, float* contrib,
                                 float* tmax_out, float* lsum_out, bool natural_log_max,
-                                cudaStream_t stream);
+                                cudaStream_t stream, const PublishSync* publish = nullptr);
 // Cross-shard steps of the NCCL merge (mpi.c:346-351 and mpi.c:358-362).
 sdpa_status launch_rescale_to_gmax(float* contrib, float* lsum, const float* tmax, const float* gmax,
                                    int rows, int dv, cudaStream_t stream);
@@ -137,7 +147,8 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
 // Split merge behind the persistent fused kernel: per row, wm_pieces(row block) states (all max_pieces if *guard == epoch).
 // out64 != NULL: normalised fp64 rows; else the merged un-normalised state (contrib, tmax, lsum) for the cross-GPU merge.
 sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64, float* contrib,
-                                float* tmax_out, float* lsum_out, const unsigned int* guard, unsigned int epoch, cudaStream_t stream);
+                                float* tmax_out, float* lsum_out, const unsigned int* guard, unsigned int epoch, cudaStream_t stream,
+                                const PublishSync* publish = nullptr);
 // Sliced merge, source side: merge the split states of `rows` rows and write each row's state into the inbox segment of
 // the rank owning its slice (slice r = rows/world + (r < rows%world) consecutive rows), then raise flag[r] = epoch at every rank.
 struct RouteTargets {

@@ -193,9 +193,9 @@ struct sdpa_ctx {
     bool last_timing_valid = true;          // false: last_timing[0..3] still have to be computed from the event pairs
     double acc_fused_launches = 0, acc_calls = 0;
     const char* last_kernel = "none";
-    // EXPERIMENTAL (SDPA_OVERLAP_PASSES=1, one GPU per process, queued passes only; off by default, not yet measured):
-    // consecutive queued passes alternate exchange slots and are not joined at the end of the call, so the comm stream
-    // merges pass i while the compute stream already runs the cast and fused kernel of pass i+1.
+    // Queued passes of a one-GPU-per-process context (sdpa_enqueue_device_full) alternate exchange slots and are not joined at
+    // the end of the call, so the comm stream merges pass i while the compute stream already runs the cast and fused kernel
+    // of pass i+1 (SDPA_OVERLAP_PASSES=0 turns that off).  Blocking calls always join.
     bool qshard = false;                    // SDPA_DIST_Q in effect: every shard holds ALL K/V rows, Q rows are sharded, no exchange
     bool overlap_passes = false;
     unsigned long long batch_seq = 0;       // batches issued in overlap mode (slot = batch_seq & 1)
@@ -221,8 +221,8 @@ struct sdpa_ctx {
         unsigned int epoch = 0;         // global batch counter, identical on every rank
         unsigned int slot_epoch[2] = {0, 0};
         DevBuf trace;                   // SDPA_EXCHANGE_TRACE=<path>: kTraceEpochs x 4 u64 %globaltimer stamps, dumped to <path>.rank<r>
-        static constexpr unsigned int kTraceEpochs = 4096;
-        unsigned long long* trace_slot(unsigned int e) { return trace.p ? trace.as<unsigned long long>() + (size_t)(e % kTraceEpochs) * 4 : nullptr; }
+        static constexpr unsigned int kTraceEpochs = 4096, kTraceWords = 12;   // [0] published [1] merge begin [2] all flags seen [3] done [4+r] flag r seen
+        unsigned long long* trace_slot(unsigned int e) { return trace.p ? trace.as<unsigned long long>() + (size_t)(e % kTraceEpochs) * kTraceWords : nullptr; }
     } ipc;
     bool has_root() const { return rank_base == 0; }
 };
@@ -605,7 +605,7 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 4096));
         if (const char* ts = getenv("SDPA_FLAG_TIMEOUT_S"); ts && atof(ts) > 0.0) SDPA_TRY(set_flag_timeout_seconds(atof(ts)));
         if (const char* tp = getenv("SDPA_EXCHANGE_TRACE"); tp && *tp) {
-            SDPA_TRY(x.trace.reserve((size_t)sdpa_ctx::Ipc::kTraceEpochs * 4 * sizeof(unsigned long long)));
+            SDPA_TRY(x.trace.reserve((size_t)sdpa_ctx::Ipc::kTraceEpochs * sdpa_ctx::Ipc::kTraceWords * sizeof(unsigned long long)));
             SDPA_CUDA_TRY(cudaMemset(x.trace.p, 0, x.trace.bytes));
         }
         x.epoch = 0;
@@ -859,9 +859,9 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 const bool pieces = by_pieces && umma_plan_last_v8(s.plan, &wm, &max_pieces, &guard, &guard_epoch);
                 if (pieces) ctx->last_kernel = "bf16_umma_v8";
                 // the shard's own partial states -> one state: normalised fp64 rows (single GPU) or (contrib, tmax, lsum)
-                auto merge_local = [&](double* out64, float* c, float* t, float* l) -> sdpa_status {
-                    if (pieces) return launch_merge_pieces(part, wm, max_pieces, bs, dv, out64, c, t, l, guard, guard_epoch, s.s_compute);
-                    return launch_merge_splits(part, bs, dv, out64, c, t, l, false, s.s_compute);
+                auto merge_local = [&](double* out64, float* c, float* t, float* l, const PublishSync* pub = nullptr) -> sdpa_status {
+                    if (pieces) return launch_merge_pieces(part, wm, max_pieces, bs, dv, out64, c, t, l, guard, guard_epoch, s.s_compute, pub);
+                    return launch_merge_splits(part, bs, dv, out64, c, t, l, false, s.s_compute, pub);
                 };
                 if (single) {
                     SDPA_TRY(merge_local(final_dst, nullptr, nullptr, nullptr));
@@ -873,7 +873,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                         float* xt = xc + (size_t)x.cap_rows * dv;
                         float* xl = xt + x.cap_rows;
                         if (i == 0) ++x.epoch;
-                        if (s.grank != 0 && x.slot_epoch[b] != 0)   // the root must have consumed the slot's previous content
+                        if (x.sliced && s.grank != 0 && x.slot_epoch[b] != 0)   // the root must have consumed the slot's previous content
                             SDPA_TRY(launch_wait_flag(x.root_flags + 2 + b, x.slot_epoch[b], s.s_compute));
                         if (x.sliced) {
                             // push: every row's merged state goes straight into the inbox of the rank that owns its slice
@@ -891,8 +891,18 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                             to.world = world;
                             SDPA_TRY(launch_merge_splits_routed(part, bs, dv, to, s.s_compute));
                         } else {
-                            SDPA_TRY(merge_local(nullptr, xc, xt, xl));
-                            SDPA_TRY(launch_signal_flag(x.flags.as<unsigned int>() + b, x.epoch, s.s_compute, x.trace_slot(x.epoch)));
+                            // one launch: wait for the root's "consumed" flag of this slot, merge the shard's partial states
+                            // into the slot, publish the epoch flag
+                            PublishSync pub;
+                            if (s.grank != 0 && x.slot_epoch[b] != 0) {
+                                pub.wait_flag = x.root_flags + 2 + b;
+                                pub.wait_epoch = x.slot_epoch[b];
+                            }
+                            pub.flag = x.flags.as<unsigned int>() + b;
+                            pub.epoch = x.epoch;
+                            pub.block_counter = x.flags.as<unsigned int>() + 12 + b;
+                            pub.trace = x.trace_slot(x.epoch);
+                            SDPA_TRY(merge_local(nullptr, xc, xt, xl, &pub));
                         }
                         x.slot_epoch[b] = x.epoch;
                     } else {
@@ -1465,8 +1475,8 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
     ctx->world = world;
     ctx->rank_base = cfg.rank_base;
     {
-        const char* ov = getenv("SDPA_OVERLAP_PASSES");
-        ctx->overlap_passes = ov && *ov == '1';
+        const char* ov = getenv("SDPA_OVERLAP_PASSES");   // SDPA_OVERLAP_PASSES=0: every queued pass joins its exchange before the next starts
+        ctx->overlap_passes = !(ov && *ov == '0');
     }
     ctx->shards.resize(L);
     sdpa_status st = SDPA_OK;
@@ -1535,15 +1545,19 @@ sdpa_status sdpa_ctx_destroy(sdpa_ctx* ctx)
         cudaDeviceSynchronize();
         if (ctx->ipc.trace.p) {   // developer aid: dump the exchange timeline of this rank
             const char* tp = getenv("SDPA_EXCHANGE_TRACE");
-            std::vector<unsigned long long> host((size_t)sdpa_ctx::Ipc::kTraceEpochs * 4);
+            const unsigned int W = sdpa_ctx::Ipc::kTraceWords;
+            std::vector<unsigned long long> host((size_t)sdpa_ctx::Ipc::kTraceEpochs * W);
             if (tp && cudaMemcpy(host.data(), ctx->ipc.trace.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
                 char path[1024];
                 snprintf(path, sizeof(path), "%s.rank%d", tp, ctx->rank_base);
                 if (FILE* f = fopen(path, "w")) {
-                    fprintf(f, "epoch published_ns merge_begin_ns flags_seen_ns merge_done_ns   (last epoch %u)\n", ctx->ipc.epoch);
+                    fprintf(f, "epoch published_ns merge_begin_ns flags_seen_ns merge_done_ns flag_seen_ns[0..7]   (last epoch %u; every GPU has its own clock)\n", ctx->ipc.epoch);
                     for (unsigned int e = 0; e < sdpa_ctx::Ipc::kTraceEpochs; ++e)
-                        if (host[e * 4] || host[e * 4 + 1])
-                            fprintf(f, "%u %llu %llu %llu %llu\n", e, host[e * 4], host[e * 4 + 1], host[e * 4 + 2], host[e * 4 + 3]);
+                        if (host[e * W] || host[e * W + 1]) {
+                            fprintf(f, "%u", e);
+                            for (unsigned int k = 0; k < W; ++k) fprintf(f, " %llu", host[e * W + k]);
+                            fprintf(f, "\n");
+                        }
                     fclose(f);
                 }
             }

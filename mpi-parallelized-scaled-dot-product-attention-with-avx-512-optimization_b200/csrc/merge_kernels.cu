@@ -82,8 +82,10 @@ struct SyncArgs {
     const unsigned int* ready[64];
     unsigned int* consumed;
     unsigned int* block_counter;
-    unsigned int epoch;
-    int enabled;
+    unsigned int epoch;        // value released into `consumed` when the last block is done
+    unsigned int spin_epoch;   // value awaited in every `ready` flag at entry
+    int enabled;               // bit 0: spin on the ready flags at entry; bit 1: release `consumed` at the end
+    int nready;                // flags to spin on (0 = the kernel's state count)
     unsigned long long* trace;
 };
 
@@ -96,7 +98,7 @@ merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restric
     if (sync.enabled) {
         // fused exchange: the states live on other GPUs; wait until each of them has published this epoch
         if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[1] = global_ns();
-        if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.epoch, 2);
+        if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.spin_epoch, 2);
         __syncthreads();
         if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[2] = global_ns();
     }
@@ -189,6 +191,93 @@ __device__ __forceinline__ void merge_one_row(const StatePtrs& st, int count, in
         *lsum_dst = gsum;
     }
 }
+
+// Flat form for up to 8 states and dv % 4 == 0: one thread owns 4 consecutive columns of one row and issues EVERY load of
+// its merge (the states' tmax, lsum and 16-byte o vectors) before the first use, so a row costs one memory round trip
+// instead of the three dependent ones of the warp-per-row form (statistics -> shuffles -> vectors); the row statistics are
+// recomputed by the 32 (dv = 128) threads that share a row -- same addresses, one broadcast transaction per warp.
+// COUNT_FROM_MAP: the number of states of a row comes from the persistent kernel's work map (pieces of its row block).
+template <bool FINAL, bool COUNT_FROM_MAP>
+__global__ void __launch_bounds__(256)
+merge_flat_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict__ out64, float* __restrict__ contrib,
+                  float* __restrict__ tmax_out, float* __restrict__ lsum_out, float max_unit, WorkMap wm, int max_pieces,
+                  const unsigned int* __restrict__ guard, unsigned int epoch, const SyncArgs sync)
+{
+    if (sync.enabled & 1) {
+        // flags to wait for: every shard's "state published" (cross-GPU merge), or the root's "slot consumed" (a shard's own
+        // split merge about to overwrite its exchange slot).  Thread r records when flag r was seen (root's clock).
+        const int nready = sync.nready > 0 ? sync.nready : count;
+        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[1] = global_ns();
+        if (threadIdx.x < nready) {
+            spin_until(sync.ready[threadIdx.x], sync.spin_epoch, 2);
+            if (sync.trace && blockIdx.x == 0 && threadIdx.x < 8 && sync.nready == 0) sync.trace[4 + threadIdx.x] = global_ns();
+        }
+        __syncthreads();
+        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[2] = global_ns();
+    }
+    const int vec_per_row = dv >> 2;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = (int)(idx / vec_per_row);
+    const int d = (int)(idx - (size_t)row * vec_per_row) << 2;
+    if (row < rows) {
+        int n = count;
+        if constexpr (COUNT_FROM_MAP) n = (*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256);
+        float t[8], l[8];
+        float4 v[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (s < n) {
+                t[s] = st.tmax[s][row];
+                l[s] = st.lsum[s][row];
+                v[s] = *reinterpret_cast<const float4*>(st.o[s] + (size_t)row * dv + d);
+            }
+        }
+        float gmax = -CUDART_INF_F;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s < n) gmax = fmaxf(gmax, t[s]);
+        float gsum = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            if (s < n) {
+                const float w = (t[s] == -CUDART_INF_F) ? 0.f : exp2f(t[s] - gmax);   // all states empty: weights 0, output 0
+                gsum = fmaf(l[s], w, gsum);
+                acc.x = fmaf(v[s].x, w, acc.x);
+                acc.y = fmaf(v[s].y, w, acc.y);
+                acc.z = fmaf(v[s].z, w, acc.z);
+                acc.w = fmaf(v[s].w, w, acc.w);
+            }
+        }
+        if (FINAL) {
+            const float inv = (gsum == 0.f) ? 0.f : 1.f / gsum;
+            double2* dst = reinterpret_cast<double2*>(out64 + (size_t)row * dv + d);
+            dst[0] = make_double2((double)(acc.x * inv), (double)(acc.y * inv));
+            dst[1] = make_double2((double)(acc.z * inv), (double)(acc.w * inv));
+        } else {
+            *reinterpret_cast<float4*>(contrib + (size_t)row * dv + d) = acc;
+            if (d == 0) {
+                tmax_out[row] = gmax * max_unit;
+                lsum_out[row] = gsum;
+            }
+        }
+    }
+    if (sync.enabled & 2) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(sync.block_counter, 1u) == gridDim.x - 1) {
+                *sync.block_counter = 0;
+                __threadfence_system();
+                st_release_sys(sync.consumed, sync.epoch);   // "merged": the peers' slots may be reused / this shard's state is published
+                if (sync.trace) sync.trace[(sync.enabled & 1) && sync.nready == 0 ? 3 : 0] = global_ns();
+            }
+        }
+    }
+}
+
+inline int flat_blocks(int rows, int dv) { return (int)(((size_t)rows * (dv >> 2) + 255) / 256); }
+inline bool flat_ok(int states, int dv, bool vec_ok) { return states <= 8 && (dv & 3) == 0 && vec_ok && getenv("SDPA_MERGE_FLAT_OFF") == nullptr; }
 
 // contrib *= 2^(tmax - gmax), lsum *= 2^(tmax - gmax)        (mpi.c:346-351)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -294,7 +383,7 @@ merge_pieces_kernel(StatePtrs st, WorkMap wm, int max_pieces, int rows, int dv, 
 __global__ void __launch_bounds__(256)
 collect_slices_kernel(double2* __restrict__ dst, const double2* __restrict__ src, size_t units, SyncArgs sync, int count)
 {
-    if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.epoch, 3);
+    if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.spin_epoch, 3);
     __syncthreads();
     const size_t total = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < units; i += total) dst[i] = src[i];
@@ -322,11 +411,30 @@ sdpa_status launch_finalize_reduced(double* out64, const float* reduced, const f
     return SDPA_OK;
 }
 
+// `publish` (exchange slot hand-over of one shard): wait until *publish->wait_flag >= wait_epoch (the root has consumed the
+// slot's previous content; NULL = no wait), merge, then release publish->flag = epoch.  Fused into the flat merge kernel; the
+// warp-per-row fallback brackets the merge with the 1-thread wait / signal kernels.
+static SyncArgs publish_args(const PublishSync* publish)
+{
+    SyncArgs sa{};
+    if (!publish) return sa;
+    sa.enabled = 2 | (publish->wait_flag ? 1 : 0);
+    sa.ready[0] = publish->wait_flag;
+    sa.nready = 1;
+    sa.spin_epoch = publish->wait_epoch;
+    sa.consumed = publish->flag;
+    sa.block_counter = publish->block_counter;
+    sa.epoch = publish->epoch;
+    sa.trace = publish->trace;
+    return sa;
+}
+
 sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, float* contrib,
                                 float* tmax_out, float* lsum_out, bool natural_log_max,
-                                cudaStream_t stream)
+                                cudaStream_t stream, const PublishSync* publish)
 {
-    if (rows <= 0) return SDPA_OK;
+    if (rows <= 0 && !publish) return SDPA_OK;
+    if (rows < 0) rows = 0;
     if (part.splits < 1 || part.splits > 64) {
         set_error("merge supports 1..64 split states (got %d)", part.splits);
         return SDPA_ERR_INVALID;
@@ -340,13 +448,30 @@ sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, 
     const int blocks = ceil_div(rows, kWarpsPerBlock);
     bool vec_ok = al16(out64) && al16(contrib);
     for (int s = 0; s < part.splits; ++s) vec_ok = vec_ok && al16(st.o[s]);
-    if (out64 != nullptr)
-        merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-            st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f, vec_ok, SyncArgs{});
-    else
-        merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(
-            st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, natural_log_max ? kLn2 : 1.f, vec_ok, SyncArgs{});
-    count_launch();
+    const float unit = natural_log_max ? kLn2 : 1.f;
+    if (flat_ok(part.splits, dv, vec_ok)) {
+        const int fb = std::max(1, flat_blocks(rows, dv));
+        const SyncArgs sa = publish_args(publish);
+        if (out64 != nullptr)
+            merge_flat_kernel<true, false><<<fb, 256, 0, stream>>>(st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f,
+                                                                  WorkMap{0, 0, 0}, 0, nullptr, 0, sa);
+        else
+            merge_flat_kernel<false, false><<<fb, 256, 0, stream>>>(st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, unit,
+                                                                   WorkMap{0, 0, 0}, 0, nullptr, 0, sa);
+        count_launch();
+    } else {
+        if (publish && publish->wait_flag) SDPA_TRY(launch_wait_flag(publish->wait_flag, publish->wait_epoch, stream));
+        if (rows > 0) {
+            if (out64 != nullptr)
+                merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr,
+                                                                                     1.f, vec_ok, SyncArgs{});
+            else
+                merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, nullptr, contrib, tmax_out,
+                                                                                      lsum_out, unit, vec_ok, SyncArgs{});
+            count_launch();
+        }
+        if (publish) SDPA_TRY(launch_signal_flag(publish->flag, publish->epoch, stream, publish->trace));
+    }
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -395,23 +520,30 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     }
     sa.consumed = sync.consumed;
     sa.block_counter = sync.block_counter;
-    sa.epoch = sync.epoch;
-    sa.enabled = 1;
+    sa.epoch = sa.spin_epoch = sync.epoch;
+    sa.enabled = 3;
+    sa.nready = 0;
     sa.trace = sync.trace;
     const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     bool vec_ok = al16(out64);
     for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
-    merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
-                                                                         nullptr, 1.f, vec_ok, sa);
+    if (flat_ok(shards, dv, vec_ok) && rows > 0)
+        merge_flat_kernel<true, false><<<flat_blocks(rows, dv), 256, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr, nullptr, 1.f,
+                                                                                 WorkMap{0, 0, 0}, 0, nullptr, 0, sa);
+    else
+        merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
+                                                                             nullptr, 1.f, vec_ok, sa);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
 
 sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64, float* contrib,
-                                float* tmax_out, float* lsum_out, const unsigned int* guard, unsigned int epoch, cudaStream_t stream)
+                                float* tmax_out, float* lsum_out, const unsigned int* guard, unsigned int epoch, cudaStream_t stream,
+                                const PublishSync* publish)
 {
-    if (rows <= 0) return SDPA_OK;
+    if (rows <= 0 && !publish) return SDPA_OK;
+    if (rows < 0) rows = 0;
     if (max_pieces < 1 || max_pieces > 64 || max_pieces > part.splits || !guard || (!out64 && !(contrib && tmax_out && lsum_out))) {
         set_error("merge_pieces: bad arguments (pieces=%d, partial slots=%d)", max_pieces, part.splits);
         return SDPA_ERR_INVALID;
@@ -425,11 +557,25 @@ sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces
         vec_ok = vec_ok && al16(st.o[s]);
     }
     const int blocks = ceil_div(rows, kWarpsPerBlock);
-    if (out64) merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr,
-                                                                                    vec_ok, guard, epoch);
-    else merge_pieces_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, nullptr, contrib, tmax_out, lsum_out,
-                                                                               vec_ok, guard, epoch);
-    count_launch();
+    if (flat_ok(max_pieces, dv, vec_ok)) {
+        const int fb = std::max(1, flat_blocks(rows, dv));
+        const SyncArgs sa = publish_args(publish);
+        if (out64) merge_flat_kernel<true, true><<<fb, 256, 0, stream>>>(st, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr, 1.f, wm, max_pieces,
+                                                                        guard, epoch, sa);
+        else merge_flat_kernel<false, true><<<fb, 256, 0, stream>>>(st, max_pieces, rows, dv, nullptr, contrib, tmax_out, lsum_out, 1.f, wm, max_pieces,
+                                                                   guard, epoch, sa);
+        count_launch();
+    } else {
+        if (publish && publish->wait_flag) SDPA_TRY(launch_wait_flag(publish->wait_flag, publish->wait_epoch, stream));
+        if (rows > 0) {
+            if (out64) merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr,
+                                                                                            vec_ok, guard, epoch);
+            else merge_pieces_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, nullptr, contrib, tmax_out,
+                                                                                       lsum_out, vec_ok, guard, epoch);
+            count_launch();
+        }
+        if (publish) SDPA_TRY(launch_signal_flag(publish->flag, publish->epoch, stream, publish->trace));
+    }
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -484,8 +630,8 @@ sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, i
     for (int r = 0; r < ranks; ++r) sa.ready[r] = sync.ready[r];
     sa.consumed = sync.consumed;
     sa.block_counter = sync.block_counter;
-    sa.epoch = sync.epoch;
-    sa.enabled = 1;
+    sa.epoch = sa.spin_epoch = sync.epoch;
+    sa.enabled = 3;
     const size_t units = (size_t)rows * dv / 2;
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>(148 * 4, (units + 255) / 256));
     collect_slices_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<double2*>(dst), reinterpret_cast<const double2*>(staged),

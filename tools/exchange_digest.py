@@ -12,15 +12,14 @@ for p in files:
     r = int(p.rsplit("rank", 1)[1])
     rows = {}
     for line in open(p).read().splitlines()[1:]:
-        e, pub, mb, fs, md = map(int, line.split())
-        rows[e] = (pub, mb, fs, md)
+        v = list(map(int, line.split()))
+        rows[v[0]] = v[1:]
     ranks[r] = rows
 if 0 not in ranks:
     sys.exit("no trace of rank 0 under " + base)
-common = set(ranks[0])
-for r in ranks:
-    common &= set(ranks[r])
-steps = sorted(e for e in common if all(ranks[r][e][0] for r in ranks) and ranks[0][e][3])
+R = ranks[0]
+n = len(ranks)
+steps = sorted(e for e in R if R[e][3] and all(R[e][4 + r] for r in range(min(n, 8))))
 steps = steps[len(steps) // 4:]          # drop the warm-up quarter
 if not steps:
     sys.exit("no complete steps")
@@ -31,14 +30,15 @@ def med(xs):
     return st.median(xs) / 1e3 if xs else float("nan")
 
 
-pub = {e: [ranks[r][e][0] for r in sorted(ranks)] for e in steps}
-print(f"{len(ranks)} ranks, {len(steps)} exchange steps (us, medians; %globaltimer of different GPUs agrees to a few us)")
-print(f"  publish skew (last - first shard's state published)        : {med(max(pub[e]) - min(pub[e]) for e in steps):8.1f}")
-print(f"  root published -> root merge kernel started                 : {med(ranks[0][e][1] - ranks[0][e][0] for e in steps):8.1f}")
-print(f"  last publish -> root saw every flag                         : {med(ranks[0][e][2] - max(pub[e]) for e in steps):8.1f}")
-print(f"  root merge kernel: flags seen -> merged + consumed raised   : {med(ranks[0][e][3] - ranks[0][e][2] for e in steps):8.1f}")
-print(f"  root merge kernel total (start -> done)                     : {med(ranks[0][e][3] - ranks[0][e][1] for e in steps):8.1f}")
-per = [med(ranks[0][b][3] - ranks[0][a][3] for a, b in zip(steps, steps[1:]) if b == a + 1)]
-print(f"  step period (done -> done of consecutive epochs)            : {per[0]:8.1f}")
-late = [max(range(len(pub[e])), key=lambda i: pub[e][i]) for e in steps]
-print("  slowest shard histogram (rank: steps)                        :", {r: late.count(r) for r in sorted(set(late))})
+# Every GPU has its own %globaltimer: all cross-rank times are taken on the ROOT's clock (when its merge kernel saw a flag).
+seen = {e: [R[e][4 + r] for r in range(min(n, 8))] for e in steps}
+print(f"{n} ranks, {len(steps)} exchange steps (us, medians, root GPU's clock)")
+print(f"  root's own state published -> root merge kernel started            : {med(R[e][1] - R[e][0] for e in steps):8.1f}")
+print(f"  merge kernel start -> last shard's flag seen (wait for the slowest) : {med(max(seen[e]) - R[e][1] for e in steps):8.1f}")
+print(f"  flag arrival spread (last - first flag seen by the root)            : {med(max(seen[e]) - min(seen[e]) for e in steps):8.1f}")
+print(f"  all flags seen -> merged, 'consumed' raised (reads over NVLink)     : {med(R[e][3] - R[e][2] for e in steps):8.1f}")
+print(f"  merge kernel total                                                  : {med(R[e][3] - R[e][1] for e in steps):8.1f}")
+print(f"  step period (merge done -> merge done of consecutive epochs)        : {med(R[b][3] - R[a][3] for a, b in zip(steps, steps[1:]) if b == a + 1):8.1f}")
+print(f"  root published -> root published of consecutive epochs              : {med(R[b][0] - R[a][0] for a, b in zip(steps, steps[1:]) if b == a + 1):8.1f}")
+late = [max(range(len(seen[e])), key=lambda i: seen[e][i]) for e in steps]
+print("  slowest shard histogram (rank: steps)                               :", {r: late.count(r) for r in sorted(set(late))})

@@ -22,7 +22,7 @@ V = torch.randn(a.n, 128, dtype=torch.float64, generator=g).cuda()
 R = torch.zeros(a.m, 128, dtype=torch.float64, device="cuda")
 with sdpa_b200.Context(precision=a.precision, q_batch=a.q_batch, kv_splits=a.kv_splits) as ctx:
     for _ in range(a.steps):
-        ctx.load_kv_device_ptrs([K.data_ptr()], [V.data_ptr()], [a.n], 128, 128)
-        ctx.attention_device_ptrs([Q.data_ptr()], R.data_ptr(), a.m)
+        # the pass bench.py times: K/V/Q cast in one launch, fused kernel (+ exact twin), split merge
+        ctx.attention_device_full([K.data_ptr()], [V.data_ptr()], [a.n], 128, 128, [Q.data_ptr()], R.data_ptr(), a.m)
     torch.cuda.synchronize()
     print(ctx.last_kernel(), ctx.last_timings())
