@@ -76,6 +76,10 @@ typedef struct sdpa_config {
 
 typedef struct sdpa_ctx sdpa_ctx;
 
+/* Whether a kernel exists for (precision, dk, dv); for SDPA_PREC_AUTO always 1 when dk, dv are in [1, 256], and
+ * *resolved (may be NULL) receives the precision AUTO selects.  Pure host function; usable without a GPU. */
+int sdpa_precision_supported(int precision, int dk, int dv, int* resolved);
+
 /* ---------------------------------------------------------------------------
  * 1. The reference entry point (replaces mpi.c:191-192; the serial flavour
  *    ser.c:20-21 is the same call with mpi_rank=0, mpi_size=1).

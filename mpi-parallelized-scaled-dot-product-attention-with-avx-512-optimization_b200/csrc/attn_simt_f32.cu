@@ -312,6 +312,15 @@ int attn_f32_pick_splits(int rows, int n, int sm_count)
     return 1;
 }
 
+void preload_attn_f32_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, attn_f32_kernel<64>);
+    cudaFuncGetAttributes(&a, attn_f32_kernel<128>);
+    cudaFuncGetAttributes(&a, attn_f32_kernel<256>);
+    cudaGetLastError();
+}
+
 sdpa_status launch_attn_f32(const float* Q, const float* K, const float* V, int rows, int n, int dk,
                             int dv, int splits, Partials part, double* out64, cudaStream_t stream)
 {

@@ -1107,6 +1107,16 @@ int attn_umma_pick_splits(int rows, int n, int sm_count)
     return best;
 }
 
+void preload_attn_umma_general_kernels();
+void preload_attn_umma_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, attn_umma_kernel_v7<false, 0, 2, 2>);
+    cudaFuncGetAttributes(&a, attn_umma_kernel_v8<0, false, false>);
+    cudaGetLastError();
+    preload_attn_umma_general_kernels();
+}
+
 sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part, double* out64,
                              int sm_count, cudaStream_t stream)
 {

@@ -485,6 +485,16 @@ attn_umma_general_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __g
 // ---------------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------------
+void preload_attn_umma_general_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, attn_umma_general_kernel<1, false>);
+    cudaFuncGetAttributes(&a, attn_umma_general_kernel<1, true>);
+    cudaFuncGetAttributes(&a, attn_umma_general_kernel<2, false>);
+    cudaFuncGetAttributes(&a, attn_umma_general_kernel<2, true>);
+    cudaGetLastError();
+}
+
 static const size_t kGenSmemLimit = 232448 - 1024;   // 227 KiB opt-in limit minus the alignment slack
 
 // Shared-memory need of a shape: Q tile + the K and V rings + barriers.  Ring depths: as deep as fits, at most 4, at least 2.

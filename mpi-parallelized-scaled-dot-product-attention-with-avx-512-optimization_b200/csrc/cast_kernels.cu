@@ -240,6 +240,19 @@ inline bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
 
 }  // namespace
 
+void preload_cast_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, cvt_in_batch_kernel<0>);
+    cudaFuncGetAttributes(&a, cvt_in_batch_kernel<1>);
+    cudaFuncGetAttributes(&a, cvt_in_batch_kernel<2>);
+    cudaFuncGetAttributes(&a, cvt_d2f_vec_kernel);
+    cudaFuncGetAttributes(&a, cvt_d2bf16_vec_kernel);
+    cudaFuncGetAttributes(&a, cvt_d2bf16x2_vec_kernel);
+    cudaFuncGetAttributes(&a, cvt_f2d_vec_kernel);
+    cudaGetLastError();
+}
+
 sdpa_status launch_cvt_d2f(float* dst, const double* src, size_t count, cudaStream_t stream)
 {
     if (count == 0) return SDPA_OK;

@@ -187,6 +187,13 @@ __host__ __device__ inline int wm_pieces(const WorkMap& w, int rb)
     return wm_cluster_of(w, (long long)(rb + 1) * w.T - 1) - wm_cluster_of(w, (long long)rb * w.T) + 1;
 }
 
+// Force the (lazily loaded) kernels of each translation unit onto the current device: cudaFuncGetAttributes loads the function.
+void preload_cast_kernels();
+void preload_merge_kernels();
+void preload_attn_f32_kernels();
+void preload_attn_umma_kernels();
+void host_staging_warm();   // pinned ring + copy threads of the pageable-source path, ahead of the first timed call
+
 // host_staging.cu: host -> device copies that run at the pinned rate for pageable sources too (pinned ring + copy threads)
 bool host_ptr_is_pageable(const void* p);
 sdpa_status h2d_any(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t stream);

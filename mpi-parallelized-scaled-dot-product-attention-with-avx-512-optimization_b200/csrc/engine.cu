@@ -107,25 +107,51 @@ const NcclApi* nccl_api()
 // ---------------------------------------------------------------------------
 // One K/V shard = one GPU.
 // ---------------------------------------------------------------------------
+// Device buffer.  Work buffers come from the device's stream-ordered memory pool (cudaMallocAsync) whose release threshold
+// is lifted at context creation and which sdpa_runtime_init pre-fills (SDPA_PREALLOC_MB): inside the timed attention() call an
+// allocation is then a pool hit (microseconds) instead of a cudaMalloc (a fraction of a millisecond each, ~25 of them on a
+// first call).  Buffers exported over CUDA IPC must be plain cudaMalloc memory (`shareable`).  SDPA_MEM_POOL=0: cudaMalloc only.
+static bool mem_pool_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("SDPA_MEM_POOL");
+        return !(e && *e == '0');
+    }();
+    return on;
+}
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
-    sdpa_status reserve(size_t want)
+    bool pooled = false;
+    sdpa_status reserve(size_t want, bool shareable = false)
     {
         if (want <= bytes) return SDPA_OK;
         if (p) {
-            SDPA_CUDA_TRY(cudaFree(p));
-            p = nullptr;
-            bytes = 0;
+            SDPA_CUDA_TRY(cudaDeviceSynchronize());   // growth while earlier work may still read the old block (rare path)
+            release();
         }
         size_t sz = (want + 255) & ~(size_t)255;
-        SDPA_CUDA_TRY(cudaMalloc(&p, sz));
+        if (!shareable && mem_pool_enabled()) {
+            SDPA_CUDA_TRY(cudaMallocAsync(&p, sz, cudaStreamPerThread));
+            SDPA_CUDA_TRY(cudaStreamSynchronize(cudaStreamPerThread));   // usable from every stream from here on
+            pooled = true;
+        } else {
+            SDPA_CUDA_TRY(cudaMalloc(&p, sz));
+            pooled = false;
+        }
         bytes = sz;
         return SDPA_OK;
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pooled) {
+                cudaFreeAsync(p, cudaStreamPerThread);
+                cudaStreamSynchronize(cudaStreamPerThread);
+            } else {
+                cudaFree(p);
+            }
+        }
         p = nullptr;
         bytes = 0;
     }
@@ -244,8 +270,20 @@ static sdpa_status new_mark(Shard& s, cudaStream_t st, int* idx)
 // the next stage may then not reuse the previous stage's end mark as its begin.
 static inline void compute_stream_touched(Shard& s) { s.open_mark = -1; }
 
+// SDPA_STAGE_TIMING=0 (developer knob): no per-stage timestamp events, only the whole-call bracket -- quantifies what the
+// stage marks cost inside a queued loop.
+static bool stage_timing_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("SDPA_STAGE_TIMING");
+        return !(e && *e == '0');
+    }();
+    return on;
+}
+
 static sdpa_status time_begin(Shard& s, int which, cudaStream_t st)
 {
+    if (which != 3 && !stage_timing_enabled()) return SDPA_OK;
     int idx = -1;
     if (st == s.s_compute && s.open_mark >= 0) idx = s.open_mark;
     else SDPA_TRY(new_mark(s, st, &idx));
@@ -255,6 +293,7 @@ static sdpa_status time_begin(Shard& s, int which, cudaStream_t st)
 }
 static sdpa_status time_end(Shard& s, int which, cudaStream_t st, bool may_share = false)
 {
+    if (which != 3 && !stage_timing_enabled()) return SDPA_OK;
     int idx = -1;
     if (may_share && st == s.s_compute && s.open_mark >= 0) idx = s.open_mark;   // nothing ran since the last end mark
     else SDPA_TRY(new_mark(s, st, &idx));
@@ -366,6 +405,12 @@ static sdpa_status shard_init(Shard& s)
         SDPA_CUDA_TRY(mk(&s.ev_comm_done[b]));
     }
     for (int j = 0; j < 3; ++j) SDPA_CUDA_TRY(mk(&s.ev_join[j]));
+    if (mem_pool_enabled()) {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, s.dev) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaGetLastError();
+    }
     int sms = 0;
     SDPA_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s.dev));
     s.sm_count = sms > 0 ? sms : 148;
@@ -594,14 +639,14 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
     x.slice_cap = slice_cap;
     for (int b = 0; b < 2; ++b) {
         x.xbuf[b].release();
-        SDPA_TRY(x.xbuf[b].reserve(xbytes));
+        SDPA_TRY(x.xbuf[b].reserve(xbytes, true));
     }
     for (int b = 0; b < 2; ++b) {
         x.stage[b].release();
-        SDPA_TRY(x.stage[b].reserve((size_t)rows_cap * dv * sizeof(double)));
+        SDPA_TRY(x.stage[b].reserve((size_t)rows_cap * dv * sizeof(double), true));
     }
     if (!x.flags.p) {
-        SDPA_TRY(x.flags.reserve(4096));
+        SDPA_TRY(x.flags.reserve(4096, true));
         SDPA_CUDA_TRY(cudaMemset(x.flags.p, 0, 4096));
         if (const char* ts = getenv("SDPA_FLAG_TIMEOUT_S"); ts && atof(ts) > 0.0) SDPA_TRY(set_flag_timeout_seconds(atof(ts)));
         if (const char* tp = getenv("SDPA_EXCHANGE_TRACE"); tp && *tp) {
@@ -1417,6 +1462,15 @@ int sdpa_owner_disp(int n, int size, int rank)
     return rank * q + (rank < r ? rank : r);
 }
 
+int sdpa_precision_supported(int precision, int dk, int dv, int* resolved)
+{
+    if (precision < SDPA_PREC_AUTO || precision > SDPA_PREC_BF16X3 || dk < 1 || dv < 1) return 0;
+    const int prec = resolve_precision(precision, dk, dv);
+    if (resolved) *resolved = prec;
+    if (is_umma(prec)) return attn_umma_supported(dk, dv, prec_hl(prec)) ? 1 : 0;
+    return attn_f32_supported(dk, dv) ? 1 : 0;
+}
+
 void sdpa_config_init(sdpa_config* cfg)
 {
     if (!cfg) return;
@@ -1756,6 +1810,35 @@ sdpa_status sdpa_accumulated_timings(sdpa_ctx* ctx, double* out6, int reset)
 }
 
 const char* sdpa_last_kernel(sdpa_ctx* ctx) { return ctx ? ctx->last_kernel : "none"; }
+
+/* Untimed preparation of a context, the analogue of what MPI_Init does for the reference before its timed region
+ * (mpi.c:504,519): fill the memory pool of every local GPU with `pool_bytes` (later allocations become pool hits), load the
+ * kernels (CUDA loads a kernel's code lazily at its first launch), start the host staging pool. */
+sdpa_status sdpa_ctx_prewarm(sdpa_ctx* ctx, size_t pool_bytes)
+{
+    if (!ctx) {
+        set_error("sdpa_ctx_prewarm: ctx is NULL");
+        return SDPA_ERR_INVALID;
+    }
+    for (Shard& s : ctx->shards) {
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        if (mem_pool_enabled() && pool_bytes > 0) {
+            void* p = nullptr;
+            if (cudaMallocAsync(&p, pool_bytes, cudaStreamPerThread) == cudaSuccess) {
+                cudaMemsetAsync(p, 0, pool_bytes, cudaStreamPerThread);   // touch: the physical pages are mapped now
+                cudaFreeAsync(p, cudaStreamPerThread);
+            }
+            cudaStreamSynchronize(cudaStreamPerThread);
+            cudaGetLastError();
+        }
+        preload_cast_kernels();
+        preload_merge_kernels();
+        preload_attn_f32_kernels();
+        preload_attn_umma_kernels();
+    }
+    host_staging_warm();
+    return SDPA_OK;
+}
 
 /* MAX of a double over every process of the context (mpi.c:524); collective. */
 sdpa_status sdpa_ctx_max(sdpa_ctx* ctx, double* value)

@@ -198,6 +198,13 @@ sdpa_status h2d_any(void* dst_dev, const void* src_host, size_t bytes, cudaStrea
     return SDPA_OK;
 }
 
+void host_staging_warm()
+{
+    Stager& st = g_stager;
+    std::lock_guard<std::mutex> lk(st.mu);
+    if (stager_prepare(st) != SDPA_OK) cudaGetLastError();   // best effort: the first pageable copy retries and reports
+}
+
 int host_staging_lanes()
 {
     Stager& st = g_stager;

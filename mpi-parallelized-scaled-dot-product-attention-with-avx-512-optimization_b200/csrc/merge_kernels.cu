@@ -219,9 +219,20 @@ merge_flat_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict_
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int row = (int)(idx / vec_per_row);
     const int d = (int)(idx - (size_t)row * vec_per_row) << 2;
+    // pieces per row block: 64-bit divisions, so they are taken once per CTA (its rows span at most a few 256-row blocks)
+    __shared__ int s_count[4];
+    [[maybe_unused]] int rb_first = 0;
+    if constexpr (COUNT_FROM_MAP) {
+        rb_first = (int)(((size_t)blockIdx.x * blockDim.x) / vec_per_row) / 256;
+        if (threadIdx.x < 4) s_count[threadIdx.x] = (*guard == epoch) ? max_pieces : (rb_first + (int)threadIdx.x < wm.RB ? wm_pieces(wm, rb_first + threadIdx.x) : 0);
+        __syncthreads();
+    }
     if (row < rows) {
         int n = count;
-        if constexpr (COUNT_FROM_MAP) n = (*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256);
+        if constexpr (COUNT_FROM_MAP) {
+            const int k = row / 256 - rb_first;
+            n = k < 4 ? s_count[k] : ((*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256));
+        }
         float t[8], l[8];
         float4 v[8];
 #pragma unroll
@@ -400,6 +411,20 @@ collect_slices_kernel(double2* __restrict__ dst, const double2* __restrict__ src
 
 }  // namespace
 
+
+void preload_merge_kernels()
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, merge_flat_kernel<true, false>);
+    cudaFuncGetAttributes(&a, merge_flat_kernel<false, false>);
+    cudaFuncGetAttributes(&a, merge_flat_kernel<true, true>);
+    cudaFuncGetAttributes(&a, merge_flat_kernel<false, true>);
+    cudaFuncGetAttributes(&a, merge_states_kernel<true>);
+    cudaFuncGetAttributes(&a, merge_states_kernel<false>);
+    cudaFuncGetAttributes(&a, signal_flag_kernel);
+    cudaFuncGetAttributes(&a, wait_flag_kernel);
+    cudaGetLastError();
+}
 
 sdpa_status launch_finalize_reduced(double* out64, const float* reduced, const float* gsum, int rows, int dv,
                                     cudaStream_t stream)

@@ -69,6 +69,7 @@ ABI = {
     "sdpa_runtime_max": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double)]),
     "sdpa_owner_count": (ctypes.c_int, [ctypes.c_int] * 3),
     "sdpa_owner_disp": (ctypes.c_int, [ctypes.c_int] * 3),
+    "sdpa_precision_supported": (ctypes.c_int, [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int)]),
     "sdpa_config_init": (None, [ctypes.POINTER(Config)]),
     "sdpa_ctx_create": (ctypes.c_int, [ctypes.POINTER(_V), ctypes.POINTER(Config), _V]),
     "sdpa_ctx_destroy": (ctypes.c_int, [_V]),
@@ -185,6 +186,14 @@ def attention(Q, K, V, result=None, m=None, n=None, dk=None, dv=None, mpi_rank: 
         return result
     L.attention(None, None, None, None, 0, 0, 0, 0, mpi_rank, mpi_size)
     return None
+
+
+def precision_supported(precision, dk: int, dv: int):
+    """(supported, resolved precision name) -- which kernel family a (precision, dk, dv) request lands on."""
+    res = ctypes.c_int(-1)
+    ok = lib().sdpa_precision_supported(_PREC[precision] if isinstance(precision, str) else int(precision), dk, dv, ctypes.byref(res))
+    names = {PREC_F32: "f32", PREC_BF16: "bf16", PREC_BF16X3: "bf16x3"}
+    return bool(ok), names.get(res.value)
 
 
 def runtime_init(mpi_rank: int = 0, mpi_size: int = 1) -> None:

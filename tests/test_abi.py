@@ -69,3 +69,18 @@ def test_staging_pool_copy_is_exact(sdpa):
             assert lanes >= 2
             assert np.array_equal(dst[off:off + nbytes], src[off:off + nbytes])
             assert not dst[:off].any() and not dst[off + nbytes:].any()
+
+
+def test_precision_resolution_rules(sdpa):
+    """AUTO keeps the reference's fp32 accuracy class: the split-precision tensor-core kernel where the shape fits the SM's
+    shared memory, else the fp32 CUDA-core kernel; plain bf16 only on request.  (Host-side rule, no GPU needed.)"""
+    ps = sdpa.precision_supported
+    assert ps("auto", 128, 128) == (True, "bf16x3") and ps("auto", 64, 64) == (True, "bf16x3") and ps("auto", 80, 48) == (True, "bf16x3")
+    assert ps("auto", 64, 256) == (True, "bf16x3")              # narrow dk leaves room for a 256-wide V
+    assert ps("auto", 128, 256) == (True, "f32") and ps("auto", 200, 64) == (True, "f32")
+    assert ps("auto", 100, 100) == (True, "f32") and ps("auto", 1, 1) == (True, "f32")   # not multiples of 8
+    assert ps("auto", 300, 64) == (False, "f32")                 # beyond every kernel (dk, dv <= 256)
+    assert ps("bf16", 256, 256) == (True, "bf16") and ps("bf16", 8, 8) == (True, "bf16") and ps("bf16", 200, 136) == (True, "bf16")
+    assert ps("bf16", 100, 128)[0] is False and ps("bf16", 264, 128)[0] is False
+    assert ps("bf16x3", 128, 128)[0] and not ps("bf16x3", 128, 256)[0] and not ps("bf16x3", 192, 64)[0]
+    assert ps("f32", 256, 256) == (True, "f32") and ps("f32", 257, 8)[0] is False

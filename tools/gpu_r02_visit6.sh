@@ -1,0 +1,34 @@
+#!/bin/bash
+# Round-2 visit 6 (TWO GPUs): flat merge kernel with fused wait/publish flags, overlapped queued passes by default.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+OUT=gpurun_out
+S=$OUT/summary_v6.log; rm -f $S $OUT/xtrace_*
+timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider -x > $OUT/v6_pytest_multi.log 2>&1
+echo "pytest multi rc=$?" >> $S
+run() {
+  local name=$1; shift
+  local envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" NCCL_DEBUG=WARN timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus 2 "$@" > $OUT/v6_$name.json 2> $OUT/v6_$name.err
+  echo "bench $name rc=$?" >> $S
+}
+run g2_default SDPA_EXCHANGE_TRACE=$OUT/xtrace_g2 -- --steps 20 --warmup 3 --extra c4
+run g2_nooverlap SDPA_OVERLAP_PASSES=0 -- --steps 20 --warmup 3
+run g2_noflat SDPA_MERGE_FLAT_OFF=1 -- --steps 20 --warmup 3
+timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --extra none > $OUT/v6_g1.json 2> $OUT/v6_g1.err
+echo "bench g1 rc=$?" >> $S
+SDPA_STAGE_TIMING=0 timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --extra none > $OUT/v6_g1_nomarks.json 2>> $OUT/v6_g1.err
+echo "bench g1 nomarks rc=$?" >> $S
+cat $S; grep -E "passed|failed" $OUT/v6_pytest_multi.log | tail -2; grep -E "^FAILED|^ERROR" $OUT/v6_pytest_multi.log | head
+python tools/exchange_digest.py $OUT/xtrace_g2
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/v6_g*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split("/")[-1], "value", round(d["value"],1), "ms", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"],1), {k:round(v,4) for k,v in d["stage_ms_per_step"].items()}, d["impl_detail"]["kernel"], "parity", d["parity_check"]["ok"], d["parity_check"]["max_abs_err"])
+        for k,v in d.get("configs",{}).items(): print("    ", k, "value", round(v["value"],1), "ms", round(v["ms_per_step"],4), "e2e", round(v["e2e"]["value"],1), v["stage_ms_per_step"], "parity", v["parity_check"]["ok"], v["parity_check"]["max_abs_err"], "batches", v["q_batches_per_step"])
+    except Exception as e:
+        print(f, "unreadable", e); print(open(f.replace(".json",".err")).read()[-1500:])
+PY
