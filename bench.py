@@ -479,6 +479,7 @@ def run_ours(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
+    os.environ["SDPA_STAGE_TIMING_EVERY"] = str(max(1, args.stage_timing_every))   # read by the library at context creation
     import sdpa_b200
     from sdpa_b200 import parallel
 
@@ -518,7 +519,7 @@ def run_ours(args) -> None:
         for _ in range(W):
             wl.step_device()
         ctx.synchronize()
-        stage = {"ms": 0.0, "launches": 0.0, "cast_ms": 0.0, "merge_ms": 0.0, "total_ms": 0.0}
+        stage = {"ms": 0.0, "launches": 0.0, "cast_ms": 0.0, "merge_ms": 0.0, "total_ms": 0.0, "calls": 0.0}
 
         def collect(t):
             stage["ms"] += t["fused_ms"]
@@ -526,6 +527,7 @@ def run_ours(args) -> None:
             stage["cast_ms"] += t["cast_ms"]
             stage["merge_ms"] += t["merge_ms"]
             stage["total_ms"] += t["total_ms"]
+            stage["calls"] += t["calls"]      # passes of the timed region that carried stage marks (every --stage-timing-every-th)
 
         clocks = None
         launches0 = sdpa_b200.launch_count()
@@ -600,8 +602,8 @@ def run_ours(args) -> None:
                 "q_rows_per_s": r["m"] * r["steps"] / (r["ms_dev"] * 1e-3), "q_batches_per_step": r["q_batches"],
                 "e2e": {"value": r["e2e_value"], "unit": "TFLOP/s", "ms_per_step": r["ms_host"] / r["steps"],
                         "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
-                "stage_ms_per_step": {"cast": r["stage"]["cast_ms"] / r["steps"], "fused": r["stage"]["ms"] / r["steps"],
-                                      "merge": r["stage"]["merge_ms"] / r["steps"]},
+                "stage_ms_per_step": {"cast": r["stage"]["cast_ms"] / max(1.0, r["stage"]["calls"]), "fused": r["stage"]["ms"] / max(1.0, r["stage"]["calls"]),
+                                      "merge": r["stage"]["merge_ms"] / max(1.0, r["stage"]["calls"]), "passes_timed": r["stage"]["calls"]},
                 "gpu_launches": r["launches"], "parity_check": r["parity"],
             }
 
@@ -610,7 +612,8 @@ def run_ours(args) -> None:
     st = head["stage"]
     m, n, n_local = head["m"], head["n"], head["n_local"]
     kernel_name = head["kernel"]
-    flops_per_launch = 2.0 * m * n_local * (DK + DV) * K / max(1.0, st["launches"])
+    calls = max(1.0, st["calls"])
+    flops_per_launch = 2.0 * m * n_local * (DK + DV) * calls / max(1.0, st["launches"])   # launches counted over the same marked passes
     avg_ms = st["ms"] / max(1.0, st["launches"])
     achieved = flops_per_launch / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
@@ -647,14 +650,17 @@ def run_ours(args) -> None:
                 "merge": "none" if world == 1 else {"peer": "device-side exchange: root merge kernel reads shard states over NVLink (CUDA IPC) behind epoch flags",
                                                     "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
                                                     "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],
-                "submission": "K passes queued back to back (sdpa_enqueue_device_full), one wait after the last; e2e uses the blocking host call"},
+                "submission": "K passes queued back to back (sdpa_enqueue_device_full), one wait after the last; e2e uses the blocking host call",
+                "stage_timing": "CUDA-event stage marks (cast | fused | merge) on every %d-th queued pass of the timed region: "
+                                "a timestamp event costs ~2 us of stream time, 4 of them per pass were 3.6 %% of the c3 step "
+                                "(profiles/r02/visit6_g1_nomarks.json)" % args.stage_timing_every},
             "e2e": {"value": head["e2e_value"], "unit": "TFLOP/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
                     "ms_per_step": ms_host / K, "q_rows_per_s": m * K / (ms_host * 1e-3)},
             "gpu_launches": head["launches"],
             "clocks": clocks,
             "roofline": roofline,
-            "stage_ms_per_step": {"cast": st["cast_ms"] / K, "fused": st["ms"] / K, "merge": st["merge_ms"] / K,
-                                  "library_total": st["total_ms"] / K},
+            "stage_ms_per_step": {"cast": st["cast_ms"] / calls, "fused": st["ms"] / calls, "merge": st["merge_ms"] / calls,
+                                  "library_total": st["total_ms"] / calls, "passes_timed": st["calls"]},
             "parity_check": head["parity"],
             "configs": extras,
         }
@@ -705,6 +711,8 @@ def main() -> None:
                     help="cross-GPU merge: peer = device-side exchange over CUDA-IPC peer memory (default); nccl2/nccl3 = NCCL collectives")
     ap.add_argument("--extra", default="",
                     help="comma list of further BASELINE configs to run behind the headline (default: c2 at 1 GPU, c4 at 4, c5 at 8; 'none' = skip)")
+    ap.add_argument("--stage-timing-every", type=int, default=4,
+                    help="stage marks (CUDA events around cast / fused kernel / merge) on every k-th queued pass (1 = every pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -193,6 +193,9 @@ struct Shard {
     // single-GPU pass records 4 events, not 11.  Pairs accumulate call after call and are only turned into
     // numbers on demand (sdpa_last_timings / sdpa_accumulated_timings): the queries cost ~11 us of host time.
     std::vector<cudaEvent_t> marks;
+    bool marks_on = true;                    // this call records stage marks (queued passes may sample: sdpa_ctx::mark_every)
+    bool last_call_queued = false;           // the previous call ended without a host wait: its end mark is this call's begin mark
+    cudaEvent_t ev_begin = nullptr;          // ordering-only begin event of an unmarked call (side streams fork from it)
     size_t marks_used = 0;
     int open_mark = -1;                      // last mark on s_compute with nothing enqueued behind it, or -1
     std::vector<int> tpair[4];               // begin, end, begin, end, ...
@@ -217,7 +220,9 @@ struct sdpa_ctx {
     bool peer_ok = false;
     float last_timing[6] = {0, 0, 0, 0, 0, 0};
     bool last_timing_valid = true;          // false: last_timing[0..3] still have to be computed from the event pairs
-    double acc_fused_launches = 0, acc_calls = 0;
+    double acc_fused_launches = 0, acc_calls = 0;   // over the calls that recorded stage marks
+    int mark_every = 1;                     // queued passes: stage marks on every mark_every-th pass (SDPA_STAGE_TIMING_EVERY); blocking: always
+    unsigned long long queued_seq = 0;
     const char* last_kernel = "none";
     // Queued passes of a one-GPU-per-process context (sdpa_enqueue_device_full) alternate exchange slots and are not joined at
     // the end of the call, so the comm stream merges pass i while the compute stream already runs the cast and fused kernel
@@ -283,7 +288,7 @@ static bool stage_timing_enabled()
 
 static sdpa_status time_begin(Shard& s, int which, cudaStream_t st)
 {
-    if (which != 3 && !stage_timing_enabled()) return SDPA_OK;
+    if (!s.marks_on || (which != 3 && !stage_timing_enabled())) return SDPA_OK;
     int idx = -1;
     if (st == s.s_compute && s.open_mark >= 0) idx = s.open_mark;
     else SDPA_TRY(new_mark(s, st, &idx));
@@ -293,7 +298,7 @@ static sdpa_status time_begin(Shard& s, int which, cudaStream_t st)
 }
 static sdpa_status time_end(Shard& s, int which, cudaStream_t st, bool may_share = false)
 {
-    if (which != 3 && !stage_timing_enabled()) return SDPA_OK;
+    if (!s.marks_on || (which != 3 && !stage_timing_enabled())) return SDPA_OK;
     int idx = -1;
     if (may_share && st == s.s_compute && s.open_mark >= 0) idx = s.open_mark;   // nothing ran since the last end mark
     else SDPA_TRY(new_mark(s, st, &idx));
@@ -436,6 +441,7 @@ static void shard_destroy(Shard& s, const NcclApi* api)
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s.marks) cudaEventDestroy(e);
+    if (s.ev_begin) cudaEventDestroy(s.ev_begin);
     cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out};
     for (cudaStream_t st : sts)
         if (st) cudaStreamDestroy(st);
@@ -800,6 +806,8 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         for (Shard& s : ctx->shards)
             if (s.plan) umma_plan_allow_v8(s.plan, by_pieces);
 
+    // stage marks: every blocking call; queued passes on every mark_every-th pass (each timestamp event costs ~2 us of stream time)
+    const bool marked = blocking || ctx->mark_every <= 1 || (ctx->queued_seq++ % (unsigned long long)ctx->mark_every) == 0;
     // which side streams this call touches (the others are neither forked nor joined: every stream operation
     // between two kernels costs front-end time on the GPU)
     const bool use_in = !on_device;                                  // H2D of the Q batches
@@ -814,17 +822,28 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             SDPA_TRY(fold_timings(s));
         }
         for (int w = 0; w < 4; ++w) s.tpair_last[w] = s.tpair[w].size();
-        compute_stream_touched(s);   // whatever ran before this call is not part of it
+        // Whatever ran before this call is not part of it -- except when both this and the previous call are queued passes:
+        // nothing separates them on the compute stream, so the previous end mark IS this call's begin mark (one event less).
+        if (!(s.last_call_queued && !blocking && s.marks_on && marked)) compute_stream_touched(s);
+        s.marks_on = marked;
         s.q_lo_off = (size_t)(((B + 127) & ~127) + 128) * dk;
         if (is_umma(ctx->prec))
             for (int b = 0; b < 2; ++b)
                 SDPA_TRY(umma_plan_bind_q(s.plan, b, s.qc[b].as<__nv_bfloat16>(), (B + 127) & ~127, dk, prec_hl(ctx->prec), s.q_lo_off));
         SDPA_TRY(time_begin(s, 3, s.s_compute));
         // the side streams this call uses start after the begin mark, so that "total" brackets everything
-        cudaEvent_t begun = s.marks[s.tpair[3].back()];
-        if (use_in) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, begun, 0));
-        if (use_comm) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, begun, 0));
-        if (use_out) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, begun, 0));
+        if (use_in || use_comm || use_out) {
+            cudaEvent_t begun = nullptr;
+            if (marked) begun = s.marks[s.tpair[3].back()];
+            else {
+                if (!s.ev_begin) SDPA_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_begin, cudaEventDisableTiming));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_begin, s.s_compute));
+                begun = s.ev_begin;
+            }
+            if (use_in) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_in, begun, 0));
+            if (use_comm) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, begun, 0));
+            if (use_out) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_out, begun, 0));
+        }
     }
 
     if (use_ipc) SDPA_TRY(ipc_setup(ctx, std::max(B, 8192), dv));
@@ -1188,9 +1207,12 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
 
     const double hp2 = host_prof ? host_now_us() : 0.0;
     if (overlap) ctx->exchange_pending = true;
-    ctx->last_timing_valid = false;   // evaluated lazily by sdpa_last_timings / sdpa_accumulated_timings
-    ctx->acc_fused_launches += fused_launches;
-    ctx->acc_calls += 1;
+    for (Shard& s : ctx->shards) s.last_call_queued = !blocking;
+    if (marked) {
+        ctx->last_timing_valid = false;   // evaluated lazily by sdpa_last_timings / sdpa_accumulated_timings
+        ctx->acc_fused_launches += fused_launches;
+        ctx->acc_calls += 1;
+    }
     if (host_prof) {
         const double hp3 = host_now_us();
         fprintf(stderr, "sdpa host profile: enqueue %.1f us, join+sync %.1f us, event queries %.1f us (device total %.1f us)\n",
@@ -1240,6 +1262,8 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
         SDPA_TRY(reserve_batch_buffers(ctx, s, B, splits, true));   // every GPU delivers rows: all need the fp64 out buffers
         if (s.marks_used > 2048) SDPA_TRY(fold_timings(s));
         for (int w = 0; w < 4; ++w) s.tpair_last[w] = s.tpair[w].size();
+        s.marks_on = true;
+        s.last_call_queued = false;
         compute_stream_touched(s);
         s.q_lo_off = (size_t)(((B + 127) & ~127) + 128) * dk;
         if (is_umma(ctx->prec)) {
@@ -1529,6 +1553,7 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
     ctx->world = world;
     ctx->rank_base = cfg.rank_base;
     {
+        if (const char* me = getenv("SDPA_STAGE_TIMING_EVERY")) ctx->mark_every = std::max(1, atoi(me));
         const char* ov = getenv("SDPA_OVERLAP_PASSES");   // SDPA_OVERLAP_PASSES=0: every queued pass joins its exchange before the next starts
         ctx->overlap_passes = !(ov && *ov == '0');
     }
@@ -1554,6 +1579,25 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
                 cudaGetLastError();
             }
         ctx->peer_ok = all;
+        // work buffers live in the devices' stream-ordered memory pools: peers read each other's exchange state, so every
+        // local device gets read/write access to every other local device's pool (cudaDeviceEnablePeerAccess does not cover pools)
+        if (all && mem_pool_enabled()) {
+            for (int i = 0; i < L; ++i) {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, ctx->shards[i].dev) != cudaSuccess) continue;
+                std::vector<cudaMemAccessDesc> desc;
+                for (int j = 0; j < L; ++j) {
+                    if (i == j) continue;
+                    cudaMemAccessDesc d{};
+                    d.location.type = cudaMemLocationTypeDevice;
+                    d.location.id = ctx->shards[j].dev;
+                    d.flags = cudaMemAccessFlagsProtReadWrite;
+                    desc.push_back(d);
+                }
+                if (!desc.empty() && cudaMemPoolSetAccess(pool, desc.data(), desc.size()) != cudaSuccess) ctx->peer_ok = false;
+            }
+            cudaGetLastError();
+        }
     }
     // NCCL communicator(s)
     const bool need_nccl = world > 1 && !(cfg.merge == SDPA_MERGE_PEER && ctx->peer_ok && world == L);

@@ -89,34 +89,47 @@ struct SyncArgs {
     unsigned long long* trace;
 };
 
+// Entry / exit protocol shared by the merge kernels (sync.enabled bit 0 / bit 1):
+//   entry: spin until every `ready` flag carries spin_epoch -- the shards' "state published" flags (cross-GPU merge on the
+//          root), or the root's "slot consumed" flag (a shard's own split merge about to overwrite its exchange slot);
+//   exit : the last block releases `consumed` = epoch -- "peers' slots may be reused" / "this shard's state is published".
+__device__ __forceinline__ void sync_enter(const SyncArgs& sync, int count)
+{
+    if (!(sync.enabled & 1)) return;
+    const int nready = sync.nready > 0 ? sync.nready : count;
+    const bool root_merge = sync.nready == 0;
+    if (sync.trace && root_merge && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[1] = global_ns();
+    if ((int)threadIdx.x < nready) {
+        spin_until(sync.ready[threadIdx.x], sync.spin_epoch, 2);
+        if (sync.trace && root_merge && blockIdx.x == 0 && threadIdx.x < 8) sync.trace[4 + threadIdx.x] = global_ns();   // flag r seen (root's clock)
+    }
+    __syncthreads();
+    if (sync.trace && root_merge && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[2] = global_ns();
+}
+__device__ __forceinline__ void sync_exit(const SyncArgs& sync)
+{
+    if (!(sync.enabled & 2)) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();   // the rows just written may sit in another GPU's memory / are read by another GPU next
+        if (atomicAdd(sync.block_counter, 1u) == gridDim.x - 1) {
+            *sync.block_counter = 0;
+            __threadfence_system();
+            st_release_sys(sync.consumed, sync.epoch);
+            if (sync.trace) sync.trace[(sync.enabled & 1) && sync.nready == 0 ? 3 : 0] = global_ns();   // [3] root merge done, [0] state published
+        }
+    }
+}
+
 template <bool FINAL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict__ out64,
                     float* __restrict__ contrib, float* __restrict__ tmax_out,
                     float* __restrict__ lsum_out, float max_unit, bool vec_ok, const SyncArgs sync)
 {
-    if (sync.enabled) {
-        // fused exchange: the states live on other GPUs; wait until each of them has published this epoch
-        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[1] = global_ns();
-        if (threadIdx.x < count) spin_until(sync.ready[threadIdx.x], sync.spin_epoch, 2);
-        __syncthreads();
-        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[2] = global_ns();
-    }
+    sync_enter(sync, count);
     merge_rows<FINAL>(st, count, rows, dv, out64, contrib, tmax_out, lsum_out, max_unit, vec_ok);
-    if (sync.enabled) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();   // the rows just written may sit in another GPU's memory (sliced merge)
-            if (atomicAdd(sync.block_counter, 1u) == gridDim.x - 1) {
-                *sync.block_counter = 0;
-                __threadfence_system();
-                // root merge: every block has read the peers' buffers, they may be reused;
-                // sliced merge: this rank's rows of the result are in the root's staging buffer
-                st_release_sys(sync.consumed, sync.epoch);
-                if (sync.trace) sync.trace[3] = global_ns();
-            }
-        }
-    }
+    sync_exit(sync);
 }
 
 template <bool FINAL>
@@ -191,104 +204,6 @@ __device__ __forceinline__ void merge_one_row(const StatePtrs& st, int count, in
         *lsum_dst = gsum;
     }
 }
-
-// Flat form for up to 8 states and dv % 4 == 0: one thread owns 4 consecutive columns of one row and issues EVERY load of
-// its merge (the states' tmax, lsum and 16-byte o vectors) before the first use, so a row costs one memory round trip
-// instead of the three dependent ones of the warp-per-row form (statistics -> shuffles -> vectors); the row statistics are
-// recomputed by the 32 (dv = 128) threads that share a row -- same addresses, one broadcast transaction per warp.
-// COUNT_FROM_MAP: the number of states of a row comes from the persistent kernel's work map (pieces of its row block).
-template <bool FINAL, bool COUNT_FROM_MAP>
-__global__ void __launch_bounds__(256)
-merge_flat_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict__ out64, float* __restrict__ contrib,
-                  float* __restrict__ tmax_out, float* __restrict__ lsum_out, float max_unit, WorkMap wm, int max_pieces,
-                  const unsigned int* __restrict__ guard, unsigned int epoch, const SyncArgs sync)
-{
-    if (sync.enabled & 1) {
-        // flags to wait for: every shard's "state published" (cross-GPU merge), or the root's "slot consumed" (a shard's own
-        // split merge about to overwrite its exchange slot).  Thread r records when flag r was seen (root's clock).
-        const int nready = sync.nready > 0 ? sync.nready : count;
-        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[1] = global_ns();
-        if (threadIdx.x < nready) {
-            spin_until(sync.ready[threadIdx.x], sync.spin_epoch, 2);
-            if (sync.trace && blockIdx.x == 0 && threadIdx.x < 8 && sync.nready == 0) sync.trace[4 + threadIdx.x] = global_ns();
-        }
-        __syncthreads();
-        if (sync.trace && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[2] = global_ns();
-    }
-    const int vec_per_row = dv >> 2;
-    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = (int)(idx / vec_per_row);
-    const int d = (int)(idx - (size_t)row * vec_per_row) << 2;
-    // pieces per row block: 64-bit divisions, so they are taken once per CTA (its rows span at most a few 256-row blocks)
-    __shared__ int s_count[4];
-    [[maybe_unused]] int rb_first = 0;
-    if constexpr (COUNT_FROM_MAP) {
-        rb_first = (int)(((size_t)blockIdx.x * blockDim.x) / vec_per_row) / 256;
-        if (threadIdx.x < 4) s_count[threadIdx.x] = (*guard == epoch) ? max_pieces : (rb_first + (int)threadIdx.x < wm.RB ? wm_pieces(wm, rb_first + threadIdx.x) : 0);
-        __syncthreads();
-    }
-    if (row < rows) {
-        int n = count;
-        if constexpr (COUNT_FROM_MAP) {
-            const int k = row / 256 - rb_first;
-            n = k < 4 ? s_count[k] : ((*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256));
-        }
-        float t[8], l[8];
-        float4 v[8];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            if (s < n) {
-                t[s] = st.tmax[s][row];
-                l[s] = st.lsum[s][row];
-                v[s] = *reinterpret_cast<const float4*>(st.o[s] + (size_t)row * dv + d);
-            }
-        }
-        float gmax = -CUDART_INF_F;
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-            if (s < n) gmax = fmaxf(gmax, t[s]);
-        float gsum = 0.f;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            if (s < n) {
-                const float w = (t[s] == -CUDART_INF_F) ? 0.f : exp2f(t[s] - gmax);   // all states empty: weights 0, output 0
-                gsum = fmaf(l[s], w, gsum);
-                acc.x = fmaf(v[s].x, w, acc.x);
-                acc.y = fmaf(v[s].y, w, acc.y);
-                acc.z = fmaf(v[s].z, w, acc.z);
-                acc.w = fmaf(v[s].w, w, acc.w);
-            }
-        }
-        if (FINAL) {
-            const float inv = (gsum == 0.f) ? 0.f : 1.f / gsum;
-            double2* dst = reinterpret_cast<double2*>(out64 + (size_t)row * dv + d);
-            dst[0] = make_double2((double)(acc.x * inv), (double)(acc.y * inv));
-            dst[1] = make_double2((double)(acc.z * inv), (double)(acc.w * inv));
-        } else {
-            *reinterpret_cast<float4*>(contrib + (size_t)row * dv + d) = acc;
-            if (d == 0) {
-                tmax_out[row] = gmax * max_unit;
-                lsum_out[row] = gsum;
-            }
-        }
-    }
-    if (sync.enabled & 2) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            if (atomicAdd(sync.block_counter, 1u) == gridDim.x - 1) {
-                *sync.block_counter = 0;
-                __threadfence_system();
-                st_release_sys(sync.consumed, sync.epoch);   // "merged": the peers' slots may be reused / this shard's state is published
-                if (sync.trace) sync.trace[(sync.enabled & 1) && sync.nready == 0 ? 3 : 0] = global_ns();
-            }
-        }
-    }
-}
-
-inline int flat_blocks(int rows, int dv) { return (int)(((size_t)rows * (dv >> 2) + 255) / 256); }
-inline bool flat_ok(int states, int dv, bool vec_ok) { return states <= 8 && (dv & 3) == 0 && vec_ok && getenv("SDPA_MERGE_FLAT_OFF") == nullptr; }
 
 // contrib *= 2^(tmax - gmax), lsum *= 2^(tmax - gmax)        (mpi.c:346-351)
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -380,13 +295,16 @@ template <bool FINAL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 merge_pieces_kernel(StatePtrs st, WorkMap wm, int max_pieces, int rows, int dv, double* __restrict__ out64, float* __restrict__ contrib,
                     float* __restrict__ tmax_out, float* __restrict__ lsum_out, bool vec_ok, const unsigned int* __restrict__ guard,
-                    unsigned int epoch)
+                    unsigned int epoch, const SyncArgs sync)
 {
+    sync_enter(sync, 0);
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int count = (*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256);
-    merge_one_row<FINAL>(st, count, row, dv, FINAL ? out64 + (size_t)row * dv : nullptr, FINAL ? nullptr : contrib + (size_t)row * dv,
-                         FINAL ? nullptr : tmax_out + row, FINAL ? nullptr : lsum_out + row, 1.f, vec_ok);
+    if (row < rows) {
+        const int count = (*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256);
+        merge_one_row<FINAL>(st, count, row, dv, FINAL ? out64 + (size_t)row * dv : nullptr, FINAL ? nullptr : contrib + (size_t)row * dv,
+                             FINAL ? nullptr : tmax_out + row, FINAL ? nullptr : lsum_out + row, 1.f, vec_ok);
+    }
+    sync_exit(sync);
 }
 
 // Root GPU, sliced merge: wait until every rank has delivered its rows of the batch into the staging buffer,
@@ -415,10 +333,8 @@ collect_slices_kernel(double2* __restrict__ dst, const double2* __restrict__ src
 void preload_merge_kernels()
 {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, merge_flat_kernel<true, false>);
-    cudaFuncGetAttributes(&a, merge_flat_kernel<false, false>);
-    cudaFuncGetAttributes(&a, merge_flat_kernel<true, true>);
-    cudaFuncGetAttributes(&a, merge_flat_kernel<false, true>);
+    cudaFuncGetAttributes(&a, merge_pieces_kernel<true>);
+    cudaFuncGetAttributes(&a, merge_pieces_kernel<false>);
     cudaFuncGetAttributes(&a, merge_states_kernel<true>);
     cudaFuncGetAttributes(&a, merge_states_kernel<false>);
     cudaFuncGetAttributes(&a, signal_flag_kernel);
@@ -437,8 +353,7 @@ sdpa_status launch_finalize_reduced(double* out64, const float* reduced, const f
 }
 
 // `publish` (exchange slot hand-over of one shard): wait until *publish->wait_flag >= wait_epoch (the root has consumed the
-// slot's previous content; NULL = no wait), merge, then release publish->flag = epoch.  Fused into the flat merge kernel; the
-// warp-per-row fallback brackets the merge with the 1-thread wait / signal kernels.
+// slot's previous content; NULL = no wait), merge, then release publish->flag = epoch -- all inside the merge kernel.
 static SyncArgs publish_args(const PublishSync* publish)
 {
     SyncArgs sa{};
@@ -470,33 +385,17 @@ sdpa_status launch_merge_splits(Partials part, int rows, int dv, double* out64, 
         st.tmax[s] = part.tmax + (size_t)s * part.rows_capacity;
         st.lsum[s] = part.lsum + (size_t)s * part.rows_capacity;
     }
-    const int blocks = ceil_div(rows, kWarpsPerBlock);
+    const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     bool vec_ok = al16(out64) && al16(contrib);
     for (int s = 0; s < part.splits; ++s) vec_ok = vec_ok && al16(st.o[s]);
-    const float unit = natural_log_max ? kLn2 : 1.f;
-    if (flat_ok(part.splits, dv, vec_ok)) {
-        const int fb = std::max(1, flat_blocks(rows, dv));
-        const SyncArgs sa = publish_args(publish);
-        if (out64 != nullptr)
-            merge_flat_kernel<true, false><<<fb, 256, 0, stream>>>(st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f,
-                                                                  WorkMap{0, 0, 0}, 0, nullptr, 0, sa);
-        else
-            merge_flat_kernel<false, false><<<fb, 256, 0, stream>>>(st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out, unit,
-                                                                   WorkMap{0, 0, 0}, 0, nullptr, 0, sa);
-        count_launch();
-    } else {
-        if (publish && publish->wait_flag) SDPA_TRY(launch_wait_flag(publish->wait_flag, publish->wait_epoch, stream));
-        if (rows > 0) {
-            if (out64 != nullptr)
-                merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr,
-                                                                                     1.f, vec_ok, SyncArgs{});
-            else
-                merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, nullptr, contrib, tmax_out,
-                                                                                      lsum_out, unit, vec_ok, SyncArgs{});
-            count_launch();
-        }
-        if (publish) SDPA_TRY(launch_signal_flag(publish->flag, publish->epoch, stream, publish->trace));
-    }
+    const SyncArgs sa = publish_args(publish);
+    if (out64 != nullptr)
+        merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, out64, nullptr, nullptr, nullptr, 1.f,
+                                                                             vec_ok, sa);
+    else
+        merge_states_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, nullptr, contrib, tmax_out, lsum_out,
+                                                                              natural_log_max ? kLn2 : 1.f, vec_ok, sa);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
@@ -552,12 +451,8 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     bool vec_ok = al16(out64);
     for (int s = 0; s < shards; ++s) vec_ok = vec_ok && al16(st.o[s]);
-    if (flat_ok(shards, dv, vec_ok) && rows > 0)
-        merge_flat_kernel<true, false><<<flat_blocks(rows, dv), 256, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr, nullptr, 1.f,
-                                                                                 WorkMap{0, 0, 0}, 0, nullptr, 0, sa);
-    else
-        merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
-                                                                             nullptr, 1.f, vec_ok, sa);
+    merge_states_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, shards, rows, dv, out64, nullptr, nullptr,
+                                                                         nullptr, 1.f, vec_ok, sa);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
@@ -581,26 +476,13 @@ sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces
         st.lsum[s] = part.lsum + (size_t)s * part.rows_capacity;
         vec_ok = vec_ok && al16(st.o[s]);
     }
-    const int blocks = ceil_div(rows, kWarpsPerBlock);
-    if (flat_ok(max_pieces, dv, vec_ok)) {
-        const int fb = std::max(1, flat_blocks(rows, dv));
-        const SyncArgs sa = publish_args(publish);
-        if (out64) merge_flat_kernel<true, true><<<fb, 256, 0, stream>>>(st, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr, 1.f, wm, max_pieces,
-                                                                        guard, epoch, sa);
-        else merge_flat_kernel<false, true><<<fb, 256, 0, stream>>>(st, max_pieces, rows, dv, nullptr, contrib, tmax_out, lsum_out, 1.f, wm, max_pieces,
-                                                                   guard, epoch, sa);
-        count_launch();
-    } else {
-        if (publish && publish->wait_flag) SDPA_TRY(launch_wait_flag(publish->wait_flag, publish->wait_epoch, stream));
-        if (rows > 0) {
-            if (out64) merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr,
-                                                                                            vec_ok, guard, epoch);
-            else merge_pieces_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, nullptr, contrib, tmax_out,
-                                                                                       lsum_out, vec_ok, guard, epoch);
-            count_launch();
-        }
-        if (publish) SDPA_TRY(launch_signal_flag(publish->flag, publish->epoch, stream, publish->trace));
-    }
+    const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
+    const SyncArgs sa = publish_args(publish);
+    if (out64) merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr,
+                                                                                    vec_ok, guard, epoch, sa);
+    else merge_pieces_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, nullptr, contrib, tmax_out, lsum_out,
+                                                                               vec_ok, guard, epoch, sa);
+    count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
 }
