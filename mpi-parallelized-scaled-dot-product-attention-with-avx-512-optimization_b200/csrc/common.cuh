@@ -160,7 +160,9 @@ struct RouteTargets {
     unsigned int epoch;
     int world;
 };
-sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const RouteTargets& to, cudaStream_t stream);
+// wm != NULL: the partials come from the persistent fused kernel (pieces per row block, see launch_merge_pieces)
+sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const RouteTargets& to, cudaStream_t stream, const WorkMap* wm = nullptr,
+                                       int max_pieces = 0, const unsigned int* guard = nullptr, unsigned int guard_epoch = 0);
 // Sliced merge, root side: wait for every rank's "my rows are staged" flag (sync.ready), copy the staged fp64 batch
 // to dst, then raise sync.consumed.
 sdpa_status launch_collect_slices(double* dst, const double* staged, int rows, int dv, const PeerSync& sync, int ranks,

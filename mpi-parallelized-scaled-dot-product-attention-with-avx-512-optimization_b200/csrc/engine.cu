@@ -791,11 +791,11 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     splits = std::max(1, std::min(splits, 64));
     // The persistent fused kernel (dk = dv = 128 bf16, enough work per SM pair) cuts every row block into pieces; its piece
     // count replaces the split count and the split merge reads pieces per row block (launch_merge_pieces).  Every shard must
-    // own the same number of keys (the partial buffers and the piece count are shared); the sliced exchange routes by splits.
+    // own the same number of keys (the partial buffers and the piece count are shared).
     bool by_pieces = false;
     bool same_n = true;
     for (Shard& s : ctx->shards) same_n = same_n && s.n_local == ctx->shards[0].n_local;
-    if (ctx->prec == SDPA_PREC_BF16 && dk == 128 && dv == 128 && ctx->cfg.kv_splits <= 0 && same_n && !(use_ipc && ipc_sliced_requested())) {
+    if (ctx->prec == SDPA_PREC_BF16 && dk == 128 && dv == 128 && ctx->cfg.kv_splits <= 0 && same_n) {
         const int pieces = attn_umma_v8_pieces(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
         if (pieces > 1) {
             splits = pieces;
@@ -953,7 +953,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                             to.block_counter = x.flags.as<unsigned int>() + 10 + b;
                             to.epoch = x.epoch;
                             to.world = world;
-                            SDPA_TRY(launch_merge_splits_routed(part, bs, dv, to, s.s_compute));
+                            SDPA_TRY(launch_merge_splits_routed(part, bs, dv, to, s.s_compute, pieces ? &wm : nullptr, max_pieces, guard, guard_epoch));
                         } else {
                             // one launch: wait for the root's "consumed" flag of this slot, merge the shard's partial states
                             // into the slot, publish the epoch flag

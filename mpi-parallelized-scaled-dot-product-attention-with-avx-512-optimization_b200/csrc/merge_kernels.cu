@@ -258,6 +258,11 @@ struct RouteArgs {
     unsigned int* block_counter;
     unsigned int epoch;
     int base, rem, world;       // slice r has base + (r < rem) rows, slices are consecutive
+    // states per row: `count`, or (persistent fused kernel) the pieces of the row's block / all max_pieces after the exact twin
+    WorkMap wm;
+    int max_pieces;             // 0: every row has `count` states
+    const unsigned int* guard;
+    unsigned int guard_epoch;
 };
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
@@ -274,7 +279,8 @@ merge_route_kernel(StatePtrs st, int count, int rows, int dv, RouteArgs rt, bool
             r = rt.rem + (row - boundary) / rt.base;
             local = (row - boundary) - (r - rt.rem) * rt.base;
         }
-        merge_one_row<false>(st, count, row, dv, nullptr, rt.o[r] + (size_t)local * dv, rt.tmax[r] + local, rt.lsum[r] + local,
+        const int n = rt.max_pieces > 0 ? ((*rt.guard == rt.guard_epoch) ? rt.max_pieces : wm_pieces(rt.wm, row / 256)) : count;
+        merge_one_row<false>(st, n, row, dv, nullptr, rt.o[r] + (size_t)local * dv, rt.tmax[r] + local, rt.lsum[r] + local,
                              1.f, vec_ok);
     }
     __syncthreads();
@@ -487,7 +493,8 @@ sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces
     return SDPA_OK;
 }
 
-sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const RouteTargets& to, cudaStream_t stream)
+sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const RouteTargets& to, cudaStream_t stream, const WorkMap* wm,
+                                       int max_pieces, const unsigned int* guard, unsigned int guard_epoch)
 {
     if (part.splits < 1 || part.splits > 64 || to.world < 1 || to.world > 64) {
         set_error("routed merge supports 1..64 split states and ranks");
@@ -515,6 +522,10 @@ sdpa_status launch_merge_splits_routed(Partials part, int rows, int dv, const Ro
     rt.world = to.world;
     rt.base = rows / to.world;
     rt.rem = rows % to.world;
+    rt.wm = wm ? *wm : WorkMap{0, 0, 0};
+    rt.max_pieces = wm ? max_pieces : 0;
+    rt.guard = guard;
+    rt.guard_epoch = guard_epoch;
     merge_route_kernel<<<std::max(1, ceil_div(rows, kWarpsPerBlock)), kWarpsPerBlock * 32, 0, stream>>>(st, part.splits, rows, dv, rt,
                                                                                                        vec_ok);
     count_launch();
