@@ -48,7 +48,8 @@ typedef enum sdpa_precision {
 /* How the per-shard softmax states are merged across GPUs (mpi.c:340-380). */
 typedef enum sdpa_merge {
     SDPA_MERGE_NCCL = 0, /* allreduce(MAX), allreduce(SUM), reduce(SUM): the reference's three collectives */
-    SDPA_MERGE_PEER = 1, /* fused device-side exchange over NVLink peer memory (single process only)       */
+    SDPA_MERGE_PEER = 1, /* fused device-side exchange over NVLink peer memory: one process driving several GPUs (peer
+                            access), or one process per GPU (slots and flags shared through CUDA IPC)                */
     SDPA_MERGE_NCCL2 = 2 /* same arithmetic in two collectives: allreduce(MAX), then ONE reduce(SUM) over
                             [contrib | lsum] with the normalisation + fp64 cast fused after it (default)   */
 } sdpa_merge;

@@ -74,3 +74,38 @@ def test_world_size_2_host_logic(sdpa, oracle, tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _bench_data_worker(rank, world, port, out_dir):
+    """bench.py's oracle check regenerates every rank's K/V shard on rank 0: the regenerated shards must be the arrays the ranks
+    built for themselves (same seeds, same owner_count split), for the weak-scaling headline and for a fixed-n config."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    for name in ("c3", "c5"):
+        m, rows = bench.config_shape(name, world, 0, 1000 if name == "c3" else 0)
+        if name == "c5":
+            rows = [r // 512 for r in rows]          # same split rule, test-sized
+        K, V = bench.make_shard(rank, rows[rank])
+        mine = torch.tensor([float(K.sum()), float(V.sum()), float(K[0, 0]), float(V[-1, -1]), float(rows[rank])], dtype=torch.float64)
+        got = [torch.zeros(5, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(got, mine)
+        if rank == 0:
+            for r in range(world):
+                Kr, Vr = bench.make_shard(r, rows[r])
+                want = torch.tensor([float(Kr.sum()), float(Vr.sum()), float(Kr[0, 0]), float(Vr[-1, -1]), float(rows[r])], dtype=torch.float64)
+                assert torch.equal(got[r], want), (name, r)
+        q = bench.make_q(64)
+        qs = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(qs, q.sum().reshape(1))
+        assert all(torch.equal(x, qs[0]) for x in qs)     # Q is replicated: identical on every rank
+    Path(out_dir, f"okb{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_world_size_2_bench_shards_are_reproducible(tmp_path):
+    world = 2
+    mp.spawn(_bench_data_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"okb{r}").exists() for r in range(world))
