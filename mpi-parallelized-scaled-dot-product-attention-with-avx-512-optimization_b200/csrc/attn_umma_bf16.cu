@@ -33,9 +33,6 @@ using namespace umma;
 
 constexpr int HEAD = 128;            // dk == dv
 constexpr float kGuardThreshold = 64.0f;              // fast mode: exponents beyond 2^64 hand the launch to the safe kernel
-constexpr int kDefaultV8Opt = 0;                      // persistent kernel: bit 0 = V producer warp, bit 1 = progressive P stores
-constexpr int kDefaultV8Poly = 0;
-constexpr int kDefaultPoly = 0;                       // of every 16 exponentials, this many run on the FMA pipe (0, 4 or 8)
 
 struct KernelParams {
     int rows;            // valid Q rows
@@ -87,15 +84,16 @@ struct __align__(1024) SharedV7 {
 };
 
 
-// GROUPS = softmax groups ping-ponged over alternating key tiles (group g owns tiles j = g mod GROUPS and the
+// Two softmax groups ping-pong over alternating key tiles (group g owns tiles j = g mod GROUPS and the
 // S/P buffers g): with the reference fixed by the first tile the tiles are independent, so while one
 // group sits in its fixed latencies (barrier wake-up, TMEM store drain, remote arrive) the other keeps the
 // MUFU / FMA pipes busy.  The groups' row sums are added in the epilogue.
-template <bool TRACE, int POLY, int NPARTS, int GROUPS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * NPARTS * GROUPS, 1)
+template <bool TRACE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
 attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
 {
+    constexpr int NPARTS = 2, GROUPS = 2;   // (row, 64-key half) threads; two softmax groups
     extern __shared__ uint8_t smem_raw[];
     SharedV7& sm = *reinterpret_cast<SharedV7*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
@@ -147,8 +145,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
     };
 
     if (warp < 4) {
-        if constexpr (NPARTS * GROUPS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (num_tiles > 0) {
             if (warp == 0) {
                 // ================================ TMA producer ================================
@@ -253,8 +250,7 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
             }
         }
     } else {
-        if constexpr (NPARTS * GROUPS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         constexpr int COLS = TILE / NPARTS;            // keys (S columns) per thread: 64 or 32
         constexpr int OCOLS = HEAD / (NPARTS * GROUPS); // output columns per thread in the epilogue
         const int sw = warp - 4;
@@ -282,16 +278,9 @@ attn_umma_kernel_v7(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 for (int c = 0; c < 16; c += 2) {
                     const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
                     const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
-                    float p0, p1;
-                    const bool poly = (POLY == 4 && (c == 2 || c == 10)) || (POLY == 8 && (c & 2));
-                    if (poly) {
-                        exp2_poly_x2(t2, p0, p1);
-                    } else {
-                        float t0, t1;
-                        unpack_f32x2(t2, t0, t1);
-                        p0 = fast_exp2(t0);
-                        p1 = fast_exp2(t1);
-                    }
+                    float t0, t1;
+                    unpack_f32x2(t2, t0, t1);
+                    const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
                     const uint64_t p2 = pack_f32x2(p0, p1);
                     if (c & 4) acc1 = add_f32x2(acc1, p2);
                     else acc0 = add_f32x2(acc0, p2);
@@ -508,10 +497,8 @@ struct SegCursor {
     }
 };
 
-// POLY: of every 16 exponentials, this many run on the FMA pipe (degree-3 polynomial) instead of the MUFU.  VW: the V tiles have
-// their own TMA producer warp (warp 2), so a K load never queues behind a V slot that is still being read.  PS: P is
-// stored chunk by chunk (the wait for PV(g-2) sits after the first two chunks) instead of being held in 32 registers.
-template <int POLY, bool VW, bool PS>
+// (Measured and rejected in round 2, profiles/README.md: a separate V producer warp, P stored chunk by chunk, part of the
+// exponentials as a polynomial on the FMA pipe.)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1)
 attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const KernelParams prm)
@@ -592,27 +579,6 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                             tma_load_2d_2sm(sm.k[ks], &map_khalf, &sm.k_full[ks], 0, key0 + 64 * (int)rank);
                             tma_load_2d_2sm(sm.k[ks] + HALF_TILE_BYTES / 2, &map_khalf, &sm.k_full[ks], 64, key0 + 64 * (int)rank);
                         }
-                        if constexpr (!VW) {
-                            mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
-                            if (elect_one_sync()) {
-                                if (leader) mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
-                                else mbar_arrive_cluster(map_to_cta(&sm.v_full[vs], 0));
-                                tma_load_2d_2sm(sm.v[vs], &map_v, &sm.v_full[vs], 64 * (int)rank, key0);
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-            } else if (VW && warp == 2) {
-                // ================================ TMA producer of the V tiles ==================
-                SegCursor cur;
-                cur.init(unit_begin, unit_end, T);
-                int g = 0;
-                while (cur.next()) {
-                    for (int j = 0; j < cur.nt; ++j, ++g) {
-                        const int vs = g % V7_VSTAGES;
-                        const uint32_t vph = (uint32_t)(g / V7_VSTAGES) & 1u;
-                        const int key0 = (cur.t0 + j) * TILE;
                         mbar_wait(&sm.v_empty[vs], vph ^ 1u, 110 + vs);
                         if (elect_one_sync()) {
                             if (leader) mbar_arrive_expect_tx(&sm.v_full[vs], TILE_BYTES);
@@ -730,17 +696,9 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 for (int c = 0; c < 16; c += 2) {
                     const uint64_t x2 = pack_f32x2(__uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
                     const uint64_t t2 = fma_f32x2(x2, scale2, neg_ref2);
-                    float p0, p1;
-                    const bool poly = (POLY == 2 && c == 6) || (POLY == 4 && (c == 2 || c == 10)) || (POLY == 6 && (c == 2 || c == 6 || c == 12)) ||
-                                      (POLY == 8 && (c & 2));
-                    if (poly) {
-                        exp2_poly_x2(t2, p0, p1);
-                    } else {
-                        float t0, t1;
-                        unpack_f32x2(t2, t0, t1);
-                        p0 = fast_exp2(t0);
-                        p1 = fast_exp2(t1);
-                    }
+                    float t0, t1;
+                    unpack_f32x2(t2, t0, t1);
+                    const float p0 = fast_exp2(t0), p1 = fast_exp2(t1);
                     const uint64_t p2 = pack_f32x2(p0, p1);
                     if (c & 4) acc1 = add_f32x2(acc1, p2);
                     else acc0 = add_f32x2(acc0, p2);
@@ -790,23 +748,6 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 }
                 const uint64_t neg_ref2 = pack_f32x2(-m_ref * scale, -m_ref * scale);
                 uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
-                if constexpr (PS) {
-                    // P buffer sb is read by PV(g-2), issued two tiles ago: by the time two chunks of exponentials are done it has
-                    // normally completed, so the wait costs nothing and the remaining chunks are stored as they are produced
-                    uint32_t pa[16];
-                    exp_chunk(sr, neg_ref2, acc0, acc1, pa);
-                    exp_chunk(sr + 16, neg_ref2, acc0, acc1, pa + 8);
-                    if (g >= 2) mbar_wait(&sm.pv_done[sb], (uint32_t)((g >> 1) - 1) & 1u, 310 + sb);
-                    tcgen05_fence_after();
-                    SDPA_TMEM_ST8(p_addr, pa);
-                    SDPA_TMEM_ST8(p_addr + 8, (pa + 8));
-                    uint32_t pb[8];
-                    exp_chunk(sr + 32, neg_ref2, acc0, acc1, pb);
-                    SDPA_TMEM_ST8(p_addr + 16, pb);
-                    uint32_t pc[8];
-                    exp_chunk(sr + 48, neg_ref2, acc0, acc1, pc);
-                    SDPA_TMEM_ST8(p_addr + 24, pc);
-                } else {
                 uint32_t pr[COLS / 2];
 #pragma unroll
                 for (int ch = 0; ch < COLS / 16; ++ch) exp_chunk(sr + 16 * ch, neg_ref2, acc0, acc1, pr + 8 * ch);
@@ -814,7 +755,6 @@ attn_umma_kernel_v8(const __grid_constant__ CUtensorMap map_khalf, const __grid_
                 tcgen05_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < COLS / 16; ++ch) SDPA_TMEM_ST8(p_addr + 8 * ch, (pr + 8 * ch));
-                }
                 float a0, a1, a2, a3;
                 unpack_f32x2(acc0, a0, a1);
                 unpack_f32x2(acc1, a2, a3);
@@ -1111,8 +1051,8 @@ void preload_attn_umma_general_kernels();
 void preload_attn_umma_kernels()
 {
     cudaFuncAttributes a;
-    cudaFuncGetAttributes(&a, attn_umma_kernel_v7<false, 0, 2, 2>);
-    cudaFuncGetAttributes(&a, attn_umma_kernel_v8<0, false, false>);
+    cudaFuncGetAttributes(&a, attn_umma_kernel_v7<false>);
+    cudaFuncGetAttributes(&a, attn_umma_kernel_v8);
     cudaGetLastError();
     preload_attn_umma_general_kernels();
 }
@@ -1163,20 +1103,13 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     }
     int dev = 0;
     SDPA_CUDA_TRY(cudaGetDevice(&dev));
-    // developer knobs: SDPA_UMMA_POLY = exponentials of every 16 on the FMA pipe; SDPA_UMMA_SAFE=1 runs the exact variant alone
-    const char* env_poly = getenv("SDPA_UMMA_POLY");
-    int poly = env_poly ? atoi(env_poly) : kDefaultPoly;
-    if (poly != 0 && poly != 4 && poly != 8) poly = kDefaultPoly;
+    // developer knob: SDPA_UMMA_SAFE=1 runs the exact variant alone
     const char* env_safe = getenv("SDPA_UMMA_SAFE");
     const bool force_safe = env_safe && *env_safe == '1';
     if (dev < 64 && !plan->attr_set[dev]) {
         const int sb7 = (int)(sizeof(SharedV7) + 1024);
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 0, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false, 8, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true, 4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
-        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
+        SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
         plan->attr_set[dev] = true;
     }
     if (!plan->guard) {
@@ -1198,8 +1131,6 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.guard = plan->guard;
     prm.epoch = ++plan->epoch;
     if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
-    const char* env_groups = getenv("SDPA_UMMA_GROUPS");   // v7: softmax groups ping-ponged over key tiles (1 or 2)
-    const bool groups2 = env_groups ? (atoi(env_groups) == 2) : true;
     const size_t smem7 = sizeof(SharedV7) + 1024;
     dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v7: 128 rows per CTA, clusters of two along x
     // persistent kernel: only when the engine announced that it merges by pieces, no direct fp64 output, and the caller's
@@ -1216,8 +1147,7 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         SDPA_CUDA_TRY(cudaMalloc(&dtrace, count * sizeof(long long)));
         SDPA_CUDA_TRY(cudaMemsetAsync(dtrace, 0, count * sizeof(long long), stream));
         prm.trace = dtrace;
-        if (groups2) attn_umma_kernel_v7<true, 4, 2, 2><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
-        else attn_umma_kernel_v7<true, 4, 2, 1><<<grid6, 384, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
+        attn_umma_kernel_v7<true><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
         std::vector<long long> host(count);
         SDPA_CUDA_TRY(cudaMemcpyAsync(host.data(), dtrace, count * sizeof(long long), cudaMemcpyDeviceToHost, stream));
@@ -1239,44 +1169,20 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     } else if (use_v8) {
         const int dev8 = dev;
         const size_t smem8 = sizeof(SharedV8) + 1024;
-        // developer knobs: SDPA_UMMA_POLY (0|2|4|6 of 16 exponentials on the FMA pipe), SDPA_V8_OPT bit 0 = V producer warp,
-        // bit 1 = progressive P stores
-        const char* env_opt = getenv("SDPA_V8_OPT");
-        const int opt = env_opt ? (atoi(env_opt) & 3) : kDefaultV8Opt;
-        const int poly8 = env_poly ? atoi(env_poly) : kDefaultV8Poly;
         prm.wm = wm8;
         const dim3 grid8(2 * wm8.C, 1);
-#define SDPA_V8_CASE(P, VW, PS)                                                                                                 \
-    {                                                                                                                          \
-        static bool attr_done[64] = {};                                                                                        \
-        if (dev8 < 64 && !attr_done[dev8]) {                                                                                   \
-            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8<P, VW, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8)); \
-            attr_done[dev8] = true;                                                                                            \
-        }                                                                                                                      \
-        attn_umma_kernel_v8<P, VW, PS><<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm); \
-    }
-#define SDPA_V8_POLY(VW, PS)                                   \
-    if (poly8 == 2) SDPA_V8_CASE(2, VW, PS)                    \
-    else if (poly8 == 4) SDPA_V8_CASE(4, VW, PS)               \
-    else if (poly8 == 6) SDPA_V8_CASE(6, VW, PS)               \
-    else SDPA_V8_CASE(0, VW, PS)
-        if (opt == 3) { SDPA_V8_POLY(true, true) }
-        else if (opt == 2) { SDPA_V8_POLY(false, true) }
-        else if (opt == 1) { SDPA_V8_POLY(true, false) }
-        else { SDPA_V8_POLY(false, false) }
-#undef SDPA_V8_POLY
-#undef SDPA_V8_CASE
+        static bool attr8_done[64] = {};
+        if (dev8 < 64 && !attr8_done[dev8]) {
+            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            attr8_done[dev8] = true;
+        }
+        attn_umma_kernel_v8<<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
         plan->last_v8 = true;
         plan->last_wm = wm8;
         plan->last_pieces = pieces8;
     } else {
-#define SDPA_LAUNCH_V7(P, G) attn_umma_kernel_v7<false, P, 2, G><<<grid6, 128 + 256 * G, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm)
-        if (!groups2) SDPA_LAUNCH_V7(4, 1);
-        else if (poly == 0) SDPA_LAUNCH_V7(0, 2);
-        else if (poly == 8) SDPA_LAUNCH_V7(8, 2);
-        else SDPA_LAUNCH_V7(4, 2);
-#undef SDPA_LAUNCH_V7
+        attn_umma_kernel_v7<false><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
     }
     SDPA_CUDA_TRY(cudaGetLastError());

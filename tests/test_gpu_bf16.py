@@ -97,10 +97,10 @@ def test_bf16_overflow_guard_hands_over_to_safe_kernel(sdpa, oracle):
         np.testing.assert_allclose(got, ref_b, rtol=0, atol=2e-2)
 
 
-@pytest.mark.parametrize("env", [{"SDPA_UMMA_SAFE": "1"}, {"SDPA_UMMA_POLY": "4"}, {"SDPA_UMMA_POLY": "8"}, {"SDPA_UMMA_GROUPS": "1"}])
+@pytest.mark.parametrize("env", [{"SDPA_UMMA_SAFE": "1"}, {"SDPA_UMMA_V8": "0"}, {"SDPA_UMMA_GENERAL": "1"}])
 def test_bf16_kernel_variants(sdpa, oracle, monkeypatch, env):
-    """The developer knobs of the plain-grid kernel (v7) behind the same contract: the exact variant alone
-    (SDPA_UMMA_SAFE), the exp2-polynomial variants, one softmax group."""
+    """The developer knobs behind the same contract: the exact variant alone (SDPA_UMMA_SAFE), the plain-grid kernel where the
+    persistent one would run (SDPA_UMMA_V8=0), the general kernel on the headline shape (SDPA_UMMA_GENERAL)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     Q, K, V, got = _run(sdpa, oracle, 600, 2500, seed=21)
@@ -110,14 +110,12 @@ def test_bf16_kernel_variants(sdpa, oracle, monkeypatch, env):
     np.testing.assert_allclose(got, oracle.attention_f64_numpy(Qb, Kb, Vb), rtol=0, atol=BF16_KERNEL_ATOL)
 
 
-@pytest.mark.parametrize("opt", ["0", "3"])
 @pytest.mark.parametrize("m,n,gain", [(512, 32768, 1.0), (700, 32768 + 77, 1.0), (8192, 16384, 1.0), (300, 40000, 3.0)])
-def test_bf16_persistent_kernel_v8(sdpa, oracle, monkeypatch, m, n, gain, opt):
+def test_bf16_persistent_kernel_v8(sdpa, oracle, monkeypatch, m, n, gain):
     """attn_umma_kernel_v8 (the default when a launch holds enough work): persistent clusters walking (row block, key tile)
     ranges, pieces instead of splits, merge by pieces.  Shapes: a range crossing row blocks, ragged keys + a partial row
     block, many row blocks, and scaled keys (the overflow guard may hand the launch to the exact twin, which fills every
-    partial slot).  opt: SDPA_V8_OPT bit 0 = V producer warp, bit 1 = progressive P stores."""
-    monkeypatch.setenv("SDPA_V8_OPT", opt)
+    partial slot)."""
     Q, K, V = oracle.make_inputs(m, n, 128, 128, seed=m + n)
     K = K * gain
     with sdpa.Context(precision="bf16") as ctx:
