@@ -5,6 +5,10 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 OUT=gpurun_out
 S=$OUT/summary_v9.log; rm -f $S $OUT/xtrace_*
+# ten-second sanity of the fused kernels on one GPU before eight GPUs are kept busy
+CUDA_VISIBLE_DEVICES=0 timeout 300 python -m pytest tests/test_gpu_bf16.py -q -m gpu -p no:cacheprovider -x -k "persistent or variants or overflow" > $OUT/v9_sanity.log 2>&1
+rc=$?; echo "sanity rc=$rc" >> $S
+if [ $rc -ne 0 ]; then cat $S; tail -20 $OUT/v9_sanity.log; exit 1; fi
 run() { # name, gpus, env..., -- args
   local name=$1 g=$2; shift 2
   local envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
