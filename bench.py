@@ -651,6 +651,8 @@ def run_ours(args) -> None:
                                                     "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
                                                     "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],
                 "submission": "K passes queued back to back (sdpa_enqueue_device_full), one wait after the last; e2e uses the blocking host call",
+                "stages": "cast = K/V/Q fp64 -> compute precision; fused = the fused attention kernel alone; merge = its guard twin "
+                          "(exact variant, exits at once unless the overflow guard fired) + split merge (+ cross-GPU exchange)",
                 "stage_timing": "CUDA-event stage marks (cast | fused | merge) on every %d-th queued pass of the timed region: "
                                 "a timestamp event costs ~2 us of stream time, 4 of them per pass were 3.6 %% of the c3 step "
                                 "(profiles/r02/visit6_g1_nomarks.json)" % args.stage_timing_every},

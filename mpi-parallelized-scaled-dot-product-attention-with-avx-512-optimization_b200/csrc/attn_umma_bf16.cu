@@ -894,6 +894,7 @@ struct UmmaPlan {
     bool attr_set[64] = {};
     unsigned int* guard = nullptr;   // device word for the overflow guard (on the plan's device)
     unsigned int epoch = 0;
+    unsigned int twin_epoch = 0;     // epoch the twin of the last fast launch must see in the guard word to run
     bool allow_v8 = false;           // set per call by the engine: the caller merges with launch_merge_pieces
     bool last_v8 = false;            // the last launch used the persistent kernel; last_wm / last_pieces describe its partials
     WorkMap last_wm{0, 0, 0};
@@ -1057,6 +1058,29 @@ void preload_attn_umma_kernels()
     preload_attn_umma_general_kernels();
 }
 
+// The exact variant behind the fast launch that just went out (same epoch): leaves at once unless the guard was raised.
+sdpa_status launch_attn_umma_twin(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part, double* out64, cudaStream_t stream)
+{
+    if (!plan || rows <= 0) return SDPA_OK;
+    if (splits < 1) splits = 1;
+    GeneralLaunch L;
+    L.rows = rows;
+    L.n = plan->n;
+    L.dk = plan->dk;
+    L.dv = plan->dv;
+    L.hl = plan->hl;
+    L.splits = splits;
+    L.exact = true;
+    L.part = part;
+    L.out64 = out64;
+    L.guard = plan->guard;
+    L.epoch = plan->twin_epoch;
+    L.maps = plan->gmaps[q_slot];
+    return launch_attn_umma_general(L, stream);
+}
+
+// The fast fused kernel only; the caller launches launch_attn_umma_twin behind it (separately, so that the stage timing of the
+// fused kernel does not include the twin's launch).
 sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part, double* out64,
                              int sm_count, cudaStream_t stream)
 {
@@ -1090,15 +1114,14 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         if (plan->epoch == 0) L.epoch = ++plan->epoch;   // 0 is the "never raised" value
         L.maps = plan->gmaps[q_slot];
         plan->last_v8 = false;
+        plan->twin_epoch = L.epoch;
         const char* env_safe = getenv("SDPA_UMMA_SAFE");
-        if (env_safe && *env_safe == '1') {   // developer knob: only the exact variant, guard forced
+        if (env_safe && *env_safe == '1') {   // developer knob: only the exact variant (the twin), guard forced
             SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
-            L.epoch = 0xffffffffu;
-        } else {
-            L.exact = false;
-            SDPA_TRY(launch_attn_umma_general(L, stream));
+            plan->twin_epoch = 0xffffffffu;
+            return SDPA_OK;
         }
-        L.exact = true;
+        L.exact = false;
         return launch_attn_umma_general(L, stream);
     }
     int dev = 0;
@@ -1185,23 +1208,9 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         attn_umma_kernel_v7<false><<<grid6, 640, smem7, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);
         count_launch();
     }
+    plan->twin_epoch = prm.epoch;
     SDPA_CUDA_TRY(cudaGetLastError());
-    // the exact variant of the general kernel: leaves immediately unless the guard was raised for this epoch; it writes the
-    // same (split, row) partial slots / the same fp64 rows as the fast kernel it repairs
-    GeneralLaunch L;
-    L.rows = rows;
-    L.n = plan->n;
-    L.dk = HEAD;
-    L.dv = HEAD;
-    L.hl = 1;
-    L.splits = splits;
-    L.exact = true;
-    L.part = part;
-    L.out64 = out64;
-    L.guard = plan->guard;
-    L.epoch = prm.epoch;
-    L.maps = plan->gmaps[q_slot];
-    return launch_attn_umma_general(L, stream);
+    return SDPA_OK;
 }
 
 }  // namespace sdpa

@@ -89,6 +89,8 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
                              size_t q_lo_off);
 sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part,
                              double* out64, int sm_count, cudaStream_t stream);
+// the exact two-phase variant behind the fast launch above (exits at once unless its overflow guard fired)
+sdpa_status launch_attn_umma_twin(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part, double* out64, cudaStream_t stream);
 bool attn_umma_supported(int dk, int dv, int hl);
 int attn_umma_pick_splits(int rows, int n, int sm_count);
 // Persistent fused kernel (EXPERIMENTAL, SDPA_UMMA_V8=1): partial slots per row block for (rows, n), 0 = not applicable.

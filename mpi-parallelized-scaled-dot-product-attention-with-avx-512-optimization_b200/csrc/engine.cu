@@ -913,9 +913,15 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             SDPA_TRY(time_end(s, 1, s.s_compute));
             ++fused_launches;
             ++all_launches;
+            // the guard twin of a tensor-core launch belongs to the merge stage ("guard twin + split merge"): the fused stage is
+            // the duration of the fused kernel alone
+            const bool twin = is_umma(ctx->prec);
+            if (twin && single && splits == 1)
+                SDPA_TRY(launch_attn_umma_twin(s.plan, b, bs, splits, part, final_dst, s.s_compute));
 
             if (!(single && splits == 1)) {
                 SDPA_TRY(time_begin(s, 2, s.s_compute));
+                if (twin) SDPA_TRY(launch_attn_umma_twin(s.plan, b, bs, splits, part, nullptr, s.s_compute));
                 WorkMap wm;
                 int max_pieces = 0;
                 const unsigned int* guard = nullptr;
@@ -1305,6 +1311,7 @@ static sdpa_status attention_qshard_host(sdpa_ctx* ctx, const double* Q, double*
             SDPA_TRY(time_begin(s, 1, s.s_compute));
             SDPA_TRY(run_fused(ctx, s, b, bs, splits, part, splits == 1 ? dst : nullptr));
             SDPA_TRY(time_end(s, 1, s.s_compute));
+            if (is_umma(ctx->prec)) SDPA_TRY(launch_attn_umma_twin(s.plan, b, bs, splits, part, splits == 1 ? dst : nullptr, s.s_compute));
             ++fused_launches;
             if (splits > 1) {
                 SDPA_TRY(time_begin(s, 2, s.s_compute));
