@@ -122,7 +122,7 @@ __device__ __forceinline__ void sync_exit(const SyncArgs& sync)
 }
 
 template <bool FINAL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 merge_states_kernel(StatePtrs st, int count, int rows, int dv, double* __restrict__ out64,
                     float* __restrict__ contrib, float* __restrict__ tmax_out,
                     float* __restrict__ lsum_out, float max_unit, bool vec_ok, const SyncArgs sync)
@@ -151,34 +151,73 @@ __device__ __forceinline__ void merge_one_row(const StatePtrs& st, int count, in
 {
     const int lane = threadIdx.x & 31;
 
+    // Up to 8 states (the pieces of a row block, the shards of a box) and 16-byte vectors: the o vectors of this lane's first
+    // four columns are requested BEFORE the statistics are reduced, so the row costs one memory round trip (local L2 or NVLink)
+    // instead of two dependent ones (statistics -> shuffles -> vectors).
+    const bool vec = (dv & 3) == 0 && vec_ok;
+    const bool pre = vec && count <= 8 && lane * 4 < dv;
+    float4 pv[8];
+    if (pre) {
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (s < count) pv[s] = *reinterpret_cast<const float4*>(st.o[s] + (size_t)row * dv + lane * 4);
+    }
+
     // lanes hold the per-state statistics (count <= 64: two per lane)
     float t0 = lane < count ? st.tmax[lane][row] : -CUDART_INF_F;
     float t1 = lane + 32 < count ? st.tmax[lane + 32][row] : -CUDART_INF_F;
+    const float l0 = lane < count ? st.lsum[lane][row] : 0.f;
+    const float l1 = lane + 32 < count ? st.lsum[lane + 32][row] : 0.f;
     float gmax = fmaxf(t0, t1);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
     // all states empty (-inf): weights 0, output 0
     const float w0 = (t0 == -CUDART_INF_F) ? 0.f : exp2f(t0 - gmax);
     const float w1 = (t1 == -CUDART_INF_F) ? 0.f : exp2f(t1 - gmax);
-    float gsum = (lane < count ? st.lsum[lane][row] * w0 : 0.f) +
-                 (lane + 32 < count ? st.lsum[lane + 32][row] * w1 : 0.f);
+    float gsum = l0 * w0 + l1 * w1;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
     const float inv = (gsum == 0.f) ? 0.f : 1.f / gsum;
 
     // weights of the states, one per lane (two if count > 32), broadcast with shuffles below
-    if ((dv & 3) == 0 && vec_ok) {
+    float wv[8];
+    if (count <= 8) {   // warp-uniform: every lane takes part in these shuffles
+#pragma unroll
+        for (int s = 0; s < 8; ++s) wv[s] = __shfl_sync(0xffffffffu, w0, s);
+    }
+    if (vec) {
         // 16-byte vectors: lane owns 4 consecutive output columns per step
         for (int d = lane * 4; d < dv; d += 128) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pre && d == lane * 4) {
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    if (s < count) {
+                        acc.x = fmaf(pv[s].x, wv[s], acc.x);
+                        acc.y = fmaf(pv[s].y, wv[s], acc.y);
+                        acc.z = fmaf(pv[s].z, wv[s], acc.z);
+                        acc.w = fmaf(pv[s].w, wv[s], acc.w);
+                    }
+                }
+            } else if (count <= 8) {
+                for (int s = 0; s < count; ++s) {
+                    const float4 v = *reinterpret_cast<const float4*>(st.o[s] + (size_t)row * dv + d);
+                    const float w = wv[s & 7];
+                    acc.x = fmaf(v.x, w, acc.x);
+                    acc.y = fmaf(v.y, w, acc.y);
+                    acc.z = fmaf(v.z, w, acc.z);
+                    acc.w = fmaf(v.w, w, acc.w);
+                }
+            } else {
 #pragma unroll 4
-            for (int s = 0; s < count; ++s) {
-                const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
-                const float4 v = *reinterpret_cast<const float4*>(st.o[s] + (size_t)row * dv + d);
-                acc.x = fmaf(v.x, w, acc.x);
-                acc.y = fmaf(v.y, w, acc.y);
-                acc.z = fmaf(v.z, w, acc.z);
-                acc.w = fmaf(v.w, w, acc.w);
+                for (int s = 0; s < count; ++s) {
+                    const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
+                    const float4 v = *reinterpret_cast<const float4*>(st.o[s] + (size_t)row * dv + d);
+                    acc.x = fmaf(v.x, w, acc.x);
+                    acc.y = fmaf(v.y, w, acc.y);
+                    acc.z = fmaf(v.z, w, acc.z);
+                    acc.w = fmaf(v.w, w, acc.w);
+                }
             }
             if (FINAL) {
                 double2* dst = reinterpret_cast<double2*>(out64_row + d);
@@ -298,7 +337,7 @@ merge_route_kernel(StatePtrs st, int count, int rows, int dv, RouteArgs rt, bool
 // number of pieces its row block was cut into (wm_pieces), unless the overflow guard handed the launch to the SAFE
 // kernel, which fills all `max_pieces` slots with equal splits.
 template <bool FINAL>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 merge_pieces_kernel(StatePtrs st, WorkMap wm, int max_pieces, int rows, int dv, double* __restrict__ out64, float* __restrict__ contrib,
                     float* __restrict__ tmax_out, float* __restrict__ lsum_out, bool vec_ok, const unsigned int* __restrict__ guard,
                     unsigned int epoch, const SyncArgs sync)
