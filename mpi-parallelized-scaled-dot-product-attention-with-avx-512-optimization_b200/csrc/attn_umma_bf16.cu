@@ -892,8 +892,12 @@ struct UmmaPlan {
     const void* v_base = nullptr;
     int q_rows[2] = {0, 0};
     bool attr_set[64] = {};
-    unsigned int* guard = nullptr;   // device word for the overflow guard (on the plan's device)
+    // Overflow guard: a ring of kGuardRing device words; the launch with epoch e uses word e % kGuardRing and a fast kernel writes
+    // e into it when an exponent would overflow.  A word equals a launch's epoch only if THAT launch raised it, so the words are
+    // never cleared and the host can inspect a whole queue of launches after the fact (deferred repair, engine.cu).
+    unsigned int* guard = nullptr;
     unsigned int epoch = 0;
+    bool force_exact = false;        // run the exact variant alone (the host-side repair of a launch whose guard fired)
     unsigned int twin_epoch = 0;     // epoch the twin of the last fast launch must see in the guard word to run
     bool allow_v8 = false;           // set per call by the engine: the caller merges with launch_merge_pieces
     bool last_v8 = false;            // the last launch used the persistent kernel; last_wm / last_pieces describe its partials
@@ -901,6 +905,21 @@ struct UmmaPlan {
     int last_pieces = 0;
     bool attr8_set[64] = {};
 };
+
+__global__ void set_word_kernel(unsigned int* p, unsigned int v) { *p = v; }
+
+static sdpa_status plan_guard_ring(UmmaPlan* plan)
+{
+    if (plan->guard) return SDPA_OK;
+    SDPA_CUDA_TRY(cudaMalloc(&plan->guard, kGuardRing * sizeof(unsigned int)));
+    SDPA_CUDA_TRY(cudaMemset(plan->guard, 0, kGuardRing * sizeof(unsigned int)));
+    return SDPA_OK;
+}
+static unsigned int plan_next_epoch(UmmaPlan* plan)
+{
+    if (++plan->epoch == 0) ++plan->epoch;   // 0 is the "never raised" value of a fresh ring
+    return plan->epoch;
+}
 
 sdpa_status umma_plan_create(UmmaPlan** plan)
 {
@@ -1017,9 +1036,21 @@ bool umma_plan_last_v8(const UmmaPlan* plan, WorkMap* wm, int* max_pieces, const
     if (!plan || !plan->last_v8) return false;
     *wm = plan->last_wm;
     *max_pieces = plan->last_pieces;
-    *guard = plan->guard;
-    *epoch = plan->epoch;
+    *guard = plan->guard + (plan->twin_epoch % kGuardRing);
+    *epoch = plan->twin_epoch;
     return true;
+}
+
+// The guard word and epoch of the fast launch that just went out (for the engine's deferred repair), and the ring itself.
+void umma_plan_last_guard(const UmmaPlan* plan, unsigned int* slot, unsigned int* epoch)
+{
+    *slot = plan->twin_epoch % kGuardRing;
+    *epoch = plan->twin_epoch;
+}
+const unsigned int* umma_plan_guard_ring(const UmmaPlan* plan) { return plan ? plan->guard : nullptr; }
+void umma_plan_force_exact(UmmaPlan* plan, bool on)
+{
+    if (plan) plan->force_exact = on;
 }
 
 int attn_umma_pick_splits(int rows, int n, int sm_count)
@@ -1073,7 +1104,7 @@ sdpa_status launch_attn_umma_twin(UmmaPlan* plan, int q_slot, int rows, int spli
     L.exact = true;
     L.part = part;
     L.out64 = out64;
-    L.guard = plan->guard;
+    L.guard = plan->guard + (plan->twin_epoch % kGuardRing);
     L.epoch = plan->twin_epoch;
     L.maps = plan->gmaps[q_slot];
     return launch_attn_umma_general(L, stream);
@@ -1096,10 +1127,7 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     }
     if (plan->general) {
         // every shape but dk = dv = 128 bf16: the general kernel, then its exact twin (leaves at once unless the guard fired)
-        if (!plan->guard) {
-            SDPA_CUDA_TRY(cudaMalloc(&plan->guard, sizeof(unsigned int)));
-            SDPA_CUDA_TRY(cudaMemset(plan->guard, 0, sizeof(unsigned int)));
-        }
+        SDPA_TRY(plan_guard_ring(plan));
         GeneralLaunch L;
         L.rows = rows;
         L.n = plan->n;
@@ -1109,16 +1137,16 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         L.splits = splits;
         L.part = part;
         L.out64 = out64;
-        L.guard = plan->guard;
-        L.epoch = ++plan->epoch;
-        if (plan->epoch == 0) L.epoch = ++plan->epoch;   // 0 is the "never raised" value
+        L.epoch = plan_next_epoch(plan);
+        L.guard = plan->guard + (L.epoch % kGuardRing);
         L.maps = plan->gmaps[q_slot];
         plan->last_v8 = false;
         plan->twin_epoch = L.epoch;
         const char* env_safe = getenv("SDPA_UMMA_SAFE");
-        if (env_safe && *env_safe == '1') {   // developer knob: only the exact variant (the twin), guard forced
-            SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
-            plan->twin_epoch = 0xffffffffu;
+        if (plan->force_exact || (env_safe && *env_safe == '1')) {
+            // only the exact variant (the twin, launched by the caller): this launch's guard word is made to carry its epoch
+            set_word_kernel<<<1, 1, 0, stream>>>(L.guard, L.epoch);
+            count_launch();
             return SDPA_OK;
         }
         L.exact = false;
@@ -1128,17 +1156,14 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     SDPA_CUDA_TRY(cudaGetDevice(&dev));
     // developer knob: SDPA_UMMA_SAFE=1 runs the exact variant alone
     const char* env_safe = getenv("SDPA_UMMA_SAFE");
-    const bool force_safe = env_safe && *env_safe == '1';
+    const bool force_safe = plan->force_exact || (env_safe && *env_safe == '1');
     if (dev < 64 && !plan->attr_set[dev]) {
         const int sb7 = (int)(sizeof(SharedV7) + 1024);
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
         SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sb7));
         plan->attr_set[dev] = true;
     }
-    if (!plan->guard) {
-        SDPA_CUDA_TRY(cudaMalloc(&plan->guard, sizeof(unsigned int)));
-        SDPA_CUDA_TRY(cudaMemset(plan->guard, 0, sizeof(unsigned int)));
-    }
+    SDPA_TRY(plan_guard_ring(plan));
     KernelParams prm;
     prm.rows = rows;
     prm.n = plan->n;
@@ -1151,9 +1176,8 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
     prm.rows_capacity = part.rows_capacity;
     prm.out64 = out64;
     prm.trace = nullptr;
-    prm.guard = plan->guard;
-    prm.epoch = ++plan->epoch;
-    if (plan->epoch == 0) prm.epoch = ++plan->epoch;   // 0 is the "never raised" value
+    prm.epoch = plan_next_epoch(plan);
+    prm.guard = plan->guard + (prm.epoch % kGuardRing);
     const size_t smem7 = sizeof(SharedV7) + 1024;
     dim3 grid6(2 * ceil_div(ceil_div(rows, TILE), 2), splits);          // v7: 128 rows per CTA, clusters of two along x
     // persistent kernel: only when the engine announced that it merges by pieces, no direct fp64 output, and the caller's
@@ -1187,8 +1211,9 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         }
         prm.trace = nullptr;
     } else if (force_safe) {
-        SDPA_CUDA_TRY(cudaMemsetAsync(plan->guard, 0xff, sizeof(unsigned int), stream));
-        prm.epoch = 0xffffffffu;
+        // only the exact variant (launched by the caller): make this launch's guard word carry its epoch
+        set_word_kernel<<<1, 1, 0, stream>>>(prm.guard, prm.epoch);
+        count_launch();
     } else if (use_v8) {
         const int dev8 = dev;
         const size_t smem8 = sizeof(SharedV8) + 1024;

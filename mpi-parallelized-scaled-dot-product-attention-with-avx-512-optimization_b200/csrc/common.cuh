@@ -89,6 +89,11 @@ sdpa_status umma_plan_bind_q(UmmaPlan* plan, int slot, const __nv_bfloat16* Q, i
                              size_t q_lo_off);
 sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part,
                              double* out64, int sm_count, cudaStream_t stream);
+// Overflow-guard ring of a plan: launch epoch e owns word e % kGuardRing; the word equals e iff that launch raised its guard.
+constexpr unsigned int kGuardRing = 4096;
+void umma_plan_last_guard(const UmmaPlan* plan, unsigned int* slot, unsigned int* epoch);
+const unsigned int* umma_plan_guard_ring(const UmmaPlan* plan);
+void umma_plan_force_exact(UmmaPlan* plan, bool on);   // the next launches run the exact variant alone (host-side repair)
 // the exact two-phase variant behind the fast launch above (exits at once unless its overflow guard fired)
 sdpa_status launch_attn_umma_twin(UmmaPlan* plan, int q_slot, int rows, int splits, Partials part, double* out64, cudaStream_t stream);
 bool attn_umma_supported(int dk, int dv, int hl);

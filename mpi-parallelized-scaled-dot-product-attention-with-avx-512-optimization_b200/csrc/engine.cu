@@ -221,6 +221,18 @@ struct sdpa_ctx {
     float last_timing[6] = {0, 0, 0, 0, 0, 0};
     bool last_timing_valid = true;          // false: last_timing[0..3] still have to be computed from the event pairs
     double acc_fused_launches = 0, acc_calls = 0;   // over the calls that recorded stage marks
+    // Deferred guard repair (single-GPU contexts, queued passes): the exact twin is not launched behind every fast kernel;
+    // sdpa_synchronize reads the guard ring once, and a pass whose guard fired is re-run with the exact variant -- its arrays
+    // are still valid then (contract of sdpa_enqueue_device_full).  SDPA_DEFER_TWIN=0 keeps the twin in the stream.
+    struct PendingPass {
+        const double* K; const double* V; int n_local, dk, dv;
+        const double* Q; double* result; int m;
+        std::vector<std::pair<unsigned int, unsigned int>> guards;   // (ring slot, epoch) of every fused launch of the pass
+    };
+    std::vector<PendingPass> pending;
+    std::vector<std::pair<unsigned int, unsigned int>> call_guards;   // collected by the attention call in flight
+    bool defer_twin = true, deferring = false, repairing = false;
+    unsigned int ring_use = 0;              // fused launches since the pending passes were last resolved (the guard ring has kGuardRing words)
     int mark_every = 1;                     // queued passes: stage marks on every mark_every-th pass (SDPA_STAGE_TIMING_EVERY); blocking: always
     unsigned long long queued_seq = 0;
     const char* last_kernel = "none";
@@ -257,6 +269,8 @@ struct sdpa_ctx {
     } ipc;
     bool has_root() const { return rank_base == 0; }
 };
+
+extern "C" { static sdpa_status resolve_pending(sdpa_ctx* ctx); }   // deferred guard repair (defined with the C ABI below)
 
 namespace sdpa {
 
@@ -806,6 +820,12 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         for (Shard& s : ctx->shards)
             if (s.plan) umma_plan_allow_v8(s.plan, by_pieces);
 
+    // guard twin: in the stream behind every fast tensor-core launch, except for queued passes of a single-GPU context
+    if (!ctx->repairing && !ctx->pending.empty() && ctx->ring_use + (unsigned int)num_iter + 8 >= kGuardRing)
+        SDPA_TRY(resolve_pending(ctx));   // the guard words of the pending passes must not be reused before they are read
+    ctx->ring_use += (unsigned int)num_iter;
+    ctx->deferring = ctx->defer_twin && !blocking && !ctx->repairing && world == 1 && L == 1 && is_umma(ctx->prec) && on_device && result_on_device;
+    ctx->call_guards.clear();
     // stage marks: every blocking call; queued passes on every mark_every-th pass (each timestamp event costs ~2 us of stream time)
     const bool marked = blocking || ctx->mark_every <= 1 || (ctx->queued_seq++ % (unsigned long long)ctx->mark_every) == 0;
     // which side streams this call touches (the others are neither forked nor joined: every stream operation
@@ -915,7 +935,12 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             ++all_launches;
             // the guard twin of a tensor-core launch belongs to the merge stage ("guard twin + split merge"): the fused stage is
             // the duration of the fused kernel alone
-            const bool twin = is_umma(ctx->prec);
+            const bool twin = is_umma(ctx->prec) && !ctx->deferring;
+            if (ctx->deferring) {
+                unsigned int slot = 0, ep = 0;
+                umma_plan_last_guard(s.plan, &slot, &ep);
+                ctx->call_guards.emplace_back(slot, ep);
+            }
             if (twin && single && splits == 1)
                 SDPA_TRY(launch_attn_umma_twin(s.plan, b, bs, splits, part, final_dst, s.s_compute));
 
@@ -1561,6 +1586,7 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
     ctx->rank_base = cfg.rank_base;
     {
         if (const char* me = getenv("SDPA_STAGE_TIMING_EVERY")) ctx->mark_every = std::max(1, atoi(me));
+        if (const char* dt = getenv("SDPA_DEFER_TWIN")) ctx->defer_twin = !(*dt == '0');
         const char* ov = getenv("SDPA_OVERLAP_PASSES");   // SDPA_OVERLAP_PASSES=0: every queued pass joins its exchange before the next starts
         ctx->overlap_passes = !(ov && *ov == '0');
     }
@@ -1762,7 +1788,46 @@ sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shard
         return SDPA_ERR_INVALID;
     }
     SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true));
-    return attention_impl(ctx, nullptr, Q_dev, result_dev, true, m, false, false);
+    SDPA_TRY(attention_impl(ctx, nullptr, Q_dev, result_dev, true, m, false, false));
+    if (ctx->deferring && !ctx->call_guards.empty())
+        ctx->pending.push_back({K_shards[0], V_shards[0], n_local[0], dk, dv, Q_dev[0], result_dev, m, ctx->call_guards});
+    return SDPA_OK;
+}
+
+/* Deferred guard repair: wait for the queued passes, read the guard ring once, re-run (exact variant alone, blocking) every
+ * pass one of whose launches raised its guard. */
+static sdpa_status resolve_pending(sdpa_ctx* ctx)
+{
+    if (ctx->pending.empty()) return SDPA_OK;
+    Shard& s = ctx->shards[0];
+    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+    std::vector<unsigned int> ring(kGuardRing, 0u);
+    const unsigned int* dev_ring = umma_plan_guard_ring(s.plan);
+    if (dev_ring) SDPA_CUDA_TRY(cudaMemcpy(ring.data(), dev_ring, kGuardRing * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    std::vector<sdpa_ctx::PendingPass> todo;
+    for (sdpa_ctx::PendingPass& p : ctx->pending) {
+        bool fired = false;
+        for (auto& g : p.guards) fired = fired || ring[g.first] == g.second;
+        if (fired) todo.push_back(p);
+    }
+    ctx->pending.clear();
+    ctx->ring_use = 0;
+    if (todo.empty()) return SDPA_OK;
+    ctx->repairing = true;
+    umma_plan_force_exact(s.plan, true);
+    sdpa_status st = SDPA_OK;
+    for (sdpa_ctx::PendingPass& p : todo) {
+        const double* kp[1] = {p.K};
+        const double* vp[1] = {p.V};
+        const double* qp[1] = {p.Q};
+        const int cnt[1] = {p.n_local};
+        st = sdpa_attention_device_full(ctx, kp, vp, cnt, p.dk, p.dv, qp, p.result, p.m);
+        if (st != SDPA_OK) break;
+    }
+    umma_plan_force_exact(s.plan, false);
+    ctx->repairing = false;
+    return st;
 }
 
 sdpa_status sdpa_synchronize(sdpa_ctx* ctx)
@@ -1776,7 +1841,7 @@ sdpa_status sdpa_synchronize(sdpa_ctx* ctx)
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
     }
-    return SDPA_OK;
+    return resolve_pending(ctx);
 }
 
 sdpa_status sdpa_online_softmax_partials(sdpa_ctx* ctx, int local, const float* Qf_dev, int m, float* contrib_dev,

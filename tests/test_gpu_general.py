@@ -180,3 +180,52 @@ def test_x3_ping_pong_batches_device_and_host_agree(sdpa, oracle):
             ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [3000], 128, 128, [Qd.data_ptr()], out.data_ptr(), 1000, blocking=False)
         ctx.synchronize()
         np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=X3_ATOL)
+
+
+@pytest.mark.parametrize("prec,d", [("bf16", 128), ("bf16x3", 128), ("bf16", 64)])
+def test_queued_passes_repair_a_fired_guard_at_synchronize(sdpa, oracle, prec, d):
+    """Queued passes of a single-GPU context do not carry the exact twin in the stream: sdpa_synchronize reads the guard ring
+    and re-runs (exact variant) the passes whose guard fired.  Three queued passes, the middle one with overflowing data."""
+    import torch
+    m = 300
+    good = oracle.make_inputs(m, 1500, d, d, seed=3)
+    bad = oracle.make_inputs(m, 1500, d, d, seed=11)
+    bad = (bad[0] * 3.0, np.concatenate([bad[1][:128] * 0.01, bad[1][128:] * 30.0]), bad[2])
+    if prec == "bf16":
+        good = tuple(oracle.bf16_round(a).astype(np.float64) for a in good)
+        bad = tuple(oracle.bf16_round(a).astype(np.float64) for a in bad)
+    cases = [good, bad, good]
+    with sdpa.Context(precision=prec) as ctx:
+        dev = [[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (K, V, Q)] for (Q, K, V) in cases]
+        outs = [torch.zeros(m, d, dtype=torch.float64, device="cuda") for _ in cases]
+        for rep in range(2):
+            for (Kd, Vd, Qd), out in zip(dev, outs):
+                ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], d, d, [Qd.data_ptr()], out.data_ptr(), m, blocking=False)
+        ctx.synchronize()
+        tols = (2e-3, 2e-2, 2e-3) if prec == "bf16" else (1e-5, 2e-2, 1e-5)   # the overflowing case has scores of magnitude ~1000
+        for (Q, K, V), out, tol in zip(cases, outs, tols):
+            got = out.cpu().numpy()
+            assert np.isfinite(got).all()
+            np.testing.assert_allclose(got, oracle.attention_f64_numpy(Q, K, V), rtol=0, atol=tol)
+
+
+def test_queued_passes_longer_than_the_guard_ring(sdpa, oracle):
+    """More queued launches than the guard ring has words (4096): the pending passes are resolved before their words are reused;
+    a pass with overflowing data early in the queue is still repaired."""
+    import torch
+    d, m = 64, 64
+    good = oracle.make_inputs(m, 256, d, d, seed=5)
+    bad = oracle.make_inputs(m, 256, d, d, seed=6)
+    bad = (bad[0] * 3.0, np.concatenate([bad[1][:128] * 0.01, bad[1][128:] * 30.0]), bad[2])
+    good, bad = (tuple(oracle.bf16_round(a).astype(np.float64) for a in t) for t in (good, bad))
+    with sdpa.Context(precision="bf16") as ctx:
+        g = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (good[1], good[2], good[0])]
+        b = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (bad[1], bad[2], bad[0])]
+        out_b = torch.zeros(m, d, dtype=torch.float64, device="cuda")
+        out_g = torch.zeros(m, d, dtype=torch.float64, device="cuda")
+        ctx.attention_device_full([b[0].data_ptr()], [b[1].data_ptr()], [256], d, d, [b[2].data_ptr()], out_b.data_ptr(), m, blocking=False)
+        for _ in range(4500):
+            ctx.attention_device_full([g[0].data_ptr()], [g[1].data_ptr()], [256], d, d, [g[2].data_ptr()], out_g.data_ptr(), m, blocking=False)
+        ctx.synchronize()
+        np.testing.assert_allclose(out_b.cpu().numpy(), oracle.attention_f64_numpy(*bad), rtol=0, atol=2e-2)
+        np.testing.assert_allclose(out_g.cpu().numpy(), oracle.attention_f64_numpy(*good), rtol=0, atol=2e-3)

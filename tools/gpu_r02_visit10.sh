@@ -9,7 +9,7 @@ timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > $OUT/v10_pyte
 echo "pytest rc=$?" >> $S
 timeout 300 python bench.py --steps 20 --warmup 5 > $OUT/v10_bench_c3.json 2> $OUT/v10_bench.err
 echo "bench rc=$?" >> $S
-timeout 300 python bench.py --steps 20 --warmup 5 --stage-timing-every 1 --no-cpu-baseline --extra none > $OUT/v10_bench_c3_allmarks.json 2>> $OUT/v10_bench.err
+SDPA_DEFER_TWIN=0 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --extra none > $OUT/v10_bench_c3_allmarks.json 2>> $OUT/v10_bench.err
 echo "bench allmarks rc=$?" >> $S
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/v10_smoke.log 2>&1
 echo "smoke rc=$?" >> $S
