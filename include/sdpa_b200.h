@@ -175,6 +175,9 @@ sdpa_status sdpa_attention_device_full(sdpa_ctx* ctx, const double* const* K_sha
 sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
                                      const int* n_local, int dk, int dv, const double* const* Q_dev,
                                      double* result_dev, int m);
+/* Waits for every queued pass.  It is also where a queued pass whose overflow guard fired is repaired (re-run with the exact
+ * kernel variant; blocking calls carry that variant in the stream instead), so results are final on return -- which is why the
+ * arrays of queued passes must stay valid until then.  On a context that spans several processes the call is collective. */
 sdpa_status sdpa_synchronize(sdpa_ctx* ctx);
 
 /* The reference's calling convention on a one-GPU-per-process context (world_size > 1):

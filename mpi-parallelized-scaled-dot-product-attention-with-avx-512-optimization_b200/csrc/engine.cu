@@ -221,16 +221,20 @@ struct sdpa_ctx {
     float last_timing[6] = {0, 0, 0, 0, 0, 0};
     bool last_timing_valid = true;          // false: last_timing[0..3] still have to be computed from the event pairs
     double acc_fused_launches = 0, acc_calls = 0;   // over the calls that recorded stage marks
-    // Deferred guard repair (single-GPU contexts, queued passes): the exact twin is not launched behind every fast kernel;
-    // sdpa_synchronize reads the guard ring once, and a pass whose guard fired is re-run with the exact variant -- its arrays
-    // are still valid then (contract of sdpa_enqueue_device_full).  SDPA_DEFER_TWIN=0 keeps the twin in the stream.
+    // Deferred guard repair (queued passes): the exact twin is not launched behind every fast kernel; sdpa_synchronize reads the
+    // guard rings once, the processes agree (MAX all-reduce) on the passes in which ANY shard raised its guard, and those
+    // passes are re-run with the exact variant -- their arrays are still valid then (contract of sdpa_enqueue_device_full; with
+    // several processes sdpa_synchronize is collective like the passes themselves).  SDPA_DEFER_TWIN=0 keeps the twin in the stream.
+    struct GuardRef { int shard; unsigned int slot, epoch; };
     struct PendingPass {
-        const double* K; const double* V; int n_local, dk, dv;
-        const double* Q; double* result; int m;
-        std::vector<std::pair<unsigned int, unsigned int>> guards;   // (ring slot, epoch) of every fused launch of the pass
+        std::vector<const double*> K, V, Q;   // per local shard
+        std::vector<int> n_local;
+        int dk, dv;
+        double* result; int m;
+        std::vector<GuardRef> guards;         // every fused launch of the pass
     };
     std::vector<PendingPass> pending;
-    std::vector<std::pair<unsigned int, unsigned int>> call_guards;   // collected by the attention call in flight
+    std::vector<GuardRef> call_guards;        // collected by the attention call in flight
     bool defer_twin = true, deferring = false, repairing = false;
     unsigned int ring_use = 0;              // fused launches since the pending passes were last resolved (the guard ring has kGuardRing words)
     int mark_every = 1;                     // queued passes: stage marks on every mark_every-th pass (SDPA_STAGE_TIMING_EVERY); blocking: always
@@ -824,7 +828,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     if (!ctx->repairing && !ctx->pending.empty() && ctx->ring_use + (unsigned int)num_iter + 8 >= kGuardRing)
         SDPA_TRY(resolve_pending(ctx));   // the guard words of the pending passes must not be reused before they are read
     ctx->ring_use += (unsigned int)num_iter;
-    ctx->deferring = ctx->defer_twin && !blocking && !ctx->repairing && world == 1 && L == 1 && is_umma(ctx->prec) && on_device && result_on_device;
+    ctx->deferring = ctx->defer_twin && !blocking && !ctx->repairing && is_umma(ctx->prec) && on_device && (result_on_device || !ctx->has_root());
     ctx->call_guards.clear();
     // stage marks: every blocking call; queued passes on every mark_every-th pass (each timestamp event costs ~2 us of stream time)
     const bool marked = blocking || ctx->mark_every <= 1 || (ctx->queued_seq++ % (unsigned long long)ctx->mark_every) == 0;
@@ -939,7 +943,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             if (ctx->deferring) {
                 unsigned int slot = 0, ep = 0;
                 umma_plan_last_guard(s.plan, &slot, &ep);
-                ctx->call_guards.emplace_back(slot, ep);
+                ctx->call_guards.push_back({i, slot, ep});
             }
             if (twin && single && splits == 1)
                 SDPA_TRY(launch_attn_umma_twin(s.plan, b, bs, splits, part, final_dst, s.s_compute));
@@ -1789,43 +1793,70 @@ sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shard
     }
     SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true));
     SDPA_TRY(attention_impl(ctx, nullptr, Q_dev, result_dev, true, m, false, false));
-    if (ctx->deferring && !ctx->call_guards.empty())
-        ctx->pending.push_back({K_shards[0], V_shards[0], n_local[0], dk, dv, Q_dev[0], result_dev, m, ctx->call_guards});
+    if (ctx->deferring && !ctx->call_guards.empty()) {
+        const size_t L = ctx->shards.size();
+        sdpa_ctx::PendingPass p;
+        p.K.assign(K_shards, K_shards + L);
+        p.V.assign(V_shards, V_shards + L);
+        p.Q.assign(Q_dev, Q_dev + L);
+        p.n_local.assign(n_local, n_local + L);
+        p.dk = dk;
+        p.dv = dv;
+        p.result = result_dev;
+        p.m = m;
+        p.guards = ctx->call_guards;
+        ctx->pending.push_back(std::move(p));
+    }
     return SDPA_OK;
 }
 
-/* Deferred guard repair: wait for the queued passes, read the guard ring once, re-run (exact variant alone, blocking) every
- * pass one of whose launches raised its guard. */
+/* Deferred guard repair: wait for the queued passes, read the guard rings once, agree across processes, re-run (exact variant
+ * alone, blocking) every pass one of whose launches raised its guard on any shard. */
 static sdpa_status resolve_pending(sdpa_ctx* ctx)
 {
     if (ctx->pending.empty()) return SDPA_OK;
-    Shard& s = ctx->shards[0];
-    SDPA_CUDA_TRY(cudaSetDevice(s.dev));
-    SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
-    std::vector<unsigned int> ring(kGuardRing, 0u);
-    const unsigned int* dev_ring = umma_plan_guard_ring(s.plan);
-    if (dev_ring) SDPA_CUDA_TRY(cudaMemcpy(ring.data(), dev_ring, kGuardRing * sizeof(unsigned int), cudaMemcpyDeviceToHost));
-    std::vector<sdpa_ctx::PendingPass> todo;
-    for (sdpa_ctx::PendingPass& p : ctx->pending) {
-        bool fired = false;
-        for (auto& g : p.guards) fired = fired || ring[g.first] == g.second;
-        if (fired) todo.push_back(p);
+    const int L = (int)ctx->shards.size();
+    SDPA_TRY(drain_exchange(ctx));
+    std::vector<std::vector<unsigned int>> ring(L, std::vector<unsigned int>(kGuardRing, 0u));
+    for (int i = 0; i < L; ++i) {
+        Shard& s = ctx->shards[i];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
+        const unsigned int* dev_ring = umma_plan_guard_ring(s.plan);
+        if (dev_ring) SDPA_CUDA_TRY(cudaMemcpy(ring[i].data(), dev_ring, kGuardRing * sizeof(unsigned int), cudaMemcpyDeviceToHost));
     }
+    std::vector<int> fired(ctx->pending.size(), 0);
+    for (size_t p = 0; p < ctx->pending.size(); ++p)
+        for (const sdpa_ctx::GuardRef& g : ctx->pending[p].guards)
+            if (ring[g.shard][g.slot] == g.epoch) fired[p] = 1;
+    if (ctx->world > L) {
+        // one process per GPU: every process queued the same passes; a pass is repaired by all of them if any shard fired
+        const NcclApi* api = nccl_api();
+        if (!api) return SDPA_ERR_NCCL;
+        Shard& s = ctx->shards[0];
+        SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+        DevBuf buf;
+        SDPA_TRY(buf.reserve(fired.size() * sizeof(int), true));
+        SDPA_CUDA_TRY(cudaMemcpyAsync(buf.p, fired.data(), fired.size() * sizeof(int), cudaMemcpyHostToDevice, s.s_comm));
+        SDPA_NCCL_TRY(api->AllReduce(buf.p, buf.p, fired.size(), ncclInt32, ncclMax, s.comm, s.s_comm));
+        SDPA_CUDA_TRY(cudaMemcpyAsync(fired.data(), buf.p, fired.size() * sizeof(int), cudaMemcpyDeviceToHost, s.s_comm));
+        SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_comm));
+        buf.release();
+    }
+    std::vector<sdpa_ctx::PendingPass> todo;
+    for (size_t p = 0; p < ctx->pending.size(); ++p)
+        if (fired[p]) todo.push_back(ctx->pending[p]);
     ctx->pending.clear();
     ctx->ring_use = 0;
     if (todo.empty()) return SDPA_OK;
     ctx->repairing = true;
-    umma_plan_force_exact(s.plan, true);
+    for (Shard& s : ctx->shards) umma_plan_force_exact(s.plan, true);
     sdpa_status st = SDPA_OK;
     for (sdpa_ctx::PendingPass& p : todo) {
-        const double* kp[1] = {p.K};
-        const double* vp[1] = {p.V};
-        const double* qp[1] = {p.Q};
-        const int cnt[1] = {p.n_local};
-        st = sdpa_attention_device_full(ctx, kp, vp, cnt, p.dk, p.dv, qp, p.result, p.m);
+        st = sdpa_attention_device_full(ctx, p.K.data(), p.V.data(), p.n_local.data(), p.dk, p.dv, p.Q.data(), p.result, p.m);
         if (st != SDPA_OK) break;
     }
-    umma_plan_force_exact(s.plan, false);
+    for (Shard& s : ctx->shards) umma_plan_force_exact(s.plan, false);
     ctx->repairing = false;
     return st;
 }
@@ -1841,7 +1872,7 @@ sdpa_status sdpa_synchronize(sdpa_ctx* ctx)
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
     }
-    return resolve_pending(ctx);
+    return resolve_pending(ctx);   // collective when the context spans several processes
 }
 
 sdpa_status sdpa_online_softmax_partials(sdpa_ctx* ctx, int local, const float* Qf_dev, int m, float* contrib_dev,
