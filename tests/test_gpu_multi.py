@@ -178,3 +178,55 @@ def test_overlapped_queued_passes(sdpa, oracle, tmp_path):
     world = 2
     mp.spawn(_overlap_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _deferred_worker(rank, world, port, out_dir):
+    """Queued passes across two processes without the exact twin in the stream: the pass whose guard fires on ONE shard only
+    must be repaired by both processes at sdpa_synchronize (MAX all-reduce of the guard verdicts)."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from sdpa_b200 import parallel
+    from oracle import oracle as o
+
+    m, d, n = 700, 128, 3000
+    good = o.make_inputs(m, n, d, d, seed=3)
+    Q, K, V = o.make_inputs(m, n, d, d, seed=11)
+    K = K.copy()
+    K[:128] *= 0.01            # shard 0's first key tile is tiny ...
+    K[128:1400] *= 30.0        # ... the rest of shard 0 enormous: only shard 0 raises its guard; shard 1 is ordinary
+    bad = (Q * 3.0, K, V)
+    cases = [tuple(o.bf16_round(a).astype(np.float64) for a in c) for c in (good, bad, good)]
+    for merge in ("peer", "nccl2"):
+        ctx = parallel.bootstrap_context(precision="bf16", q_batch=512, local_rank=rank, merge=merge)
+        dev, outs = [], []
+        for Qc, Kc, Vc in cases:
+            first, count = parallel.shard_rows(n, world, rank)
+            dev.append([torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (Kc[first:first + count], Vc[first:first + count], Qc)])
+            outs.append(torch.zeros(m, d, dtype=torch.float64, device="cuda") if rank == 0 else None)
+        for rep in range(2):
+            for (Kd, Vd, Qd), out in zip(dev, outs):
+                ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], d, d, [Qd.data_ptr()],
+                                          out.data_ptr() if out is not None else None, m, blocking=False)
+        ctx.synchronize()
+        if rank == 0:
+            for (Qc, Kc, Vc), out, tol in zip(cases, outs, (2e-3, 2e-2, 2e-3)):
+                got = out.cpu().numpy()
+                assert np.isfinite(got).all()
+                np.testing.assert_allclose(got, o.attention_f64_numpy(Qc, Kc, Vc), rtol=0, atol=tol)
+        ctx.close()
+    dist.barrier()
+    Path(out_dir, f"okd{rank}").write_text("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_deferred_guard_repair_across_processes(sdpa, oracle, tmp_path):
+    _need_gpus(sdpa, 2)
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_deferred_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"okd{r}").exists() for r in range(world))
