@@ -209,6 +209,9 @@ struct Shard {
 
 using namespace sdpa;
 
+// Deferred guard repair on contexts with several K/V shards (agreement by all-reduce at sdpa_synchronize): default.
+static constexpr bool kDeferAcrossGpus = false;
+
 struct sdpa_ctx {
     sdpa_config cfg;
     std::vector<Shard> shards;
@@ -236,6 +239,7 @@ struct sdpa_ctx {
     std::vector<PendingPass> pending;
     std::vector<GuardRef> call_guards;        // collected by the attention call in flight
     bool defer_twin = true, deferring = false, repairing = false;
+    bool defer_multi = kDeferAcrossGpus;    // contexts with several shards: SDPA_DEFER_TWIN=2 / 1 overrides
     unsigned int ring_use = 0;              // fused launches since the pending passes were last resolved (the guard ring has kGuardRing words)
     int mark_every = 1;                     // queued passes: stage marks on every mark_every-th pass (SDPA_STAGE_TIMING_EVERY); blocking: always
     unsigned long long queued_seq = 0;
@@ -828,7 +832,8 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     if (!ctx->repairing && !ctx->pending.empty() && ctx->ring_use + (unsigned int)num_iter + 8 >= kGuardRing)
         SDPA_TRY(resolve_pending(ctx));   // the guard words of the pending passes must not be reused before they are read
     ctx->ring_use += (unsigned int)num_iter;
-    ctx->deferring = ctx->defer_twin && !blocking && !ctx->repairing && is_umma(ctx->prec) && on_device && (result_on_device || !ctx->has_root());
+    ctx->deferring = ctx->defer_twin && (world == 1 || ctx->defer_multi) && !blocking && !ctx->repairing && is_umma(ctx->prec) && on_device &&
+                     (result_on_device || !ctx->has_root());
     ctx->call_guards.clear();
     // stage marks: every blocking call; queued passes on every mark_every-th pass (each timestamp event costs ~2 us of stream time)
     const bool marked = blocking || ctx->mark_every <= 1 || (ctx->queued_seq++ % (unsigned long long)ctx->mark_every) == 0;
@@ -1590,7 +1595,10 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
     ctx->rank_base = cfg.rank_base;
     {
         if (const char* me = getenv("SDPA_STAGE_TIMING_EVERY")) ctx->mark_every = std::max(1, atoi(me));
-        if (const char* dt = getenv("SDPA_DEFER_TWIN")) ctx->defer_twin = !(*dt == '0');
+        if (const char* dt = getenv("SDPA_DEFER_TWIN")) {   // 0: twin always in the stream; 1: deferred on single-shard contexts only; 2: everywhere
+            ctx->defer_twin = *dt != '0';
+            ctx->defer_multi = *dt == '2' ? true : (*dt == '1' ? false : ctx->defer_multi);
+        }
         const char* ov = getenv("SDPA_OVERLAP_PASSES");   // SDPA_OVERLAP_PASSES=0: every queued pass joins its exchange before the next starts
         ctx->overlap_passes = !(ov && *ov == '0');
     }

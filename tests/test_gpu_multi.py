@@ -184,7 +184,8 @@ def _deferred_worker(rank, world, port, out_dir):
     """Queued passes across two processes without the exact twin in the stream: the pass whose guard fires on ONE shard only
     must be repaired by both processes at sdpa_synchronize (MAX all-reduce of the guard verdicts)."""
     sys.path.insert(0, str(ROOT))
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      SDPA_DEFER_TWIN="2")
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
