@@ -86,6 +86,7 @@ struct SyncArgs {
     unsigned int spin_epoch;   // value awaited in every `ready` flag at entry
     int enabled;               // bit 0: spin on the ready flags at entry; bit 1: release `consumed` at the end
     int nready;                // flags to spin on (0 = the kernel's state count)
+    int root;                  // this is the root's cross-GPU merge (timeline trace slots 1-3 and 4+r)
     unsigned long long* trace;
 };
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ void sync_enter(const SyncArgs& sync, int count)
 {
     if (!(sync.enabled & 1)) return;
     const int nready = sync.nready > 0 ? sync.nready : count;
-    const bool root_merge = sync.nready == 0;
+    const bool root_merge = sync.root != 0;
     if (sync.trace && root_merge && blockIdx.x == 0 && threadIdx.x == 0) sync.trace[1] = global_ns();
     if ((int)threadIdx.x < nready) {
         spin_until(sync.ready[threadIdx.x], sync.spin_epoch, 2);
@@ -116,7 +117,7 @@ __device__ __forceinline__ void sync_exit(const SyncArgs& sync)
             *sync.block_counter = 0;
             __threadfence_system();
             st_release_sys(sync.consumed, sync.epoch);
-            if (sync.trace) sync.trace[(sync.enabled & 1) && sync.nready == 0 ? 3 : 0] = global_ns();   // [3] root merge done, [0] state published
+            if (sync.trace) sync.trace[sync.root ? 3 : 0] = global_ns();   // [3] root merge done, [0] state published
         }
     }
 }
@@ -340,12 +341,14 @@ template <bool FINAL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 merge_pieces_kernel(StatePtrs st, WorkMap wm, int max_pieces, int rows, int dv, double* __restrict__ out64, float* __restrict__ contrib,
                     float* __restrict__ tmax_out, float* __restrict__ lsum_out, bool vec_ok, const unsigned int* __restrict__ guard,
-                    unsigned int epoch, const SyncArgs sync)
+                    unsigned int epoch, const SyncArgs sync, int base, int fixed_own)
 {
+    // states [0, base): other shards' published states (root's in-stream merge); then this shard's own partial states:
+    // fixed_own split states, or (persistent fused kernel) the pieces of the row's block / all max_pieces after the exact twin
     sync_enter(sync, 0);
     const int row = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (row < rows) {
-        const int count = (*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256);
+        const int count = base + (fixed_own > 0 ? fixed_own : ((*guard == epoch) ? max_pieces : wm_pieces(wm, row / 256)));
         merge_one_row<FINAL>(st, count, row, dv, FINAL ? out64 + (size_t)row * dv : nullptr, FINAL ? nullptr : contrib + (size_t)row * dv,
                              FINAL ? nullptr : tmax_out + row, FINAL ? nullptr : lsum_out + row, 1.f, vec_ok);
     }
@@ -492,6 +495,7 @@ sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const fl
     sa.epoch = sa.spin_epoch = sync.epoch;
     sa.enabled = 3;
     sa.nready = 0;
+    sa.root = sync.trace ? 1 : 0;
     sa.trace = sync.trace;
     const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     bool vec_ok = al16(out64);
@@ -524,9 +528,56 @@ sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces
     const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     const SyncArgs sa = publish_args(publish);
     if (out64) merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, out64, nullptr, nullptr, nullptr,
-                                                                                    vec_ok, guard, epoch, sa);
+                                                                                    vec_ok, guard, epoch, sa, 0, 0);
     else merge_pieces_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm, max_pieces, rows, dv, nullptr, contrib, tmax_out, lsum_out,
-                                                                               vec_ok, guard, epoch, sa);
+                                                                               vec_ok, guard, epoch, sa, 0, 0);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+// Root GPU, in-stream form of the cross-GPU merge: ONE kernel merges the root's own partial states (pieces of the persistent
+// kernel when wm != NULL, else part.splits split states) with the other shards' published states -- it waits for their flags
+// at entry, writes the normalised fp64 rows and releases "consumed".  The root neither publishes a state of its own nor runs a
+// second merge.
+sdpa_status launch_merge_root_instream(Partials part, const WorkMap* wm, int max_pieces, const unsigned int* guard, unsigned int guard_epoch,
+                                       const float* const* peer_c, const float* const* peer_t, const float* const* peer_l, int npeers,
+                                       int rows, int dv, double* out64, const PeerSync& sync, cudaStream_t stream)
+{
+    const int own = wm ? max_pieces : part.splits;
+    if (npeers < 1 || own < 1 || npeers + own > 64 || !out64) {
+        set_error("in-stream root merge: %d peers + %d own states (at most 64 together)", npeers, own);
+        return SDPA_ERR_INVALID;
+    }
+    if (rows < 0) rows = 0;
+    StatePtrs st;
+    bool vec_ok = al16(out64);
+    for (int r = 0; r < npeers; ++r) {
+        st.o[r] = peer_c[r];
+        st.tmax[r] = peer_t[r];
+        st.lsum[r] = peer_l[r];
+        vec_ok = vec_ok && al16(st.o[r]);
+    }
+    for (int k = 0; k < own; ++k) {
+        st.o[npeers + k] = part.o + (size_t)k * part.rows_capacity * dv;
+        st.tmax[npeers + k] = part.tmax + (size_t)k * part.rows_capacity;
+        st.lsum[npeers + k] = part.lsum + (size_t)k * part.rows_capacity;
+        vec_ok = vec_ok && al16(st.o[npeers + k]);
+    }
+    SyncArgs sa{};
+    for (int r = 0; r < npeers; ++r) sa.ready[r] = sync.ready[r];
+    sa.nready = npeers;
+    sa.consumed = sync.consumed;
+    sa.block_counter = sync.block_counter;
+    sa.epoch = sa.spin_epoch = sync.epoch;
+    sa.enabled = 3;
+    sa.root = sync.trace ? 1 : 0;
+    sa.trace = sync.trace;
+    static const unsigned int never = 0;   // no guard word: split states, count fixed
+    const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
+    merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm ? *wm : WorkMap{1, 1, 1}, max_pieces, rows, dv, out64, nullptr, nullptr,
+                                                                         nullptr, vec_ok, wm ? guard : &never, guard_epoch, sa, npeers,
+                                                                         wm ? 0 : part.splits);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
