@@ -244,12 +244,12 @@ def oracle_rows(m: int, shard_rows, rows):
     import numpy as np
     from oracle import oracle
     Q = make_q(m).numpy()[rows]
-    Ks, Vs = [], []
-    for r, cnt in enumerate(shard_rows):
-        K, V = make_shard(r, cnt)
-        Ks.append(K.numpy())
-        Vs.append(V.numpy())
-    return oracle.attention_f64_numpy(Q, np.concatenate(Ks), np.concatenate(Vs))
+
+    def shards():   # one shard in host memory at a time (c5: 1M keys = 2 GiB of fp64 K/V)
+        for r, cnt in enumerate(shard_rows):
+            K, V = make_shard(r, cnt)
+            yield K.numpy(), V.numpy()
+    return oracle.attention_f64_streamed(Q, shards())
 
 
 # --------------------------------------------------------------------------- reference / CPU baseline

@@ -151,6 +151,10 @@ struct PeerSync {
 sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
                                       const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
                                       const PeerSync& sync, cudaStream_t stream);
+// Root GPU, in-stream cross-GPU merge: own partial states (pieces if wm != NULL, else part.splits) + the peers' published states.
+sdpa_status launch_merge_root_instream(Partials part, const WorkMap* wm, int max_pieces, const unsigned int* guard, unsigned int guard_epoch,
+                                       const float* const* peer_c, const float* const* peer_t, const float* const* peer_l, int npeers,
+                                       int rows, int dv, double* out64, const PeerSync& sync, cudaStream_t stream);
 // Split merge behind the persistent fused kernel: per row, wm_pieces(row block) states (all max_pieces if *guard == epoch).
 // out64 != NULL: normalised fp64 rows; else the merged un-normalised state (contrib, tmax, lsum) for the cross-GPU merge.
 sdpa_status launch_merge_pieces(Partials part, const WorkMap& wm, int max_pieces, int rows, int dv, double* out64, float* contrib,

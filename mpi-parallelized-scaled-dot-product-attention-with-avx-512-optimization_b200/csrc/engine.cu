@@ -209,6 +209,8 @@ struct Shard {
 
 using namespace sdpa;
 
+// Root form of the device-side exchange: in-stream (one merge kernel on the root per batch) or on the comm stream.
+static constexpr bool kRootMergeInstream = false;
 // Deferred guard repair on contexts with several K/V shards (agreement by all-reduce at sdpa_synchronize): default.
 static constexpr bool kDeferAcrossGpus = false;
 
@@ -268,6 +270,7 @@ struct sdpa_ctx {
         unsigned int* root_flags = nullptr;     // the root's flag block (== peer_flags[0])
         double* root_stage[2] = {nullptr, nullptr};
         bool sliced = false;            // the root merges all rows (default) / every rank merges its share of the rows
+        bool instream = false;          // root form: the root merges its own pieces and the peers' states in ONE kernel of its compute stream
         std::vector<void*> opened;      // IPC mappings to close
         unsigned int epoch = 0;         // global batch counter, identical on every rank
         unsigned int slot_epoch[2] = {0, 0};
@@ -687,6 +690,10 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         // share of the rows from an inbox the others push into.  Measured equal at 8 GPUs (0.354 vs 0.356 ms per c3 step) and
         // the root form ahead at 2 (0.308 vs 0.331 ms): the exchange is bound by its flag hops, not by the root's ingress.
         x.sliced = ipc_sliced_requested();
+        {
+            const char* rm = getenv("SDPA_ROOT_MERGE");   // instream | overlap
+            x.instream = !x.sliced && (rm ? !strcmp(rm, "instream") : kRootMergeInstream);
+        }
     }
     struct Handles { cudaIpcMemHandle_t x0, x1, fl, s0, s1; };
     Handles mine;
@@ -994,6 +1001,27 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                             to.epoch = x.epoch;
                             to.world = world;
                             SDPA_TRY(launch_merge_splits_routed(part, bs, dv, to, s.s_compute, pieces ? &wm : nullptr, max_pieces, guard, guard_epoch));
+                        } else if (x.instream && s.grank == 0) {
+                            // the root: its own partial states and every other shard's published state in ONE merge, right here in
+                            // the compute stream (no state of its own to publish, no second merge on the comm stream)
+                            const float* cp[64];
+                            const float* tp[64];
+                            const float* lp[64];
+                            PeerSync sync;
+                            for (int r = 1; r < world; ++r) {
+                                const float* base = reinterpret_cast<const float*>(x.peer_x[b][r]);
+                                cp[r - 1] = base;
+                                tp[r - 1] = base + (size_t)x.cap_rows * dv;
+                                lp[r - 1] = tp[r - 1] + x.cap_rows;
+                                sync.ready[r - 1] = x.peer_flags[r] + b;
+                            }
+                            sync.consumed = x.flags.as<unsigned int>() + 2 + b;
+                            sync.block_counter = x.flags.as<unsigned int>() + 4 + b;
+                            sync.epoch = x.epoch;
+                            sync.trace = x.trace_slot(x.epoch);
+                            double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+                            SDPA_TRY(launch_merge_root_instream(part, pieces ? &wm : nullptr, max_pieces, guard, guard_epoch, cp, tp, lp, world - 1, bs,
+                                                                dv, dst, sync, s.s_compute));
                         } else {
                             // one launch: wait for the root's "consumed" flag of this slot, merge the shard's partial states
                             // into the slot, publish the epoch flag
@@ -1063,6 +1091,9 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_TRY(time_end(s, 2, s.s_comm));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
                 if (s.grank != 0) SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+            } else if (s.grank == 0 && x.instream) {
+                // the merge already ran in the compute stream
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_compute));
             } else if (s.grank == 0) {
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
                 const float* cp[64];

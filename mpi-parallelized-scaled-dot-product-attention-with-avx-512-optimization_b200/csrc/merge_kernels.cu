@@ -571,12 +571,11 @@ sdpa_status launch_merge_root_instream(Partials part, const WorkMap* wm, int max
     sa.block_counter = sync.block_counter;
     sa.epoch = sa.spin_epoch = sync.epoch;
     sa.enabled = 3;
-    sa.root = sync.trace ? 1 : 0;
+    sa.root = 1;
     sa.trace = sync.trace;
-    static const unsigned int never = 0;   // no guard word: split states, count fixed
     const int blocks = std::max(1, ceil_div(rows, kWarpsPerBlock));
     merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm ? *wm : WorkMap{1, 1, 1}, max_pieces, rows, dv, out64, nullptr, nullptr,
-                                                                         nullptr, vec_ok, wm ? guard : &never, guard_epoch, sa, npeers,
+                                                                         nullptr, vec_ok, wm ? guard : nullptr, guard_epoch, sa, npeers,
                                                                          wm ? 0 : part.splits);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());

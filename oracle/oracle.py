@@ -126,6 +126,31 @@ def attention_f64_numpy(Q, K, V, rows: slice | None = None) -> np.ndarray:
     return out
 
 
+def attention_f64_streamed(Q, kv_shards) -> np.ndarray:
+    """The same fp64 definition with K/V arriving shard by shard (`kv_shards` yields (K_r, V_r) in row order): per-shard
+    (max, sum, weighted V) states in fp64, combined with the identity of attention-mpi.c:342-380 -- never more than one
+    shard in host memory (c5: 2 x 1 GiB of fp64 K/V).  Equal to attention_f64_numpy up to fp64 rounding."""
+    Q = _c64(Q)
+    scale = 1.0 / np.sqrt(float(Q.shape[1]))
+    gmax = np.full((Q.shape[0], 1), -np.inf)
+    gsum = np.zeros((Q.shape[0], 1))
+    acc = None
+    for K, V in kv_shards:
+        K, V = _c64(K), _c64(V)
+        if acc is None:
+            acc = np.zeros((Q.shape[0], V.shape[1]))
+        if K.shape[0] == 0:
+            continue
+        s = (Q @ K.T) * scale
+        new_max = np.maximum(gmax, s.max(axis=1, keepdims=True))
+        keep = np.where(np.isneginf(gmax), 0.0, np.exp(gmax - new_max))
+        np.exp(s - new_max, out=s)
+        gsum = gsum * keep + s.sum(axis=1, keepdims=True)
+        acc = acc * keep + s @ V
+        gmax = new_max
+    return acc / gsum
+
+
 def attention_f64(Q, K, V, row_begin: int = 0, row_end: int | None = None) -> np.ndarray:
     """C restatement with the reference's exact operation order (bit-identical to
     the compiled attention.c).  Rows outside [row_begin,row_end) are left zero."""

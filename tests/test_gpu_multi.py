@@ -84,7 +84,8 @@ def _overlap_worker(rank, world, port, out_dir):
 
     m, d = 1500, 128
     cases = [o.make_inputs(m, 4000 + 300 * k, d, d, seed=90 + k) for k in range(3)]   # different K/V/Q per pass
-    for prec, atol in (("bf16", 1e-2), ("f32", 1e-5)):
+    for prec, atol, root_merge in (("bf16", 1e-2, "overlap"), ("f32", 1e-5, "overlap"), ("bf16", 1e-2, "instream"), ("f32", 1e-5, "instream")):
+        os.environ["SDPA_ROOT_MERGE"] = root_merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge="peer")
         dev, outs = [], []
         for Q, K, V in cases:
@@ -122,11 +123,14 @@ def _rank_worker(rank, world, port, out_dir, id_file):
     ref = o.attention_f64_numpy(Q, K, V) if rank == 0 else None
     first, count = parallel.shard_rows(n, world, rank)
     for prec, atol, merge in (("f32", 1e-5, "nccl2"), ("bf16", 1e-2, "nccl3"), ("bf16", 1e-2, "peer"), ("f32", 1e-5, "peer"),
-                              ("bf16", 1e-2, "peer-sliced"), ("f32", 1e-5, "peer-sliced"), ("bf16x3", 1e-5, "peer"), ("auto", 1e-5, "nccl2")):
+                              ("bf16", 1e-2, "peer-sliced"), ("f32", 1e-5, "peer-sliced"), ("bf16x3", 1e-5, "peer"), ("auto", 1e-5, "nccl2"),
+                              ("bf16", 1e-2, "peer-instream"), ("f32", 1e-5, "peer-instream"), ("bf16x3", 1e-5, "peer-instream")):
         # (1) pre-sharded inputs, one context per rank (bench.py's model); merge="peer" = CUDA-IPC device-side exchange
         # (the root GPU merges all rows; "peer-sliced" = every rank merges its share of the rows from a pushed inbox)
+        # "peer-instream" = the root merges its own partial states and the other shards' states in one kernel of its compute stream
         os.environ["SDPA_IPC_MERGE"] = "sliced" if merge == "peer-sliced" else "root"
-        merge = "peer" if merge == "peer-sliced" else merge
+        os.environ["SDPA_ROOT_MERGE"] = "instream" if merge == "peer-instream" else "overlap"
+        merge = "peer" if merge.startswith("peer-") else merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge=merge)
         ctx.load_kv_host([K[first:first + count]], [V[first:first + count]])
         for _ in range(2):   # twice: slot reuse across calls

@@ -19,7 +19,10 @@ if 0 not in ranks:
     sys.exit("no trace of rank 0 under " + base)
 R = ranks[0]
 n = len(ranks)
-steps = sorted(e for e in R if R[e][3] and all(R[e][4 + r] for r in range(min(n, 8))))
+# in-stream root merge (SDPA_ROOT_MERGE=instream): the root publishes nothing (slot 0 stays 0) and waits for n-1 flags
+instream = sum(1 for e in R if R[e][3] and not R[e][0]) > len(R) // 2
+nflags = min(n - 1 if instream else n, 8)
+steps = sorted(e for e in R if R[e][3] and all(R[e][4 + r] for r in range(nflags)))
 steps = steps[len(steps) // 4:]          # drop the warm-up quarter
 if not steps:
     sys.exit("no complete steps")
@@ -31,14 +34,16 @@ def med(xs):
 
 
 # Every GPU has its own %globaltimer: all cross-rank times are taken on the ROOT's clock (when its merge kernel saw a flag).
-seen = {e: [R[e][4 + r] for r in range(min(n, 8))] for e in steps}
-print(f"{n} ranks, {len(steps)} exchange steps (us, medians, root GPU's clock)")
-print(f"  root's own state published -> root merge kernel started            : {med(R[e][1] - R[e][0] for e in steps):8.1f}")
+seen = {e: [R[e][4 + r] for r in range(nflags)] for e in steps}
+print(f"{n} ranks, {len(steps)} exchange steps (us, medians, root GPU's clock)" + (", in-stream root merge" if instream else ""))
+if not instream:
+    print(f"  root's own state published -> root merge kernel started            : {med(R[e][1] - R[e][0] for e in steps):8.1f}")
 print(f"  merge kernel start -> last shard's flag seen (wait for the slowest) : {med(max(seen[e]) - R[e][1] for e in steps):8.1f}")
 print(f"  flag arrival spread (last - first flag seen by the root)            : {med(max(seen[e]) - min(seen[e]) for e in steps):8.1f}")
 print(f"  all flags seen -> merged, 'consumed' raised (reads over NVLink)     : {med(R[e][3] - R[e][2] for e in steps):8.1f}")
 print(f"  merge kernel total                                                  : {med(R[e][3] - R[e][1] for e in steps):8.1f}")
 print(f"  step period (merge done -> merge done of consecutive epochs)        : {med(R[b][3] - R[a][3] for a, b in zip(steps, steps[1:]) if b == a + 1):8.1f}")
-print(f"  root published -> root published of consecutive epochs              : {med(R[b][0] - R[a][0] for a, b in zip(steps, steps[1:]) if b == a + 1):8.1f}")
+if not instream:
+    print(f"  root published -> root published of consecutive epochs              : {med(R[b][0] - R[a][0] for a, b in zip(steps, steps[1:]) if b == a + 1):8.1f}")
 late = [max(range(len(seen[e])), key=lambda i: seen[e][i]) for e in steps]
 print("  slowest shard histogram (rank: steps)                               :", {r: late.count(r) for r in sorted(set(late))})
