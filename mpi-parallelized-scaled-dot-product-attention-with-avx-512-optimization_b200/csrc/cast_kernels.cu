@@ -6,6 +6,7 @@
 // d2f and f2d, 10 B/element for d2bf16.  Each thread moves 16-byte vectors with
 // several independent loads in flight; a scalar kernel covers unaligned pointers and tails.
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
 namespace sdpa {
 
@@ -227,6 +228,95 @@ __global__ void __launch_bounds__(kCastThreads) cvt_in_batch_kernel(CastBatch cb
     }
 }
 
+// The same batch as a BACKGROUND kernel (queued passes: the casts of pass i+1 run while the fused kernel of pass i owns the
+// tensor cores).  It has to fit beside a resident CTA of the persistent fused kernel (640 threads x 96 registers, ~183 KB of
+// shared memory): ONE CTA per SM of 128 threads x <= 32 registers and 32 KB of shared memory.  The bytes in flight that an
+// HBM-bound copy needs therefore live in shared memory, not in registers: thread 0 keeps kBgStages bulk copies
+// (cp.async.bulk, 8 KB of fp64 each, L2 evict-first: the source is read once and must not push the fused kernel's K/V
+// tiles out of L2) in flight; the CTA converts a landed chunk and stores it with 128-byte coalesced stores.
+constexpr int kBgThreads = 128;
+constexpr int kBgChunkUnits = 512;                       // 2-element units per chunk = 8 KB of fp64
+constexpr int kBgStages = 4;
+constexpr size_t kBgSmem = (size_t)kBgStages * kBgChunkUnits * 16 + 64;
+
+__device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(umma::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(umma::smem_u32(bar)), "l"(policy) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBatch cb)
+{
+    extern __shared__ __align__(128) uint8_t bg_smem[];
+    double2* ring = reinterpret_cast<double2*>(bg_smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(bg_smem + (size_t)kBgStages * kBgChunkUnits * 16);
+    // chunks: segment after segment, every segment's last chunk may be short
+    const unsigned int c0 = (unsigned int)((cb.units[0] + kBgChunkUnits - 1) / kBgChunkUnits);
+    const unsigned int c1 = c0 + (unsigned int)((cb.units[1] + kBgChunkUnits - 1) / kBgChunkUnits);
+    const unsigned int nchunks = c1 + (unsigned int)((cb.units[2] + kBgChunkUnits - 1) / kBgChunkUnits);
+    auto locate = [&](unsigned int chunk, int& seg, size_t& first, unsigned int& units) {
+        seg = chunk < c0 ? 0 : (chunk < c1 ? 1 : 2);
+        first = (size_t)(chunk - (seg == 0 ? 0u : (seg == 1 ? c0 : c1))) * kBgChunkUnits;
+        const size_t left = cb.units[seg] - first;
+        units = left < (size_t)kBgChunkUnits ? (unsigned int)left : (unsigned int)kBgChunkUnits;
+    };
+    auto issue = [&](unsigned int chunk, int stage) {
+        int seg;
+        size_t first;
+        unsigned int units;
+        locate(chunk, seg, first, units);
+        umma::mbar_arrive_expect_tx(&full[stage], units * 16u);
+        bulk_load_evict_first(ring + (size_t)stage * kBgChunkUnits, reinterpret_cast<const double2*>(cb.src[seg]) + first, units * 16u, &full[stage]);
+    };
+    if (threadIdx.x == 0) {
+        for (int st = 0; st < kBgStages; ++st) umma::mbar_init(&full[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int st = 0; st < kBgStages; ++st) {
+            const unsigned int chunk = blockIdx.x + (unsigned int)st * gridDim.x;
+            if (chunk < nchunks) issue(chunk, st);
+        }
+    unsigned int k = 0;
+    for (unsigned int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++k) {
+        const int stage = (int)(k % kBgStages);
+        int seg;
+        size_t first;
+        unsigned int units;
+        locate(chunk, seg, first, units);
+        umma::mbar_wait(&full[stage], (k / kBgStages) & 1u, 90);
+        const double2* in = ring + (size_t)stage * kBgChunkUnits;
+        void* dst = cb.dst[seg];
+        const size_t lo = cb.lo_off[seg];
+        double2 v[kBgChunkUnits / kBgThreads];
+#pragma unroll
+        for (int j = 0; j < kBgChunkUnits / kBgThreads; ++j) v[j] = in[j * kBgThreads + threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < kBgChunkUnits / kBgThreads; ++j) {
+            const unsigned int u = j * kBgThreads + threadIdx.x;
+            if (u >= units) continue;
+            const size_t off = first + u;
+            if (MODE == 2) {
+                uint32_t h, l;
+                split_bf16x2(v[j], h, l);
+                reinterpret_cast<uint32_t*>(dst)[off] = h;
+                reinterpret_cast<uint32_t*>(dst)[off + lo] = l;
+            } else if (MODE == 1) {
+                reinterpret_cast<uint32_t*>(dst)[off] = pack_bf16x2(__double2float_rn(v[j].x), __double2float_rn(v[j].y));
+            } else {
+                reinterpret_cast<float2*>(dst)[off] = make_float2(__double2float_rn(v[j].x), __double2float_rn(v[j].y));
+            }
+        }
+        __syncthreads();   // every thread has read its share of the stage
+        const unsigned int next = chunk + (unsigned int)kBgStages * gridDim.x;
+        if (threadIdx.x == 0 && next < nchunks) issue(next, stage);
+    }
+}
+
 inline int cast_grid(size_t work_items)
 {
     // 148 SMs x 8 resident CTAs of 256 threads; never more CTAs than work.
@@ -246,6 +336,9 @@ void preload_cast_kernels()
     cudaFuncGetAttributes(&a, cvt_in_batch_kernel<0>);
     cudaFuncGetAttributes(&a, cvt_in_batch_kernel<1>);
     cudaFuncGetAttributes(&a, cvt_in_batch_kernel<2>);
+    cudaFuncGetAttributes(&a, cvt_in_batch_bg_kernel<0>);
+    cudaFuncGetAttributes(&a, cvt_in_batch_bg_kernel<1>);
+    cudaFuncGetAttributes(&a, cvt_in_batch_bg_kernel<2>);
     cudaFuncGetAttributes(&a, cvt_d2f_vec_kernel);
     cudaFuncGetAttributes(&a, cvt_d2bf16_vec_kernel);
     cudaFuncGetAttributes(&a, cvt_d2bf16x2_vec_kernel);
@@ -332,7 +425,7 @@ sdpa_status launch_cvt_d2bf16x2(__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, co
 // Up to three operands in one launch; falls back to one launch per operand when a pointer is not 16-byte aligned
 // or a count is odd (the batched kernel moves 2-element units only).
 sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, const size_t* lo_off,
-                                int nseg, cudaStream_t stream)
+                                int nseg, cudaStream_t stream, int background_ctas)
 {
     if (nseg < 0 || nseg > 3) {
         set_error("launch_cvt_in_batch: 0..3 segments");
@@ -366,6 +459,15 @@ sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const*
             } else if (prec == SDPA_PREC_BF16) SDPA_TRY(launch_cvt_d2bf16(reinterpret_cast<__nv_bfloat16*>(dst[k]), src[k], count[k], stream));
             else SDPA_TRY(launch_cvt_d2f(reinterpret_cast<float*>(dst[k]), src[k], count[k], stream));
         }
+        return SDPA_OK;
+    }
+    if (background_ctas > 0) {
+        // small-footprint form, one CTA per SM
+        if (split) cvt_in_batch_bg_kernel<2><<<background_ctas, kBgThreads, kBgSmem, stream>>>(cb);
+        else if (prec == SDPA_PREC_BF16) cvt_in_batch_bg_kernel<1><<<background_ctas, kBgThreads, kBgSmem, stream>>>(cb);
+        else cvt_in_batch_bg_kernel<0><<<background_ctas, kBgThreads, kBgSmem, stream>>>(cb);
+        count_launch();
+        SDPA_CUDA_TRY(cudaGetLastError());
         return SDPA_OK;
     }
     const int grid = cast_grid(units_total / kUnroll);

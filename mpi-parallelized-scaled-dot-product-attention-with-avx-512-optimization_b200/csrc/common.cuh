@@ -67,7 +67,9 @@ struct CastBatch {
 };
 // lo_off (elements, per segment) is read for SDPA_PREC_BF16X3 only and may be NULL otherwise.
 sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, const size_t* lo_off,
-                                int nseg, cudaStream_t stream);
+                                int nseg, cudaStream_t stream, int background_ctas = 0);
+// background_ctas > 0: the small-footprint form (that many CTAs of 128 threads, 32 KB of shared memory, <= 32 registers) that
+// fits on an SM beside a resident CTA of the persistent fused kernel.
 
 // fp32 CUDA-core fused attention.  Q [rows x dk], K [n x dk], V [n x dv] fp32 row-major.
 // If out64 != nullptr (requires splits == 1) the normalised result is written as fp64

@@ -166,6 +166,15 @@ struct Shard {
 
     // resident shard in compute precision
     DevBuf Kc, Vc;
+    // Cast-ahead (queued device-resident passes): a second K/V set, so that the casts of pass i+1 (side stream s_cast,
+    // small-footprint kernel) run under the fused kernel of pass i, which still reads the other set.  Kc / Vc always name
+    // the set of the pass being issued (the sets swap per pass); kv_guard[set] = event behind the last kernel that read it.
+    DevBuf KcAlt, VcAlt;
+    cudaStream_t s_cast = nullptr;
+    cudaEvent_t ev_cast_done = nullptr;
+    cudaEvent_t kv_guard[2] = {nullptr, nullptr}, ev_kv_read[2] = {nullptr, nullptr};
+    int kv_set = 0;
+    bool ahead_call = false;                 // the pass being issued casts ahead (set by load_kv, consumed by attention_impl)
     size_t k_lo_off = 0, v_lo_off = 0, q_lo_off = 0;   // split precision: elements from an operand's hi array to its lo array
     int n_local = 0;
     // staging for fp64 uploads of K/V (two chunks in flight)
@@ -251,7 +260,8 @@ struct sdpa_ctx {
     // of pass i+1 (SDPA_OVERLAP_PASSES=0 turns that off).  Blocking calls always join.
     bool qshard = false;                    // SDPA_DIST_Q in effect: every shard holds ALL K/V rows, Q rows are sharded, no exchange
     bool overlap_passes = false;
-    unsigned long long batch_seq = 0;       // batches issued in overlap mode (slot = batch_seq & 1)
+    bool cast_ahead = true;                 // SDPA_CAST_AHEAD=0: the casts of a queued pass stay on the compute stream
+    unsigned long long batch_seq = 0;       // batches issued by queued passes with sequence slots (slot = batch_seq & 1)
     bool exchange_pending = false;          // overlap mode left exchange work behind: drain before freeing / reallocating slots
     // device-side exchange across processes (one GPU per process): state buffers + flags shared through CUDA IPC
     struct Ipc {
@@ -435,6 +445,9 @@ static sdpa_status shard_init(Shard& s)
         SDPA_CUDA_TRY(mk(&s.ev_comm_done[b]));
     }
     for (int j = 0; j < 3; ++j) SDPA_CUDA_TRY(mk(&s.ev_join[j]));
+    SDPA_CUDA_TRY(cudaStreamCreateWithFlags(&s.s_cast, cudaStreamNonBlocking));
+    SDPA_CUDA_TRY(mk(&s.ev_cast_done));
+    for (int b = 0; b < 2; ++b) SDPA_CUDA_TRY(mk(&s.ev_kv_read[b]));
     if (mem_pool_enabled()) {   // keep freed blocks in the pool instead of returning them to the driver at every synchronisation
         cudaMemPool_t pool;
         unsigned long long keep = ~0ull;
@@ -453,7 +466,7 @@ static void shard_destroy(Shard& s, const NcclApi* api)
     cudaDeviceSynchronize();
     if (s.comm && api) api->CommDestroy(s.comm);
     if (s.plan) umma_plan_destroy(s.plan);
-    DevBuf* bufs[] = {&s.Kc, &s.Vc, &s.kv_stage[0], &s.kv_stage[1], &s.q64[0], &s.q64[1], &s.qc[0], &s.qc[1],
+    DevBuf* bufs[] = {&s.Kc, &s.Vc, &s.KcAlt, &s.VcAlt, &s.kv_stage[0], &s.kv_stage[1], &s.q64[0], &s.q64[1], &s.qc[0], &s.qc[1],
                       &s.part_o, &s.part_tmax, &s.part_lsum, &s.contrib[0], &s.contrib[1], &s.tmax[0],
                       &s.tmax[1], &s.lsum[0], &s.lsum[1], &s.gmax[0], &s.gmax[1], &s.gsum[0], &s.gsum[1],
                       &s.out32[0], &s.out32[1], &s.out64[0], &s.out64[1]};
@@ -462,12 +475,12 @@ static void shard_destroy(Shard& s, const NcclApi* api)
                          s.ev_q_ready[0], s.ev_q_ready[1], s.ev_q_free[0], s.ev_q_free[1],
                          s.ev_compute_done[0], s.ev_compute_done[1], s.ev_slot_free[0], s.ev_slot_free[1],
                          s.ev_comm_done[0], s.ev_comm_done[1],
-                         s.ev_join[0], s.ev_join[1], s.ev_join[2]};
+                         s.ev_join[0], s.ev_join[1], s.ev_join[2], s.ev_cast_done, s.ev_kv_read[0], s.ev_kv_read[1]};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s.marks) cudaEventDestroy(e);
     if (s.ev_begin) cudaEventDestroy(s.ev_begin);
-    cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out};
+    cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out, s.s_cast};
     for (cudaStream_t st : sts)
         if (st) cudaStreamDestroy(st);
 }
@@ -501,7 +514,7 @@ static sdpa_status upload_cast(Shard& s, int prec, void* dst, size_t lo_off, con
 }
 
 static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
-                           const int* n_local, int dk, int dv, bool on_device, bool defer_casts = false)
+                           const int* n_local, int dk, int dv, bool on_device, bool defer_casts = false, bool ahead = false)
 {
     if (!ctx || !n_local || dk < 1 || dv < 1) {
         set_error("load_kv: bad arguments");
@@ -522,6 +535,12 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
         }
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         s.n_local = n_local[i];
+        s.ahead_call = ahead && defer_casts && on_device && s.n_local > 0;
+        if (s.ahead_call) {   // this pass fills (and its kernels read) the other K/V set
+            std::swap(s.Kc, s.KcAlt);
+            std::swap(s.Vc, s.VcAlt);
+            s.kv_set ^= 1;
+        }
         // +128 rows of slack so TMA boxes / vector loads past the last row stay in bounds
         SDPA_TRY(s.Kc.reserve(((size_t)s.n_local + 128) * dk * esz));
         SDPA_TRY(s.Vc.reserve(((size_t)s.n_local + 128) * dv * esz));
@@ -552,6 +571,18 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
             SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
         }
     return SDPA_OK;
+}
+
+static int pick_q_batch(const sdpa_ctx* ctx, int m);
+// Pieces per row block when the persistent fused kernel takes the pass (dk = dv = 128 bf16, automatic splits, every shard the
+// same number of keys, enough work per SM pair), else 0.
+static int persistent_pieces(const sdpa_ctx* ctx, int prec, int dk, int dv, int B, const int* n_local)
+{
+    if (prec != SDPA_PREC_BF16 || dk != 128 || dv != 128 || ctx->cfg.kv_splits > 0) return 0;
+    for (size_t i = 1; i < ctx->shards.size(); ++i)
+        if (n_local[i] != n_local[0]) return 0;
+    const int pieces = attn_umma_v8_pieces(B, n_local[0], ctx->shards[0].sm_count);
+    return pieces > 1 ? pieces : 0;
 }
 
 static int pick_q_batch(const sdpa_ctx* ctx, int m)
@@ -800,6 +831,8 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             const size_t lo[2] = {s.k_lo_off, s.v_lo_off};
             SDPA_TRY(launch_cvt_in_batch(ctx->prec, s.pend_dst, s.pend_src, s.pend_cnt, lo, 2, s.s_compute));
             s.npend = 0;
+            s.ahead_call = false;
+            s.kv_guard[s.kv_set] = nullptr;
         }
         return SDPA_OK;
     }
@@ -822,15 +855,19 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     // count replaces the split count and the split merge reads pieces per row block (launch_merge_pieces).  Every shard must
     // own the same number of keys (the partial buffers and the piece count are shared).
     bool by_pieces = false;
-    bool same_n = true;
-    for (Shard& s : ctx->shards) same_n = same_n && s.n_local == ctx->shards[0].n_local;
-    if (ctx->prec == SDPA_PREC_BF16 && dk == 128 && dv == 128 && ctx->cfg.kv_splits <= 0 && same_n) {
-        const int pieces = attn_umma_v8_pieces(B, ctx->shards[0].n_local, ctx->shards[0].sm_count);
+    {
+        std::vector<int> nl;
+        for (Shard& s : ctx->shards) nl.push_back(s.n_local);
+        const int pieces = persistent_pieces(ctx, ctx->prec, dk, dv, B, nl.data());
         if (pieces > 1) {
             splits = pieces;
             by_pieces = true;
         }
     }
+    // cast-ahead pass (decided by sdpa_enqueue_device_full): the first cast runs on the side stream; Q slots follow the batch sequence
+    bool ahead = false;
+    for (Shard& s : ctx->shards) ahead = ahead || s.ahead_call;
+    const bool seq_slots = overlap || ahead;
     if (is_umma(ctx->prec))
         for (Shard& s : ctx->shards)
             if (s.plan) umma_plan_allow_v8(s.plan, by_pieces);
@@ -890,7 +927,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     for (int ii = 0; ii < num_iter; ++ii) {
         const int row0 = ii * B;
         const int bs = std::min(B, m - row0);
-        const int b = overlap ? (int)(ctx->batch_seq & 1) : (ii & 1);
+        const int b = seq_slots ? (int)(ctx->batch_seq & 1) : (ii & 1);
 
         // ---- per shard: Q batch in, cast, fused kernel, split merge -------------------------
         for (int i = 0; i < L; ++i) {
@@ -911,18 +948,27 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 q_src_dev = s.q64[b].as<double>();
             }
             // slot b (contrib/out buffers) must have been drained by batch ii-2's collectives / D2H
-            if ((overlap ? ctx->batch_seq >= 2 : ii >= 2) && use_out) {
+            if ((seq_slots ? ctx->batch_seq >= 2 : ii >= 2) && use_out) {
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_slot_free[b], 0));
                 compute_stream_touched(s);
             }
 
-            SDPA_TRY(time_begin(s, 0, s.s_compute));
+            // cast-ahead: K, V and the first Q batch of this pass are cast on the side stream by the small-footprint kernel --
+            // gated by the last readers of the K/V set (two passes back) and of the Q slot (two batches back), not by the pass
+            // in front, whose fused kernel it runs beside
+            const bool cast_aside = s.ahead_call && s.npend > 0;
+            cudaStream_t cst = cast_aside ? s.s_cast : s.s_compute;
+            if (cast_aside) {
+                if (s.kv_guard[s.kv_set]) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_cast, s.kv_guard[s.kv_set], 0));
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_cast, s.ev_compute_done[b], 0));
+            }
+            SDPA_TRY(time_begin(s, 0, cst));
             if (s.npend > 0) {
                 void* cd[3] = {s.pend_dst[0], s.pend_dst[1], s.qc[b].p};
                 const double* cs[3] = {s.pend_src[0], s.pend_src[1], q_src_dev};
                 const size_t cc[3] = {s.pend_cnt[0], s.pend_cnt[1], (size_t)bs * dk};
                 const size_t lo[3] = {s.k_lo_off, s.v_lo_off, s.q_lo_off};
-                SDPA_TRY(launch_cvt_in_batch(ctx->prec, cd, cs, cc, lo, have_q ? 3 : 2, s.s_compute));
+                SDPA_TRY(launch_cvt_in_batch(ctx->prec, cd, cs, cc, lo, have_q ? 3 : 2, cst, cast_aside ? s.sm_count : 0));
                 s.npend = 0;
                 ++all_launches;
             } else if (have_q) {
@@ -937,7 +983,12 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                     SDPA_NCCL_TRY(api->Broadcast(lo, lo, (size_t)bs * dk * 2, ncclUint8, 0, s.comm, s.s_compute));
                 }
             }
-            SDPA_TRY(time_end(s, 0, s.s_compute));
+            SDPA_TRY(time_end(s, 0, cst));
+            if (cast_aside) {
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_cast_done, s.s_cast));
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_compute, s.ev_cast_done, 0));
+                compute_stream_touched(s);
+            }
             if (!on_device && have_q) SDPA_CUDA_TRY(cudaEventRecord(s.ev_q_free[b], s.s_compute));
 
             Partials part{s.part_o.as<float>(), s.part_tmax.as<float>(), s.part_lsum.as<float>(), splits, B};
@@ -1045,7 +1096,16 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_TRY(time_end(s, 2, s.s_compute));
                 ++all_launches;
             }
-            if (use_comm || use_out) SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
+            if (use_comm || use_out || ahead) SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
+            if (ii == num_iter - 1) {
+                // who read this pass's K/V set last: the batch just issued
+                if (!ahead) s.kv_guard[s.kv_set] = nullptr;   // not a cast-ahead context / a blocking call (ends with a wait)
+                else if (num_iter == 1) s.kv_guard[s.kv_set] = s.ev_compute_done[b];
+                else {
+                    SDPA_CUDA_TRY(cudaEventRecord(s.ev_kv_read[s.kv_set], s.s_compute));
+                    s.kv_guard[s.kv_set] = s.ev_kv_read[s.kv_set];
+                }
+            }
         }
 
         // ---- cross-shard merge ----------------------------------------------------------------
@@ -1242,7 +1302,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                                               cudaMemcpyDeviceToHost, s.s_out));
             SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_out));
         }
-        if (overlap) ++ctx->batch_seq;
+        if (seq_slots) ++ctx->batch_seq;
     }
 
     if (use_ipc && ctx->shards[0].grank != 0 && !overlap) {
@@ -1278,7 +1338,10 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
 
     const double hp2 = host_prof ? host_now_us() : 0.0;
     if (overlap) ctx->exchange_pending = true;
-    for (Shard& s : ctx->shards) s.last_call_queued = !blocking;
+    for (Shard& s : ctx->shards) {
+        s.last_call_queued = !blocking;
+        s.ahead_call = false;
+    }
     if (marked) {
         ctx->last_timing_valid = false;   // evaluated lazily by sdpa_last_timings / sdpa_accumulated_timings
         ctx->acc_fused_launches += fused_launches;
@@ -1632,6 +1695,8 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
         }
         const char* ov = getenv("SDPA_OVERLAP_PASSES");   // SDPA_OVERLAP_PASSES=0: every queued pass joins its exchange before the next starts
         ctx->overlap_passes = !(ov && *ov == '0');
+        const char* ca = getenv("SDPA_CAST_AHEAD");
+        ctx->cast_ahead = !(ca && *ca == '0');
     }
     ctx->shards.resize(L);
     sdpa_status st = SDPA_OK;
@@ -1830,7 +1895,16 @@ sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shard
         set_error("sdpa_enqueue_device_full: Q_dev is NULL");
         return SDPA_ERR_INVALID;
     }
-    SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true));
+    // Cast-ahead: where the persistent fused kernel takes the pass (it leaves room on every SM for one small CTA), on one GPU or
+    // with the overlapped device-side exchange, the casts of this pass run beside the previous pass's fused kernel.
+    bool ahead = false;
+    if (ctx && ctx->cast_ahead && !ctx->repairing && n_local && m > 0 && dk == 128 && dv == 128) {
+        const int L = (int)ctx->shards.size();
+        const bool ipc = ctx->world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && L == 1 && ctx->overlap_passes;
+        const int prec = resolve_precision(ctx->cfg.precision, dk, dv);
+        ahead = (ctx->world == 1 || ipc) && persistent_pieces(ctx, prec, dk, dv, pick_q_batch(ctx, m), n_local) > 1;
+    }
+    SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true, ahead));
     SDPA_TRY(attention_impl(ctx, nullptr, Q_dev, result_dev, true, m, false, false));
     if (ctx->deferring && !ctx->call_guards.empty()) {
         const size_t L = ctx->shards.size();

@@ -133,3 +133,36 @@ def test_bf16_persistent_kernel_v8(sdpa, oracle, monkeypatch, m, n, gain):
         ctx.load_kv_host_full(K, V)
         base = ctx.attention_host(Q)
     np.testing.assert_allclose(got, base, rtol=0, atol=2e-3 if gain == 1.0 else 2e-2)
+
+
+def test_cast_ahead_queued_passes(sdpa, oracle, monkeypatch):
+    """Queued device-resident passes on the persistent kernel cast K/V/Q of pass i+1 on a side stream (small-footprint kernel,
+    second K/V set) while the fused kernel of pass i runs.  Different K/V/Q (and key counts) per pass, three rounds, then a
+    blocking pass on the same context; every result against the oracle and bit-identical to the in-stream casts
+    (SDPA_CAST_AHEAD=0)."""
+    import torch
+    m, d = 600, 128
+    cases = [oracle.make_inputs(m, n, d, d, seed=40 + k) for k, n in enumerate((16384, 20000, 16384 + 136))]
+    refs = [oracle.attention_f64_numpy(*(oracle.bf16_round(a).astype(np.float64) for a in c)) for c in cases]
+    results = {}
+    for ahead in ("1", "0"):
+        monkeypatch.setenv("SDPA_CAST_AHEAD", ahead)
+        with sdpa.Context(precision="bf16") as ctx:
+            dev = [[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (K, V, Q)] for (Q, K, V) in cases]
+            outs = [torch.zeros(m, d, dtype=torch.float64, device="cuda") for _ in cases]
+            for rep in range(3):
+                for (Kd, Vd, Qd), out in zip(dev, outs):
+                    ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], d, d, [Qd.data_ptr()], out.data_ptr(), m,
+                                              blocking=False)
+            ctx.synchronize()
+            assert ctx.last_kernel() == "bf16_umma_v8"
+            got = [o.cpu().numpy() for o in outs]
+            Kd, Vd, Qd = dev[1]
+            last = torch.zeros(m, d, dtype=torch.float64, device="cuda")
+            ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], d, d, [Qd.data_ptr()], last.data_ptr(), m)
+            got.append(last.cpu().numpy())
+        results[ahead] = got
+        for g, r in zip(got, refs + [refs[1]]):
+            np.testing.assert_allclose(g, r, rtol=0, atol=BF16_KERNEL_ATOL)
+    for a, b in zip(results["1"], results["0"]):
+        assert np.array_equal(a, b)

@@ -84,7 +84,11 @@ def _overlap_worker(rank, world, port, out_dir):
 
     m, d = 1500, 128
     cases = [o.make_inputs(m, 4000 + 300 * k, d, d, seed=90 + k) for k in range(3)]   # different K/V/Q per pass
-    for prec, atol, root_merge in (("bf16", 1e-2, "overlap"), ("f32", 1e-5, "overlap"), ("bf16", 1e-2, "instream"), ("f32", 1e-5, "instream")):
+    # the last two: enough keys per shard for the persistent kernel -> the casts of pass i+1 run on a side stream beside the
+    # fused kernel of pass i (cast-ahead), with both root forms of the exchange
+    big = [o.make_inputs(m, 32768 + 512 * k, d, d, seed=70 + k) for k in range(3)]
+    for prec, atol, root_merge, cases in (("bf16", 1e-2, "overlap", cases), ("f32", 1e-5, "overlap", cases), ("bf16", 1e-2, "instream", cases),
+                                          ("f32", 1e-5, "instream", cases), ("bf16", 1e-2, "overlap", big), ("bf16", 1e-2, "instream", big)):
         os.environ["SDPA_ROOT_MERGE"] = root_merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge="peer")
         dev, outs = [], []
