@@ -494,14 +494,18 @@ def run_ours(args) -> None:
                                               local_rank=local_rank, merge=args.merge)
         return sdpa_b200.Context(precision=prec, q_batch=args.q_batch, kv_splits=args.kv_splits, first_device=local_rank)
 
+    host_enqueue_us = [0.0]
+
     def timed(ctx, fn, steps, collect=None):
         barrier()
         if collect is not None:
             ctx.accumulated_timings(reset=True)   # stage events are queried once, after the loop
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        h0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_enqueue_us[0] = (time.perf_counter() - h0) * 1e6 / max(1, steps)   # host time to ISSUE one step (not a device time)
         ctx.synchronize()   # the library runs on its own streams: wait for them before the closing event
         e1.record()
         barrier()
@@ -548,6 +552,7 @@ def run_ours(args) -> None:
             ms_dev = timed(ctx, wl.step_device, K, collect)
             launches = sdpa_b200.launch_count() - launches0
         kernel_name = ctx.last_kernel()
+        issue_us = host_enqueue_us[0]
         # e2e: pinned host buffers through the C ABI (blocking calls, the reference's semantics)
         for _ in range(2):
             wl.step_host()
@@ -557,7 +562,7 @@ def run_ours(args) -> None:
             "name": name, "m": m, "n": wl.n, "n_local": wl.n_local, "prec": prec, "kernel": kernel_name, "steps": K, "warmup": W,
             "ms_dev": ms_dev, "ms_host": ms_host, "flops_step": wl.flops_step, "launches": int(launches),
             "value": wl.flops_step * K / (ms_dev * 1e-3) / 1e12, "e2e_value": wl.flops_step * K / (ms_host * 1e-3) / 1e12,
-            "h2d": wl.h2d_bytes(), "d2h": wl.d2h_bytes(), "stage": stage, "clocks": clocks, "parity": parity,
+            "h2d": wl.h2d_bytes(), "d2h": wl.d2h_bytes(), "stage": stage, "clocks": clocks, "parity": parity, "host_issue_us": issue_us,
             "q_batches": -(-m // (args.q_batch or 8192)),
         }
         wl.free()
@@ -659,6 +664,7 @@ def run_ours(args) -> None:
             "e2e": {"value": head["e2e_value"], "unit": "TFLOP/s", "h2d_bytes_per_step": head["h2d"], "d2h_bytes_per_step": head["d2h"],
                     "ms_per_step": ms_host / K, "q_rows_per_s": m * K / (ms_host * 1e-3)},
             "gpu_launches": head["launches"],
+            "host_issue_us_per_step": head["host_issue_us"],   # host time to enqueue one queued pass (must stay below the device step)
             "clocks": clocks,
             "roofline": roofline,
             "stage_ms_per_step": {"cast": st["cast_ms"] / calls, "fused": st["ms"] / calls, "merge": st["merge_ms"] / calls,

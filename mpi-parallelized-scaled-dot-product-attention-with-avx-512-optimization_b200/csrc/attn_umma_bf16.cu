@@ -1222,6 +1222,9 @@ sdpa_status launch_attn_umma(UmmaPlan* plan, int q_slot, int rows, int splits, P
         static bool attr8_done[64] = {};
         if (dev8 < 64 && !attr8_done[dev8]) {
             SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            // the SM's shared-memory carveout at its maximum (228 KB), not the smallest step that holds this CTA (196 KB): the
+            // rest is what the small-footprint side kernels (cast-ahead, background merge) run in beside a resident CTA
+            SDPA_CUDA_TRY(cudaFuncSetAttribute(attn_umma_kernel_v8, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             attr8_done[dev8] = true;
         }
         attn_umma_kernel_v8<<<grid8, 640, smem8, stream>>>(plan->map_khalf, plan->map_q[q_slot], plan->map_k, plan->map_v, prm);

@@ -230,14 +230,27 @@ __global__ void __launch_bounds__(kCastThreads) cvt_in_batch_kernel(CastBatch cb
 
 // The same batch as a BACKGROUND kernel (queued passes: the casts of pass i+1 run while the fused kernel of pass i owns the
 // tensor cores).  It has to fit beside a resident CTA of the persistent fused kernel (640 threads x 96 registers, ~183 KB of
-// shared memory): ONE CTA per SM of 128 threads x <= 32 registers and 32 KB of shared memory.  The bytes in flight that an
-// HBM-bound copy needs therefore live in shared memory, not in registers: thread 0 keeps kBgStages bulk copies
-// (cp.async.bulk, 8 KB of fp64 each, L2 evict-first: the source is read once and must not push the fused kernel's K/V
-// tiles out of L2) in flight; the CTA converts a landed chunk and stores it with 128-byte coalesced stores.
+// shared memory): ONE CTA per SM of 128 threads x <= 32 registers and 40 KB of shared memory.  The bytes in flight that an
+// HBM-bound copy needs therefore live in shared memory, not in registers: every warp keeps kBgStages bulk copies
+// (cp.async.bulk, 2 KB of fp64 each, L2 evict-first: the source is read once and must not push the fused kernel's K/V
+// tiles out of L2) in flight in a ring of its own -- 40 KB per SM -- converts a landed chunk and stores it with 128-byte
+// coalesced stores.  No CTA-wide barrier in the loop: beside the fused kernel the four warps are scheduled when its warps
+// leave issue slots, each on its own.
 constexpr int kBgThreads = 128;
-constexpr int kBgChunkUnits = 512;                       // 2-element units per chunk = 8 KB of fp64
-constexpr int kBgStages = 4;
-constexpr size_t kBgSmem = (size_t)kBgStages * kBgChunkUnits * 16 + 64;
+constexpr int kBgChunkUnits = 128;                       // 2-element units per chunk = 2 KB of fp64, 4 units per lane
+constexpr int kBgMaxStages = 5;                          // per WARP: every warp runs its own ring (no CTA-wide barrier in the loop)
+constexpr int kBgWarps = kBgThreads / 32;
+inline size_t bg_smem_bytes(int stages) { return (size_t)kBgWarps * stages * kBgChunkUnits * 16 + (size_t)kBgWarps * kBgMaxStages * 8; }
+// ring depth per warp (SDPA_BG_STAGES, 1..5): 5 = 40 KB of shared memory per CTA
+inline int bg_stages()
+{
+    static const int st = [] {
+        const char* e = getenv("SDPA_BG_STAGES");
+        const int v = e ? atoi(e) : kBgMaxStages;
+        return v < 1 ? 1 : (v > kBgMaxStages ? kBgMaxStages : v);
+    }();
+    return st;
+}
 
 __device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
 {
@@ -247,16 +260,27 @@ __device__ __forceinline__ void bulk_load_evict_first(void* smem_dst, const void
                  :: "r"(umma::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(umma::smem_u32(bar)), "l"(policy) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long cast_global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void stamp_kernel(unsigned long long* dst) { *dst = cast_global_ns(); }
+
 template <int MODE>
-__global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBatch cb)
+__global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBatch cb, int kBgStages)
 {
     extern __shared__ __align__(128) uint8_t bg_smem[];
-    double2* ring = reinterpret_cast<double2*>(bg_smem);
-    uint64_t* full = reinterpret_cast<uint64_t*>(bg_smem + (size_t)kBgStages * kBgChunkUnits * 16);
-    // chunks: segment after segment, every segment's last chunk may be short
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (cb.trace && threadIdx.x == 0) cb.trace[2 * blockIdx.x] = cast_global_ns();
+    double2* ring = reinterpret_cast<double2*>(bg_smem) + (size_t)warp * kBgStages * kBgChunkUnits;
+    uint64_t* full = reinterpret_cast<uint64_t*>(bg_smem + (size_t)kBgWarps * kBgStages * kBgChunkUnits * 16) + warp * kBgMaxStages;
+    // chunks: segment after segment, every segment's last chunk may be short; warp w of CTA c takes chunks c*4+w, +4*grid, ...
     const unsigned int c0 = (unsigned int)((cb.units[0] + kBgChunkUnits - 1) / kBgChunkUnits);
     const unsigned int c1 = c0 + (unsigned int)((cb.units[1] + kBgChunkUnits - 1) / kBgChunkUnits);
     const unsigned int nchunks = c1 + (unsigned int)((cb.units[2] + kBgChunkUnits - 1) / kBgChunkUnits);
+    const unsigned int first_chunk = blockIdx.x * kBgWarps + warp, stride = gridDim.x * kBgWarps;
     auto locate = [&](unsigned int chunk, int& seg, size_t& first, unsigned int& units) {
         seg = chunk < c0 ? 0 : (chunk < c1 ? 1 : 2);
         first = (size_t)(chunk - (seg == 0 ? 0u : (seg == 1 ? c0 : c1))) * kBgChunkUnits;
@@ -271,18 +295,17 @@ __global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBat
         umma::mbar_arrive_expect_tx(&full[stage], units * 16u);
         bulk_load_evict_first(ring + (size_t)stage * kBgChunkUnits, reinterpret_cast<const double2*>(cb.src[seg]) + first, units * 16u, &full[stage]);
     };
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
         for (int st = 0; st < kBgStages; ++st) umma::mbar_init(&full[st], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0)
         for (int st = 0; st < kBgStages; ++st) {
-            const unsigned int chunk = blockIdx.x + (unsigned int)st * gridDim.x;
+            const unsigned int chunk = first_chunk + (unsigned int)st * stride;
             if (chunk < nchunks) issue(chunk, st);
         }
+    }
+    __syncwarp();
     unsigned int k = 0;
-    for (unsigned int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++k) {
+    for (unsigned int chunk = first_chunk; chunk < nchunks; chunk += stride, ++k) {
         const int stage = (int)(k % kBgStages);
         int seg;
         size_t first;
@@ -292,12 +315,12 @@ __global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBat
         const double2* in = ring + (size_t)stage * kBgChunkUnits;
         void* dst = cb.dst[seg];
         const size_t lo = cb.lo_off[seg];
-        double2 v[kBgChunkUnits / kBgThreads];
+        double2 v[kBgChunkUnits / 32];
 #pragma unroll
-        for (int j = 0; j < kBgChunkUnits / kBgThreads; ++j) v[j] = in[j * kBgThreads + threadIdx.x];
+        for (int j = 0; j < kBgChunkUnits / 32; ++j) v[j] = in[j * 32 + lane];
 #pragma unroll
-        for (int j = 0; j < kBgChunkUnits / kBgThreads; ++j) {
-            const unsigned int u = j * kBgThreads + threadIdx.x;
+        for (int j = 0; j < kBgChunkUnits / 32; ++j) {
+            const unsigned int u = j * 32 + lane;
             if (u >= units) continue;
             const size_t off = first + u;
             if (MODE == 2) {
@@ -311,9 +334,13 @@ __global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBat
                 reinterpret_cast<float2*>(dst)[off] = make_float2(__double2float_rn(v[j].x), __double2float_rn(v[j].y));
             }
         }
-        __syncthreads();   // every thread has read its share of the stage
-        const unsigned int next = chunk + (unsigned int)kBgStages * gridDim.x;
-        if (threadIdx.x == 0 && next < nchunks) issue(next, stage);
+        __syncwarp();   // every lane has read its share of the stage
+        const unsigned int next = chunk + (unsigned int)kBgStages * stride;
+        if (lane == 0 && next < nchunks) issue(next, stage);
+    }
+    if (cb.trace) {
+        __syncthreads();
+        if (threadIdx.x == 0) cb.trace[2 * blockIdx.x + 1] = cast_global_ns();
     }
 }
 
@@ -329,6 +356,15 @@ inline int cast_grid(size_t work_items)
 inline bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
 
 }  // namespace
+
+static unsigned long long* g_cast_trace = nullptr;
+void set_cast_trace(unsigned long long* buf) { g_cast_trace = buf; }
+sdpa_status launch_stamp(unsigned long long* dst, cudaStream_t stream)
+{
+    stamp_kernel<<<1, 1, 0, stream>>>(dst);
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
 
 void preload_cast_kernels()
 {
@@ -440,6 +476,7 @@ sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const*
         cb.units[k] = 0;
         cb.lo_off[k] = 0;
     }
+    cb.trace = background_ctas > 0 ? g_cast_trace : nullptr;
     const bool split = prec == SDPA_PREC_BF16X3;
     for (int k = 0; k < nseg; ++k) {
         if (count[k] == 0) continue;
@@ -462,10 +499,21 @@ sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const*
         return SDPA_OK;
     }
     if (background_ctas > 0) {
-        // small-footprint form, one CTA per SM
-        if (split) cvt_in_batch_bg_kernel<2><<<background_ctas, kBgThreads, kBgSmem, stream>>>(cb);
-        else if (prec == SDPA_PREC_BF16) cvt_in_batch_bg_kernel<1><<<background_ctas, kBgThreads, kBgSmem, stream>>>(cb);
-        else cvt_in_batch_bg_kernel<0><<<background_ctas, kBgThreads, kBgSmem, stream>>>(cb);
+        // small-footprint form, one CTA per SM; same (maximum) shared-memory carveout as the fused kernel it runs beside
+        static bool carve_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !carve_done[dev]) {
+            cudaFuncSetAttribute(cvt_in_batch_bg_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(cvt_in_batch_bg_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(cvt_in_batch_bg_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve_done[dev] = true;
+        }
+        const int stages = bg_stages();
+        const size_t smem = bg_smem_bytes(stages);
+        if (split) cvt_in_batch_bg_kernel<2><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages);
+        else if (prec == SDPA_PREC_BF16) cvt_in_batch_bg_kernel<1><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages);
+        else cvt_in_batch_bg_kernel<0><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages);
         count_launch();
         SDPA_CUDA_TRY(cudaGetLastError());
         return SDPA_OK;

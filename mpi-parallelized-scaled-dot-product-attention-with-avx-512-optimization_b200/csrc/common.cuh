@@ -64,11 +64,16 @@ struct CastBatch {
     const double* src[3];
     size_t units[3];   // 2-element units per segment
     size_t lo_off[3];  // split precision: distance from the hi to the lo array, in 2-element units
+    unsigned long long* trace;   // developer aid (background form): per CTA [start, end] %globaltimer stamps, or NULL
 };
+// Developer aid: where the background cast kernel leaves its per-CTA stamps (NULL = off), and a one-thread kernel that
+// stamps %globaltimer into *dst in stream order.
+void set_cast_trace(unsigned long long* buf);
+sdpa_status launch_stamp(unsigned long long* dst, cudaStream_t stream);
 // lo_off (elements, per segment) is read for SDPA_PREC_BF16X3 only and may be NULL otherwise.
 sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const* src, const size_t* count, const size_t* lo_off,
                                 int nseg, cudaStream_t stream, int background_ctas = 0);
-// background_ctas > 0: the small-footprint form (that many CTAs of 128 threads, 32 KB of shared memory, <= 32 registers) that
+// background_ctas > 0: the small-footprint form (that many CTAs of 128 threads, 40 KB of shared memory, <= 32 registers) that
 // fits on an SM beside a resident CTA of the persistent fused kernel.
 
 // fp32 CUDA-core fused attention.  Q [rows x dk], K [n x dk], V [n x dv] fp32 row-major.
@@ -153,6 +158,13 @@ struct PeerSync {
 sdpa_status launch_merge_peers_synced(const float* const* contrib_ptrs, const float* const* tmax_ptrs,
                                       const float* const* lsum_ptrs, int shards, int rows, int dv, double* out64,
                                       const PeerSync& sync, cudaStream_t stream);
+// Root GPU, push form: merge the `world` states the shards have pushed into the root's local inbox (segment r at r * seg_floats:
+// [o cap_rows*dv | tmax cap_rows | lsum cap_rows]) once ready[r] >= epoch for every r; write fp64 rows; release `consumed[r]`
+// (every rank's own flag word) = epoch.  Small-footprint kernel (`ctas` CTAs x 128 threads, <= 32 registers): runs beside
+// the persistent fused kernel of the next queued pass.
+sdpa_status launch_merge_inbox_background(const float* inbox, size_t seg_floats, int cap_rows, int world, const unsigned int* ready,
+                                          unsigned int* const* consumed, unsigned int* block_counter, unsigned int epoch,
+                                          unsigned long long* trace, int rows, int dv, double* out64, int ctas, cudaStream_t stream);
 // Root GPU, in-stream cross-GPU merge: own partial states (pieces if wm != NULL, else part.splits) + the peers' published states.
 sdpa_status launch_merge_root_instream(Partials part, const WorkMap* wm, int max_pieces, const unsigned int* guard, unsigned int guard_epoch,
                                        const float* const* peer_c, const float* const* peer_t, const float* const* peer_l, int npeers,

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <string>
 #include <vector>
 
 namespace sdpa {
@@ -175,6 +176,7 @@ struct Shard {
     cudaEvent_t kv_guard[2] = {nullptr, nullptr}, ev_kv_read[2] = {nullptr, nullptr};
     int kv_set = 0;
     bool ahead_call = false;                 // the pass being issued casts ahead (set by load_kv, consumed by attention_impl)
+    cudaEvent_t ev_fence = nullptr;
     size_t k_lo_off = 0, v_lo_off = 0, q_lo_off = 0;   // split precision: elements from an operand's hi array to its lo array
     int n_local = 0;
     // staging for fp64 uploads of K/V (two chunks in flight)
@@ -219,7 +221,7 @@ struct Shard {
 using namespace sdpa;
 
 // Root form of the device-side exchange: in-stream (one merge kernel on the root per batch) or on the comm stream.
-static constexpr bool kRootMergeInstream = false;
+static constexpr const char* kRootMergeDefault = "overlap";
 // Deferred guard repair on contexts with several K/V shards (agreement by all-reduce at sdpa_synchronize): default.
 static constexpr bool kDeferAcrossGpus = false;
 
@@ -260,6 +262,9 @@ struct sdpa_ctx {
     // of pass i+1 (SDPA_OVERLAP_PASSES=0 turns that off).  Blocking calls always join.
     bool qshard = false;                    // SDPA_DIST_Q in effect: every shard holds ALL K/V rows, Q rows are sharded, no exchange
     bool overlap_passes = false;
+    DevBuf cast_trace;                      // SDPA_CAST_TRACE=<path> (developer aid, single-GPU contexts): per-CTA stamps of the background cast
+    std::string cast_trace_path;            // + [600..603] begin/end stamps of the fused kernels of the last two passes, dumped at destroy
+    unsigned long long trace_pass = 0;
     bool cast_ahead = true;                 // SDPA_CAST_AHEAD=0: the casts of a queued pass stay on the compute stream
     unsigned long long batch_seq = 0;       // batches issued by queued passes with sequence slots (slot = batch_seq & 1)
     bool exchange_pending = false;          // overlap mode left exchange work behind: drain before freeing / reallocating slots
@@ -281,6 +286,10 @@ struct sdpa_ctx {
         double* root_stage[2] = {nullptr, nullptr};
         bool sliced = false;            // the root merges all rows (default) / every rank merges its share of the rows
         bool instream = false;          // root form: the root merges its own pieces and the peers' states in ONE kernel of its compute stream
+        bool push = false;              // root form: every shard PUSHES its state into the root's inbox (xbuf = world segments), flags are
+                                        // pushed too (ready[r] lives on the root, consumed on every rank): nobody reads or polls over NVLink;
+                                        // the root's merge is a small-footprint kernel beside the next pass's fused kernel
+        static constexpr int kFlagReady = 768;   // [kFlagReady + slot*64 + r] "shard r's state of the batch is in the root's inbox" (root's copy)
         std::vector<void*> opened;      // IPC mappings to close
         unsigned int epoch = 0;         // global batch counter, identical on every rank
         unsigned int slot_epoch[2] = {0, 0};
@@ -480,6 +489,7 @@ static void shard_destroy(Shard& s, const NcclApi* api)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : s.marks) cudaEventDestroy(e);
     if (s.ev_begin) cudaEventDestroy(s.ev_begin);
+    if (s.ev_fence) cudaEventDestroy(s.ev_fence);
     cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out, s.s_cast};
     for (cudaStream_t st : sts)
         if (st) cudaStreamDestroy(st);
@@ -573,6 +583,14 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
     return SDPA_OK;
 }
 
+static bool pass_fence()
+{
+    static const bool on = [] {
+        const char* e = getenv("SDPA_PASS_FENCE");
+        return e && *e == '1';
+    }();
+    return on;
+}
 static int pick_q_batch(const sdpa_ctx* ctx, int m);
 // Pieces per row block when the persistent fused kernel takes the pass (dk = dv = 128 bf16, automatic splits, every shard the
 // same number of keys, enough work per SM pair), else 0.
@@ -695,8 +713,19 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
     // every rank re-allocates together (the decision depends only on arguments all ranks share)
     // root merge: [o rows*dv | tmax rows | lsum rows]; sliced merge: one inbox segment per source rank,
     // [o slice*dv | tmax slice | lsum slice] each, slice = rows of one rank's share (rounded up to a multiple of 4)
+    if (!x.flags.p) {
+        // "root" (default): the root GPU merges every row; "sliced": every rank merges its share of the rows from an inbox the
+        // others push into.  Root forms (SDPA_ROOT_MERGE): overlap = comm-stream merge reading the states over NVLink,
+        // instream = one merge on the root's compute stream, push = states pushed into the root's inbox + background merge.
+        x.sliced = ipc_sliced_requested();
+        const char* rm = getenv("SDPA_ROOT_MERGE");   // push | instream | overlap
+        const char* form = rm ? rm : kRootMergeDefault;
+        x.instream = !x.sliced && !strcmp(form, "instream");
+        x.push = !x.sliced && !strcmp(form, "push");
+    }
     const int slice_cap = ((rows_cap + ctx->world - 1) / ctx->world + 3) & ~3;
-    const size_t xbytes = std::max(((size_t)rows_cap * dv + 2 * (size_t)rows_cap),
+    const size_t state_floats = (size_t)rows_cap * dv + 2 * (size_t)rows_cap;
+    const size_t xbytes = std::max(x.push ? (size_t)ctx->world * state_floats : state_floats,
                                    (size_t)ctx->world * slice_cap * ((size_t)dv + 2)) * sizeof(float);
     x.slice_cap = slice_cap;
     for (int b = 0; b < 2; ++b) {
@@ -717,14 +746,6 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         }
         x.epoch = 0;
         x.slot_epoch[0] = x.slot_epoch[1] = 0;
-        // "root" (default): the root GPU merges every row, reading the states over NVLink; "sliced": every rank merges its
-        // share of the rows from an inbox the others push into.  Measured equal at 8 GPUs (0.354 vs 0.356 ms per c3 step) and
-        // the root form ahead at 2 (0.308 vs 0.331 ms): the exchange is bound by its flag hops, not by the root's ingress.
-        x.sliced = ipc_sliced_requested();
-        {
-            const char* rm = getenv("SDPA_ROOT_MERGE");   // instream | overlap
-            x.instream = !x.sliced && (rm ? !strcmp(rm, "instream") : kRootMergeInstream);
-        }
     }
     struct Handles { cudaIpcMemHandle_t x0, x1, fl, s0, s1; };
     Handles mine;
@@ -762,7 +783,7 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         }
         if (s.grank != 0 && r != 0 && !x.sliced) continue;   // root merge: non-root ranks only need the root's flags
         void* p = nullptr;
-        if (s.grank == 0 || x.sliced) {
+        if (s.grank == 0 || x.sliced || (x.push && r == 0)) {
             SDPA_TRY(open(all[r].x0, &p));
             x.peer_x[0][r] = p;
             SDPA_TRY(open(all[r].x1, &p));
@@ -996,7 +1017,9 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             if (single) final_dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
 
             SDPA_TRY(time_begin(s, 1, s.s_compute));
+            if (ctx->cast_trace.p) SDPA_TRY(launch_stamp(ctx->cast_trace.as<unsigned long long>() + 600 + 2 * (ctx->trace_pass & 1), s.s_compute));
             SDPA_TRY(run_fused(ctx, s, b, bs, splits, part, (single && splits == 1) ? final_dst : nullptr));
+            if (ctx->cast_trace.p) SDPA_TRY(launch_stamp(ctx->cast_trace.as<unsigned long long>() + 601 + 2 * (ctx->trace_pass++ & 1), s.s_compute));
             SDPA_TRY(time_end(s, 1, s.s_compute));
             ++fused_launches;
             ++all_launches;
@@ -1073,6 +1096,24 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                             double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
                             SDPA_TRY(launch_merge_root_instream(part, pieces ? &wm : nullptr, max_pieces, guard, guard_epoch, cp, tp, lp, world - 1, bs,
                                                                 dv, dst, sync, s.s_compute));
+                        } else if (x.push) {
+                            // one launch: wait until the root's merge has handed the slot back (consumed, pushed into THIS rank's
+                            // flag block), merge the shard's partial states straight into segment grank of the root's inbox
+                            // (posted stores over NVLink; local on the root), raise ready[grank] on the root
+                            const size_t seg = (size_t)x.cap_rows * ((size_t)dv + 2);
+                            float* ic = reinterpret_cast<float*>(x.peer_x[b][0]) + (size_t)s.grank * seg;
+                            float* it = ic + (size_t)x.cap_rows * dv;
+                            float* il = it + x.cap_rows;
+                            PublishSync pub;
+                            if (x.slot_epoch[b] != 0) {
+                                pub.wait_flag = x.flags.as<unsigned int>() + 2 + b;
+                                pub.wait_epoch = x.slot_epoch[b];
+                            }
+                            pub.flag = x.root_flags + sdpa_ctx::Ipc::kFlagReady + b * 64 + s.grank;
+                            pub.epoch = x.epoch;
+                            pub.block_counter = x.flags.as<unsigned int>() + 12 + b;
+                            pub.trace = x.trace_slot(x.epoch);
+                            SDPA_TRY(merge_local(nullptr, ic, it, il, &pub));
                         } else {
                             // one launch: wait for the root's "consumed" flag of this slot, merge the shard's partial states
                             // into the slot, publish the epoch flag
@@ -1097,6 +1138,10 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 ++all_launches;
             }
             if (use_comm || use_out || ahead) SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
+            if (ahead && pass_fence()) {   // experiment: a timing-enabled event record behind every cast-ahead batch
+                if (!s.ev_fence) SDPA_CUDA_TRY(cudaEventCreate(&s.ev_fence));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_fence, s.s_compute));
+            }
             if (ii == num_iter - 1) {
                 // who read this pass's K/V set last: the batch just issued
                 if (!ahead) s.kv_guard[s.kv_set] = nullptr;   // not a cast-ahead context / a blocking call (ends with a wait)
@@ -1151,6 +1196,19 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_TRY(time_end(s, 2, s.s_comm));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
                 if (s.grank != 0) SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+            } else if (s.grank == 0 && x.push) {
+                // background merge of the inbox on the comm stream (after the root's own state is in): all reads local
+                SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
+                unsigned int* consumed[64];
+                for (int r = 0; r < world; ++r) consumed[r] = x.peer_flags[r] + 2 + b;
+                double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+                SDPA_TRY(time_begin(s, 2, s.s_comm));
+                SDPA_TRY(launch_merge_inbox_background(x.xbuf[b].as<float>(), (size_t)x.cap_rows * ((size_t)dv + 2), x.cap_rows, world,
+                                                       x.flags.as<unsigned int>() + sdpa_ctx::Ipc::kFlagReady + b * 64, consumed,
+                                                       x.flags.as<unsigned int>() + 4 + b, x.epoch, x.trace_slot(x.epoch), bs, dv, dst,
+                                                       s.sm_count, s.s_comm));
+                SDPA_TRY(time_end(s, 2, s.s_comm));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
             } else if (s.grank == 0 && x.instream) {
                 // the merge already ran in the compute stream
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_compute));
@@ -1705,6 +1763,15 @@ sdpa_status sdpa_ctx_create(sdpa_ctx** out, const sdpa_config* cfg_in, const voi
         ctx->shards[i].grank = cfg.rank_base + i;
         st = shard_init(ctx->shards[i]);
     }
+    if (const char* tp = getenv("SDPA_CAST_TRACE"); st == SDPA_OK && tp && *tp && L == 1 && world == 1) {
+        ctx->cast_trace_path = tp;
+        cudaSetDevice(ctx->shards[0].dev);
+        st = ctx->cast_trace.reserve(1024 * sizeof(unsigned long long));
+        if (st == SDPA_OK) {
+            cudaMemset(ctx->cast_trace.p, 0, ctx->cast_trace.bytes);
+            set_cast_trace(ctx->cast_trace.as<unsigned long long>());
+        }
+    }
     // peer access among the local GPUs (for the fused exchange)
     if (st == SDPA_OK && L > 1) {
         bool all = true;
@@ -1782,6 +1849,18 @@ sdpa_status sdpa_ctx_destroy(sdpa_ctx* ctx)
         drain_exchange(ctx);
         cudaSetDevice(ctx->shards[0].dev);
         cudaDeviceSynchronize();
+        if (ctx->cast_trace.p) {   // developer aid: per-CTA stamps of the last background cast + the last two fused kernels
+            std::vector<unsigned long long> host(1024);
+            if (cudaMemcpy(host.data(), ctx->cast_trace.p, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess)
+                if (FILE* f = fopen(ctx->cast_trace_path.c_str(), "w")) {
+                    fprintf(f, "fused %llu %llu %llu %llu passes %llu\n", host[600], host[601], host[602], host[603], ctx->trace_pass);
+                    for (int c = 0; c < 300; ++c)
+                        if (host[2 * c]) fprintf(f, "cta %d %llu %llu\n", c, host[2 * c], host[2 * c + 1]);
+                    fclose(f);
+                }
+            set_cast_trace(nullptr);
+            ctx->cast_trace.release();
+        }
         if (ctx->ipc.trace.p) {   // developer aid: dump the exchange timeline of this rank
             const char* tp = getenv("SDPA_EXCHANGE_TRACE");
             const unsigned int W = sdpa_ctx::Ipc::kTraceWords;

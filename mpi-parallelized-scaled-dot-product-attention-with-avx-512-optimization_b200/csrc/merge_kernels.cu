@@ -375,6 +375,95 @@ collect_slices_kernel(double2* __restrict__ dst, const double2* __restrict__ src
     }
 }
 
+// Root GPU, push form of the exchange: every shard has written its state into segment r of the root's LOCAL inbox (posted
+// stores over NVLink) and raised ready[r] in the root's memory.  This kernel merges the `world` states of every row and writes
+// the normalised fp64 rows; the last block hands the slot back by writing `consumed` into every rank's own flag block (again
+// posted stores: nobody polls over NVLink).  It is a BACKGROUND kernel: sm_count CTAs of 128 threads and <= 32 registers, no
+// shared memory, so that it runs beside the persistent fused kernel of the next queued pass instead of between two passes.
+struct InboxArgs {
+    const float* inbox;          // segment r at r * seg floats: [o cap_rows*dv | tmax cap_rows | lsum cap_rows]
+    size_t seg;
+    int cap_rows, world;
+    const unsigned int* ready;   // ready[r], local
+    unsigned int* consumed[64];  // per rank (own block for the root)
+    unsigned int* block_counter;
+    unsigned int epoch;
+    unsigned long long* trace;
+};
+
+__global__ void __launch_bounds__(128, 16)
+merge_inbox_bg_kernel(const InboxArgs a, double* __restrict__ out64, int rows, int dv, bool vec_ok)
+{
+    const int lane = threadIdx.x & 31;
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[1] = global_ns();
+    if ((int)threadIdx.x < a.world) {
+        spin_until(a.ready + threadIdx.x, a.epoch, 4);
+        if (a.trace && blockIdx.x == 0 && threadIdx.x < 8) a.trace[4 + threadIdx.x] = global_ns();
+    }
+    __syncthreads();
+    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[2] = global_ns();
+    const float* tmax0 = a.inbox + (size_t)a.cap_rows * dv;
+    const float* lsum0 = tmax0 + a.cap_rows;
+    const bool vec = vec_ok && (dv & 3) == 0;
+    for (int row = blockIdx.x * 4 + (threadIdx.x >> 5); row < rows; row += gridDim.x * 4) {
+        const float t0 = lane < a.world ? tmax0[(size_t)lane * a.seg + row] : -CUDART_INF_F;
+        const float t1 = lane + 32 < a.world ? tmax0[(size_t)(lane + 32) * a.seg + row] : -CUDART_INF_F;
+        const float l0 = lane < a.world ? lsum0[(size_t)lane * a.seg + row] : 0.f;
+        const float l1 = lane + 32 < a.world ? lsum0[(size_t)(lane + 32) * a.seg + row] : 0.f;
+        float gmax = fmaxf(t0, t1);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, off));
+        const float w0 = (t0 == -CUDART_INF_F) ? 0.f : exp2f(t0 - gmax);
+        const float w1 = (t1 == -CUDART_INF_F) ? 0.f : exp2f(t1 - gmax);
+        float gsum = l0 * w0 + l1 * w1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, off);
+        const float inv = (gsum == 0.f) ? 0.f : 1.f / gsum;
+        const float* orow = a.inbox + (size_t)row * dv;
+        double* dst = out64 + (size_t)row * dv;
+        if (vec) {
+            for (int d0 = 0; d0 < dv; d0 += 128) {   // warp-uniform trip count: the shuffles below need every lane
+                const int d = d0 + lane * 4;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int s = 0; s < a.world; ++s) {
+                    const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
+                    if (d < dv) {
+                        const float4 v = *reinterpret_cast<const float4*>(orow + (size_t)s * a.seg + d);
+                        acc.x = fmaf(v.x, w, acc.x);
+                        acc.y = fmaf(v.y, w, acc.y);
+                        acc.z = fmaf(v.z, w, acc.z);
+                        acc.w = fmaf(v.w, w, acc.w);
+                    }
+                }
+                if (d < dv) {
+                    reinterpret_cast<double2*>(dst + d)[0] = make_double2((double)(acc.x * inv), (double)(acc.y * inv));
+                    reinterpret_cast<double2*>(dst + d)[1] = make_double2((double)(acc.z * inv), (double)(acc.w * inv));
+                }
+            }
+        } else {
+            for (int d0 = 0; d0 < dv; d0 += 32) {
+                const int d = d0 + lane;
+                float acc = 0.f;
+                for (int s = 0; s < a.world; ++s) {
+                    const float w = __shfl_sync(0xffffffffu, s < 32 ? w0 : w1, s & 31);
+                    if (d < dv) acc = fmaf(orow[(size_t)s * a.seg + d], w, acc);
+                }
+                if (d < dv) dst[d] = (double)(acc * inv);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.block_counter, 1u) == gridDim.x - 1) {
+            *a.block_counter = 0;
+            __threadfence_system();
+            for (int r = 0; r < a.world; ++r) st_release_sys(a.consumed[r], a.epoch);
+            if (a.trace) a.trace[3] = global_ns();
+        }
+    }
+}
+
 }  // namespace
 
 
@@ -385,6 +474,7 @@ void preload_merge_kernels()
     cudaFuncGetAttributes(&a, merge_pieces_kernel<false>);
     cudaFuncGetAttributes(&a, merge_states_kernel<true>);
     cudaFuncGetAttributes(&a, merge_states_kernel<false>);
+    cudaFuncGetAttributes(&a, merge_inbox_bg_kernel);
     cudaFuncGetAttributes(&a, signal_flag_kernel);
     cudaFuncGetAttributes(&a, wait_flag_kernel);
     cudaGetLastError();
@@ -577,6 +667,41 @@ sdpa_status launch_merge_root_instream(Partials part, const WorkMap* wm, int max
     merge_pieces_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(st, wm ? *wm : WorkMap{1, 1, 1}, max_pieces, rows, dv, out64, nullptr, nullptr,
                                                                          nullptr, vec_ok, wm ? guard : nullptr, guard_epoch, sa, npeers,
                                                                          wm ? 0 : part.splits);
+    count_launch();
+    SDPA_CUDA_TRY(cudaGetLastError());
+    return SDPA_OK;
+}
+
+sdpa_status launch_merge_inbox_background(const float* inbox, size_t seg_floats, int cap_rows, int world, const unsigned int* ready,
+                                          unsigned int* const* consumed, unsigned int* block_counter, unsigned int epoch,
+                                          unsigned long long* trace, int rows, int dv, double* out64, int ctas, cudaStream_t stream)
+{
+    if (world < 1 || world > 64 || !inbox || !out64 || ctas < 1) {
+        set_error("inbox merge: 1..64 shards, an inbox and a destination");
+        return SDPA_ERR_INVALID;
+    }
+    if (rows < 0) rows = 0;
+    InboxArgs a{};
+    a.inbox = inbox;
+    a.seg = seg_floats;
+    a.cap_rows = cap_rows;
+    a.world = world;
+    a.ready = ready;
+    for (int r = 0; r < world; ++r) a.consumed[r] = consumed[r];
+    a.block_counter = block_counter;
+    a.epoch = epoch;
+    a.trace = trace;
+    const bool vec_ok = al16(out64) && al16(inbox) && (seg_floats % 4 == 0) && (((size_t)cap_rows * dv) % 4 == 0);
+    {
+        static bool carve_done[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && !carve_done[dev]) {   // never makes an SM re-partition its shared memory under the fused kernel
+            cudaFuncSetAttribute(merge_inbox_bg_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve_done[dev] = true;
+        }
+    }
+    merge_inbox_bg_kernel<<<ctas, 128, 0, stream>>>(a, out64, rows, dv, vec_ok);
     count_launch();
     SDPA_CUDA_TRY(cudaGetLastError());
     return SDPA_OK;
