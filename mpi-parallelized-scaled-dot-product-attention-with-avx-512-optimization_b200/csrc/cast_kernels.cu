@@ -5,6 +5,7 @@
 // cast that feeds the tensor-core kernel.  Algorithmic traffic: 12 B/element for
 // d2f and f2d, 10 B/element for d2bf16.  Each thread moves 16-byte vectors with
 // several independent loads in flight; a scalar kernel covers unaligned pointers and tails.
+#include <cstring>
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -241,12 +242,13 @@ constexpr int kBgChunkUnits = 128;                       // 2-element units per 
 constexpr int kBgMaxStages = 5;                          // per WARP: every warp runs its own ring (no CTA-wide barrier in the loop)
 constexpr int kBgWarps = kBgThreads / 32;
 inline size_t bg_smem_bytes(int stages) { return (size_t)kBgWarps * stages * kBgChunkUnits * 16 + (size_t)kBgWarps * kBgMaxStages * 8; }
-// ring depth per warp (SDPA_BG_STAGES, 1..5): 5 = 40 KB of shared memory per CTA
+// ring depth per warp (SDPA_BG_STAGES, 1..5; default 2 = 16 KB of shared memory per CTA: measured on c3 beside the fused
+// kernel, 1 / 2 / 3 / 5 stages give the same step, 217.3 / 216.9 / 219.0 / 216.5 us -- the cast has 190 us to hide in)
 inline int bg_stages()
 {
     static const int st = [] {
         const char* e = getenv("SDPA_BG_STAGES");
-        const int v = e ? atoi(e) : kBgMaxStages;
+        const int v = e ? atoi(e) : 2;
         return v < 1 ? 1 : (v > kBgMaxStages ? kBgMaxStages : v);
     }();
     return st;
@@ -269,7 +271,7 @@ __device__ __forceinline__ unsigned long long cast_global_ns()
 __global__ void stamp_kernel(unsigned long long* dst) { *dst = cast_global_ns(); }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBatch cb, int kBgStages)
+__global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBatch cb, int kBgStages, int streaming_stores)
 {
     extern __shared__ __align__(128) uint8_t bg_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,15 +325,26 @@ __global__ void __launch_bounds__(kBgThreads, 16) cvt_in_batch_bg_kernel(CastBat
             const unsigned int u = j * 32 + lane;
             if (u >= units) continue;
             const size_t off = first + u;
+            // streaming_stores: the converted operands belong to the NEXT pass -- stored evict-first they do not push the running
+            // fused kernel's K/V tiles out of L2
             if (MODE == 2) {
                 uint32_t h, l;
                 split_bf16x2(v[j], h, l);
-                reinterpret_cast<uint32_t*>(dst)[off] = h;
-                reinterpret_cast<uint32_t*>(dst)[off + lo] = l;
+                if (streaming_stores) {
+                    __stcs(reinterpret_cast<unsigned int*>(dst) + off, h);
+                    __stcs(reinterpret_cast<unsigned int*>(dst) + off + lo, l);
+                } else {
+                    reinterpret_cast<uint32_t*>(dst)[off] = h;
+                    reinterpret_cast<uint32_t*>(dst)[off + lo] = l;
+                }
             } else if (MODE == 1) {
-                reinterpret_cast<uint32_t*>(dst)[off] = pack_bf16x2(__double2float_rn(v[j].x), __double2float_rn(v[j].y));
+                const uint32_t w = pack_bf16x2(__double2float_rn(v[j].x), __double2float_rn(v[j].y));
+                if (streaming_stores) __stcs(reinterpret_cast<unsigned int*>(dst) + off, w);
+                else reinterpret_cast<uint32_t*>(dst)[off] = w;
             } else {
-                reinterpret_cast<float2*>(dst)[off] = make_float2(__double2float_rn(v[j].x), __double2float_rn(v[j].y));
+                const float2 w = make_float2(__double2float_rn(v[j].x), __double2float_rn(v[j].y));
+                if (streaming_stores) __stcs(reinterpret_cast<float2*>(dst) + off, w);
+                else reinterpret_cast<float2*>(dst)[off] = w;
             }
         }
         __syncwarp();   // every lane has read its share of the stage
@@ -511,9 +524,13 @@ sdpa_status launch_cvt_in_batch(int prec, void* const* dst, const double* const*
         }
         const int stages = bg_stages();
         const size_t smem = bg_smem_bytes(stages);
-        if (split) cvt_in_batch_bg_kernel<2><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages);
-        else if (prec == SDPA_PREC_BF16) cvt_in_batch_bg_kernel<1><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages);
-        else cvt_in_batch_bg_kernel<0><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages);
+        static const int cs = [] {
+            const char* e = getenv("SDPA_BG_STORE");   // cs (evict-first stores) | default
+            return (e && !strcmp(e, "cs")) ? 1 : 0;
+        }();
+        if (split) cvt_in_batch_bg_kernel<2><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages, cs);
+        else if (prec == SDPA_PREC_BF16) cvt_in_batch_bg_kernel<1><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages, cs);
+        else cvt_in_batch_bg_kernel<0><<<background_ctas, kBgThreads, smem, stream>>>(cb, stages, cs);
         count_launch();
         SDPA_CUDA_TRY(cudaGetLastError());
         return SDPA_OK;

@@ -449,7 +449,8 @@ static sdpa_status shard_init(Shard& s)
         SDPA_CUDA_TRY(mk(&s.ev_stage_free[b]));
         SDPA_CUDA_TRY(mk(&s.ev_q_ready[b]));
         SDPA_CUDA_TRY(mk(&s.ev_q_free[b]));
-        SDPA_CUDA_TRY(mk(&s.ev_compute_done[b]));
+        if (getenv("SDPA_PASS_FENCE") && atoi(getenv("SDPA_PASS_FENCE")) == 2) SDPA_CUDA_TRY(cudaEventCreate(&s.ev_compute_done[b]));
+        else SDPA_CUDA_TRY(mk(&s.ev_compute_done[b]));
         SDPA_CUDA_TRY(mk(&s.ev_slot_free[b]));
         SDPA_CUDA_TRY(mk(&s.ev_comm_done[b]));
     }
@@ -583,13 +584,18 @@ static sdpa_status load_kv(sdpa_ctx* ctx, const double* const* K_shards, const d
     return SDPA_OK;
 }
 
-static bool pass_fence()
+// Cast-ahead needs the end of a pass to be visible to the side stream AT ONCE: behind an event without a timestamp the cast of
+// pass i+2 was seen to start only when the fused kernel of pass i+1 had finished (239 us per c3 step instead of 216;
+// profiles/r02/visit17_*).  A timing-enabled event record at the end of the pass (what the stage marks do on a marked pass)
+// restores the overlap.  SDPA_PASS_FENCE=0: off; 1 (default): one extra timing event per cast-ahead batch; 2: the gate event
+// itself carries the timestamp.
+static int pass_fence()
 {
-    static const bool on = [] {
+    static const int mode = [] {
         const char* e = getenv("SDPA_PASS_FENCE");
-        return e && *e == '1';
+        return e ? atoi(e) : 1;
     }();
-    return on;
+    return mode;
 }
 static int pick_q_batch(const sdpa_ctx* ctx, int m);
 // Pieces per row block when the persistent fused kernel takes the pass (dk = dv = 128 bf16, automatic splits, every shard the
@@ -1138,7 +1144,7 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 ++all_launches;
             }
             if (use_comm || use_out || ahead) SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
-            if (ahead && pass_fence()) {   // experiment: a timing-enabled event record behind every cast-ahead batch
+            if (ahead && pass_fence() == 1) {
                 if (!s.ev_fence) SDPA_CUDA_TRY(cudaEventCreate(&s.ev_fence));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_fence, s.s_compute));
             }

@@ -17,10 +17,10 @@ run() { local name=$1 g=$2; shift 2
   echo "bench $name rc=$?" >> $S
 }
 for form in push instream overlap; do
-  for a in 1 0; do
-    run g${G}_${form}_ahead$a $G SDPA_ROOT_MERGE=$form SDPA_CAST_AHEAD=$a SDPA_EXCHANGE_TRACE=$OUT/xtrace_g${G}_${form}_ahead$a -- --steps 30 --warmup 5 --extra none
-  done
+  run g${G}_${form}_ahead1 $G SDPA_ROOT_MERGE=$form SDPA_CAST_AHEAD=1 SDPA_EXCHANGE_TRACE=$OUT/xtrace_g${G}_${form}_ahead1 -- --steps 30 --warmup 5 --extra none
 done
+run g${G}_push_ahead0 $G SDPA_ROOT_MERGE=push SDPA_CAST_AHEAD=0 SDPA_EXCHANGE_TRACE=$OUT/xtrace_g${G}_push_ahead0 -- --steps 30 --warmup 5 --extra none
+run g${G}_push_ahead1_k100 $G SDPA_ROOT_MERGE=push SDPA_CAST_AHEAD=1 -- --steps 100 --warmup 5 --extra none --stage-timing-every 10
 cat $S
 for t in push_ahead1 instream_ahead1 overlap_ahead1 push_ahead0; do echo "== $t"; python tools/exchange_digest.py $OUT/xtrace_g${G}_$t; done
 python - <<'PY'
