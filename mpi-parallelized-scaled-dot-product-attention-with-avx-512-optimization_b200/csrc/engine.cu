@@ -289,6 +289,7 @@ struct sdpa_ctx {
         bool push = false;              // root form: every shard PUSHES its state into the root's inbox (xbuf = world segments), flags are
                                         // pushed too (ready[r] lives on the root, consumed on every rank): nobody reads or polls over NVLink;
                                         // the root's merge is a small-footprint kernel beside the next pass's fused kernel
+        bool push_sync = false;         // push form whose final merge runs on the root's COMPUTE stream (full-size kernel, local reads) instead of in the background
         static constexpr int kFlagReady = 768;   // [kFlagReady + slot*64 + r] "shard r's state of the batch is in the root's inbox" (root's copy)
         std::vector<void*> opened;      // IPC mappings to close
         unsigned int epoch = 0;         // global batch counter, identical on every rank
@@ -727,7 +728,8 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         const char* rm = getenv("SDPA_ROOT_MERGE");   // push | instream | overlap
         const char* form = rm ? rm : kRootMergeDefault;
         x.instream = !x.sliced && !strcmp(form, "instream");
-        x.push = !x.sliced && !strcmp(form, "push");
+        x.push = !x.sliced && (!strcmp(form, "push") || !strcmp(form, "pushsync"));
+        x.push_sync = x.push && !strcmp(form, "pushsync");
     }
     const int slice_cap = ((rows_cap + ctx->world - 1) / ctx->world + 3) & ~3;
     const size_t state_floats = (size_t)rows_cap * dv + 2 * (size_t)rows_cap;
@@ -1111,8 +1113,10 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                             float* it = ic + (size_t)x.cap_rows * dv;
                             float* il = it + x.cap_rows;
                             PublishSync pub;
-                            if (x.slot_epoch[b] != 0) {
-                                pub.wait_flag = x.flags.as<unsigned int>() + 2 + b;
+                            if (x.slot_epoch[b] != 0 && !(x.push_sync && s.grank == 0)) {
+                                // background form: `consumed` is pushed into every rank's own flag block; in-stream form: the root's
+                                // final merge releases its own copy only (its own publish is ordered behind it by the stream)
+                                pub.wait_flag = (x.push_sync ? x.root_flags : x.flags.as<unsigned int>()) + 2 + b;
                                 pub.wait_epoch = x.slot_epoch[b];
                             }
                             pub.flag = x.root_flags + sdpa_ctx::Ipc::kFlagReady + b * 64 + s.grank;
@@ -1202,6 +1206,30 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_TRY(time_end(s, 2, s.s_comm));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_comm));
                 if (s.grank != 0) SDPA_CUDA_TRY(cudaEventRecord(s.ev_slot_free[b], s.s_comm));
+            } else if (s.grank == 0 && x.push_sync) {
+                // final merge of the inbox right behind the root's own publish, on the compute stream: every read and every flag
+                // poll is local; what it waits for is the other shards' pushes (posted NVLink stores issued when THEIR fused kernels ended)
+                const float* cp[64];
+                const float* tp[64];
+                const float* lp[64];
+                PeerSync sync;
+                const size_t seg = (size_t)x.cap_rows * ((size_t)dv + 2);
+                for (int r = 0; r < world; ++r) {
+                    const float* base = x.xbuf[b].as<float>() + (size_t)r * seg;
+                    cp[r] = base;
+                    tp[r] = base + (size_t)x.cap_rows * dv;
+                    lp[r] = tp[r] + x.cap_rows;
+                    sync.ready[r] = x.flags.as<unsigned int>() + sdpa_ctx::Ipc::kFlagReady + b * 64 + r;
+                }
+                sync.consumed = x.flags.as<unsigned int>() + 2 + b;
+                sync.block_counter = x.flags.as<unsigned int>() + 4 + b;
+                sync.epoch = x.epoch;
+                sync.trace = x.trace_slot(x.epoch);
+                double* dst = result_on_device ? result + (size_t)row0 * dv : s.out64[b].as<double>();
+                SDPA_TRY(time_begin(s, 2, s.s_compute));
+                SDPA_TRY(launch_merge_peers_synced(cp, tp, lp, world, bs, dv, dst, sync, s.s_compute));
+                SDPA_TRY(time_end(s, 2, s.s_compute));
+                SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_compute));
             } else if (s.grank == 0 && x.push) {
                 // background merge of the inbox on the comm stream (after the root's own state is in): all reads local
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));

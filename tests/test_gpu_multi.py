@@ -89,7 +89,9 @@ def _overlap_worker(rank, world, port, out_dir):
     big = [o.make_inputs(m, 40960 + 512 * k, d, d, seed=70 + k) for k in range(3)]
     for prec, atol, root_merge, cases in (("bf16", 1e-2, "overlap", cases), ("f32", 1e-5, "overlap", cases), ("bf16", 1e-2, "instream", cases),
                                           ("f32", 1e-5, "instream", cases), ("bf16", 1e-2, "push", cases), ("f32", 1e-5, "push", cases),
-                                          ("bf16", 1e-2, "overlap", big), ("bf16", 1e-2, "instream", big), ("bf16", 1e-2, "push", big)):
+                                          ("bf16", 1e-2, "pushsync", cases), ("f32", 1e-5, "pushsync", cases),
+                                          ("bf16", 1e-2, "overlap", big), ("bf16", 1e-2, "instream", big), ("bf16", 1e-2, "push", big),
+                                          ("bf16", 1e-2, "pushsync", big)):
         os.environ["SDPA_ROOT_MERGE"] = root_merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge="peer")
         dev, outs = [], []
@@ -130,13 +132,15 @@ def _rank_worker(rank, world, port, out_dir, id_file):
     for prec, atol, merge in (("f32", 1e-5, "nccl2"), ("bf16", 1e-2, "nccl3"), ("bf16", 1e-2, "peer"), ("f32", 1e-5, "peer"),
                               ("bf16", 1e-2, "peer-sliced"), ("f32", 1e-5, "peer-sliced"), ("bf16x3", 1e-5, "peer"), ("auto", 1e-5, "nccl2"),
                               ("bf16", 1e-2, "peer-instream"), ("f32", 1e-5, "peer-instream"), ("bf16x3", 1e-5, "peer-instream"),
-                              ("bf16", 1e-2, "peer-push"), ("f32", 1e-5, "peer-push"), ("bf16x3", 1e-5, "peer-push")):
+                              ("bf16", 1e-2, "peer-push"), ("f32", 1e-5, "peer-push"), ("bf16x3", 1e-5, "peer-push"),
+                              ("bf16", 1e-2, "peer-pushsync"), ("f32", 1e-5, "peer-pushsync")):
         # (1) pre-sharded inputs, one context per rank (bench.py's model); merge="peer" = CUDA-IPC device-side exchange
         # (the root GPU merges all rows; "peer-sliced" = every rank merges its share of the rows from a pushed inbox)
         # "peer-instream" = the root merges its own partial states and the other shards' states in one kernel of its compute stream
         os.environ["SDPA_IPC_MERGE"] = "sliced" if merge == "peer-sliced" else "root"
         # "peer-push" = every shard pushes its state into the root's inbox, the root merges it with a small background kernel
-        os.environ["SDPA_ROOT_MERGE"] = {"peer-instream": "instream", "peer-push": "push"}.get(merge, "overlap")
+        # "peer-pushsync" = the same pushes, final merge of the inbox on the root's compute stream
+        os.environ["SDPA_ROOT_MERGE"] = {"peer-instream": "instream", "peer-push": "push", "peer-pushsync": "pushsync"}.get(merge, "overlap")
         merge = "peer" if merge.startswith("peer-") else merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge=merge)
         ctx.load_kv_host([K[first:first + count]], [V[first:first + count]])

@@ -16,18 +16,31 @@ run() { local name=$1 g=$2; shift 2
       bench.py --gpus $g "$@" > $OUT/v15_$name.json 2> $OUT/v15_$name.err
   echo "bench $name rc=$?" >> $S
 }
+for form in ${FORMS:-pushsync instream}; do
+  run g${G}_${form}_ahead1 $G SDPA_ROOT_MERGE=$form SDPA_CAST_AHEAD=1 SDPA_EXCHANGE_TRACE=$OUT/xtrace_g${G}_${form}_ahead1 -- --steps 30 --warmup 5 --extra none
+  run g${G}_${form}_ahead1_b $G SDPA_ROOT_MERGE=$form SDPA_CAST_AHEAD=1 -- --steps 30 --warmup 5 --extra ${EXTRA:-none}
+done
+cat $S; tail -40 $OUT/v15_multi.log; exit 1; fi
+fi
+run() { local name=$1 g=$2; shift 2
+  local envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+  env "${envs[@]}" NCCL_DEBUG=WARN timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $g "$@" > $OUT/v15_$name.json 2> $OUT/v15_$name.err
+  echo "bench $name rc=$?" >> $S
+}
 for form in push instream overlap; do
   run g${G}_${form}_ahead1 $G SDPA_ROOT_MERGE=$form SDPA_CAST_AHEAD=1 SDPA_EXCHANGE_TRACE=$OUT/xtrace_g${G}_${form}_ahead1 -- --steps 30 --warmup 5 --extra none
 done
 run g${G}_push_ahead0 $G SDPA_ROOT_MERGE=push SDPA_CAST_AHEAD=0 SDPA_EXCHANGE_TRACE=$OUT/xtrace_g${G}_push_ahead0 -- --steps 30 --warmup 5 --extra none
 run g${G}_push_ahead1_k100 $G SDPA_ROOT_MERGE=push SDPA_CAST_AHEAD=1 -- --steps 100 --warmup 5 --extra none --stage-timing-every 10
 cat $S
-for t in push_ahead1 instream_ahead1 overlap_ahead1 push_ahead0; do echo "== $t"; python tools/exchange_digest.py $OUT/xtrace_g${G}_$t; done
+for form in ${FORMS:-pushsync instream}; do echo "== $form"; python tools/exchange_digest.py $OUT/xtrace_g${G}_${form}_ahead1; done
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob("gpurun_out/v15_g*.json")):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
+        for k,v in d.get("configs",{}).items(): print("    ", k, "value", round(v["value"],1), "ms", round(v["ms_per_step"],4), "e2e", round(v["e2e"]["value"],1), v["stage_ms_per_step"], "parity", v["parity_check"]["ok"], v["parity_check"]["max_abs_err"], "batches", v["q_batches_per_step"])
         print(f.split("/")[-1], "value", round(d["value"],1), "ms", round(d["ms_per_step"],4), {k:round(v,4) for k,v in d["stage_ms_per_step"].items()}, d["impl_detail"]["kernel"], "parity", d["parity_check"]["ok"], d["parity_check"]["max_abs_err"], d["clocks"].get("per_rank_sm_mhz"))
     except Exception as e:
         print(f, "unreadable", e); print(open(f.replace(".json",".err")).read()[-2500:])
