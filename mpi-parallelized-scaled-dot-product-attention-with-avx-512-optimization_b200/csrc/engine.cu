@@ -221,7 +221,7 @@ struct Shard {
 using namespace sdpa;
 
 // Root form of the device-side exchange: in-stream (one merge kernel on the root per batch) or on the comm stream.
-static constexpr const char* kRootMergeDefault = "overlap";
+static constexpr const char* kRootMergeDefault = "instream";
 // Deferred guard repair on contexts with several K/V shards (agreement by all-reduce at sdpa_synchronize): default.
 static constexpr bool kDeferAcrossGpus = false;
 
@@ -1230,6 +1230,14 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
                 SDPA_TRY(launch_merge_peers_synced(cp, tp, lp, world, bs, dv, dst, sync, s.s_compute));
                 SDPA_TRY(time_end(s, 2, s.s_compute));
                 SDPA_CUDA_TRY(cudaEventRecord(s.ev_comm_done[b], s.s_compute));
+                if (ahead) {
+                    // The side stream's gate moves behind this merge: a background cast released while the merge still runs is
+                    // placed on whatever SMs have room -- several of its CTAs on one SM, which then cannot take a CTA of the next
+                    // fused kernel (measured: that kernel ran in two waves, 336 us instead of 190).  Released together with the
+                    // fused kernel on an empty GPU its CTAs land one per SM.
+                    SDPA_CUDA_TRY(cudaEventRecord(s.ev_compute_done[b], s.s_compute));
+                    if (pass_fence() == 1 && s.ev_fence) SDPA_CUDA_TRY(cudaEventRecord(s.ev_fence, s.s_compute));
+                }
             } else if (s.grank == 0 && x.push) {
                 // background merge of the inbox on the comm stream (after the root's own state is in): all reads local
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_comm, s.ev_compute_done[b], 0));
@@ -2015,7 +2023,10 @@ sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shard
         const int L = (int)ctx->shards.size();
         const bool ipc = ctx->world > 1 && ctx->cfg.merge == SDPA_MERGE_PEER && L == 1 && ctx->overlap_passes;
         const int prec = resolve_precision(ctx->cfg.precision, dk, dv);
-        ahead = (ctx->world == 1 || ipc) && persistent_pieces(ctx, prec, dk, dv, pick_q_batch(ctx, m), n_local) > 1;
+        // single-batch passes only: between two batches of one pass the side kernel would be released while other kernels
+        // still run, and its CTAs pile up on the SMs that happen to have room (see the gate of the pushsync root form)
+        const int B = pick_q_batch(ctx, m);
+        ahead = (ctx->world == 1 || ipc) && m <= B && persistent_pieces(ctx, prec, dk, dv, B, n_local) > 1;
     }
     SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true, ahead));
     SDPA_TRY(attention_impl(ctx, nullptr, Q_dev, result_dev, true, m, false, false));

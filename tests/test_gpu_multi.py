@@ -93,7 +93,8 @@ def _overlap_worker(rank, world, port, out_dir):
                                           ("bf16", 1e-2, "overlap", big), ("bf16", 1e-2, "instream", big), ("bf16", 1e-2, "push", big),
                                           ("bf16", 1e-2, "pushsync", big)):
         os.environ["SDPA_ROOT_MERGE"] = root_merge
-        ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge="peer")
+        # big cases: one Q batch per pass (cast-ahead takes single-batch passes only); the others ping-pong three batches
+        ctx = parallel.bootstrap_context(precision=prec, q_batch=2048 if cases is big else 512, local_rank=rank, merge="peer")
         dev, outs = [], []
         for Q, K, V in cases:
             first, count = parallel.shard_rows(K.shape[0], world, rank)
