@@ -681,7 +681,14 @@ def run_ours(args) -> None:
             "config": shared_config(args.config, world, m, n, n_local),
             "impl_detail": {
                 "precision": head["prec"], "kernel": kernel_name,
-                "merge": "none" if world == 1 else {"peer": "device-side exchange: root merge kernel reads shard states over NVLink (CUDA IPC) behind epoch flags",
+                "merge": "none" if world == 1 else {"peer": "device-side exchange (CUDA IPC, epoch flags): %s" % {
+                                                        "instream": "ONE merge kernel on the root's compute stream takes its own pieces and the other shards' states (read over NVLink)",
+                                                        "overlap": "root merge kernel on the comm stream reads every shard's state over NVLink",
+                                                        "push": "shards push their states into the root's inbox, background merge kernel on the root",
+                                                        "pushsync": "shards push their states into the root's inbox, final merge on the root's compute stream",
+                                                                                                            "auto": "single-batch passes: shards push their states into the root's inbox, final merge on the root's compute "
+                                                                "stream; passes of several Q batches: root merge on the comm stream reads the states over NVLink",
+                                                    }.get(os.environ.get("SDPA_ROOT_MERGE", "auto"), "root merge"),
                                                     "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
                                                     "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],
                 "submission": "K passes queued back to back (sdpa_enqueue_device_full), one wait after the last; e2e uses the blocking host call",

@@ -221,7 +221,8 @@ struct Shard {
 using namespace sdpa;
 
 // Root form of the device-side exchange: in-stream (one merge kernel on the root per batch) or on the comm stream.
-static constexpr const char* kRootMergeDefault = "instream";
+// "auto": pushsync for single-batch passes, overlap (comm-stream merge, measured on c4 at 4 GPUs) for passes of several Q batches.
+static constexpr const char* kRootMergeDefault = "auto";
 // Deferred guard repair on contexts with several K/V shards (agreement by all-reduce at sdpa_synchronize): default.
 static constexpr bool kDeferAcrossGpus = false;
 
@@ -290,6 +291,8 @@ struct sdpa_ctx {
                                         // pushed too (ready[r] lives on the root, consumed on every rank): nobody reads or polls over NVLink;
                                         // the root's merge is a small-footprint kernel beside the next pass's fused kernel
         bool push_sync = false;         // push form whose final merge runs on the root's COMPUTE stream (full-size kernel, local reads) instead of in the background
+        bool auto_form = false;         // default: pushsync for single-batch passes, overlap for passes of several Q batches (chosen per call)
+        bool inbox = false;             // the slots are sized (and mapped) as inboxes: any root form may be chosen
         static constexpr int kFlagReady = 768;   // [kFlagReady + slot*64 + r] "shard r's state of the batch is in the root's inbox" (root's copy)
         std::vector<void*> opened;      // IPC mappings to close
         unsigned int epoch = 0;         // global batch counter, identical on every rank
@@ -730,10 +733,12 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         x.instream = !x.sliced && !strcmp(form, "instream");
         x.push = !x.sliced && (!strcmp(form, "push") || !strcmp(form, "pushsync"));
         x.push_sync = x.push && !strcmp(form, "pushsync");
+        x.auto_form = !x.sliced && !strcmp(form, "auto");
+        x.inbox = x.push || x.auto_form;
     }
     const int slice_cap = ((rows_cap + ctx->world - 1) / ctx->world + 3) & ~3;
     const size_t state_floats = (size_t)rows_cap * dv + 2 * (size_t)rows_cap;
-    const size_t xbytes = std::max(x.push ? (size_t)ctx->world * state_floats : state_floats,
+    const size_t xbytes = std::max(x.inbox ? (size_t)ctx->world * state_floats : state_floats,
                                    (size_t)ctx->world * slice_cap * ((size_t)dv + 2)) * sizeof(float);
     x.slice_cap = slice_cap;
     for (int b = 0; b < 2; ++b) {
@@ -791,7 +796,7 @@ static sdpa_status ipc_setup(sdpa_ctx* ctx, int rows_cap, int dv)
         }
         if (s.grank != 0 && r != 0 && !x.sliced) continue;   // root merge: non-root ranks only need the root's flags
         void* p = nullptr;
-        if (s.grank == 0 || x.sliced || (x.push && r == 0)) {
+        if (s.grank == 0 || x.sliced || (x.inbox && r == 0)) {
             SDPA_TRY(open(all[r].x0, &p));
             x.peer_x[0][r] = p;
             SDPA_TRY(open(all[r].x1, &p));
@@ -948,7 +953,10 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
         }
     }
 
-    if (use_ipc) SDPA_TRY(ipc_setup(ctx, std::max(B, 8192), dv));
+    if (use_ipc) {
+        SDPA_TRY(ipc_setup(ctx, std::max(B, 8192), dv));
+        if (ctx->ipc.auto_form) ctx->ipc.push = ctx->ipc.push_sync = (num_iter == 1);   // the forms share slots, epochs and the "consumed" flag
+    }
 
     int fused_launches = 0, all_launches = 0;
     const unsigned long long launches_before = launch_count();

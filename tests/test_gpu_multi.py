@@ -91,7 +91,7 @@ def _overlap_worker(rank, world, port, out_dir):
                                           ("f32", 1e-5, "instream", cases), ("bf16", 1e-2, "push", cases), ("f32", 1e-5, "push", cases),
                                           ("bf16", 1e-2, "pushsync", cases), ("f32", 1e-5, "pushsync", cases),
                                           ("bf16", 1e-2, "overlap", big), ("bf16", 1e-2, "instream", big), ("bf16", 1e-2, "push", big),
-                                          ("bf16", 1e-2, "pushsync", big)):
+                                          ("bf16", 1e-2, "pushsync", big), ("bf16", 1e-2, "auto", cases), ("bf16", 1e-2, "auto", big)):
         os.environ["SDPA_ROOT_MERGE"] = root_merge
         # big cases: one Q batch per pass (cast-ahead takes single-batch passes only); the others ping-pong three batches
         ctx = parallel.bootstrap_context(precision=prec, q_batch=2048 if cases is big else 512, local_rank=rank, merge="peer")
@@ -134,14 +134,14 @@ def _rank_worker(rank, world, port, out_dir, id_file):
                               ("bf16", 1e-2, "peer-sliced"), ("f32", 1e-5, "peer-sliced"), ("bf16x3", 1e-5, "peer"), ("auto", 1e-5, "nccl2"),
                               ("bf16", 1e-2, "peer-instream"), ("f32", 1e-5, "peer-instream"), ("bf16x3", 1e-5, "peer-instream"),
                               ("bf16", 1e-2, "peer-push"), ("f32", 1e-5, "peer-push"), ("bf16x3", 1e-5, "peer-push"),
-                              ("bf16", 1e-2, "peer-pushsync"), ("f32", 1e-5, "peer-pushsync")):
+                              ("bf16", 1e-2, "peer-pushsync"), ("f32", 1e-5, "peer-pushsync"), ("bf16", 1e-2, "peer-overlap"), ("f32", 1e-5, "peer-overlap")):
         # (1) pre-sharded inputs, one context per rank (bench.py's model); merge="peer" = CUDA-IPC device-side exchange
         # (the root GPU merges all rows; "peer-sliced" = every rank merges its share of the rows from a pushed inbox)
         # "peer-instream" = the root merges its own partial states and the other shards' states in one kernel of its compute stream
         os.environ["SDPA_IPC_MERGE"] = "sliced" if merge == "peer-sliced" else "root"
         # "peer-push" = every shard pushes its state into the root's inbox, the root merges it with a small background kernel
         # "peer-pushsync" = the same pushes, final merge of the inbox on the root's compute stream
-        os.environ["SDPA_ROOT_MERGE"] = {"peer-instream": "instream", "peer-push": "push", "peer-pushsync": "pushsync"}.get(merge, "overlap")
+        os.environ["SDPA_ROOT_MERGE"] = {"peer-instream": "instream", "peer-push": "push", "peer-pushsync": "pushsync", "peer": "auto"}.get(merge, "overlap")
         merge = "peer" if merge.startswith("peer-") else merge
         ctx = parallel.bootstrap_context(precision=prec, q_batch=512, local_rank=rank, merge=merge)
         ctx.load_kv_host([K[first:first + count]], [V[first:first + count]])
@@ -151,6 +151,15 @@ def _rank_worker(rank, world, port, out_dir, id_file):
             np.testing.assert_allclose(got, ref, rtol=0, atol=atol)
         else:
             assert got is None
+        # one-batch calls between the three-batch ones: the default root form switches per call (inbox + in-stream final merge
+        # for single-batch passes, comm-stream merge otherwise) on the same slots, epochs and flags
+        for rows in (400, 512):
+            part = ctx.attention_host(Q[:rows])
+            if rank == 0:
+                np.testing.assert_allclose(part, ref[:rows], rtol=0, atol=atol)
+        again = ctx.attention_host(Q)
+        if rank == 0:
+            np.testing.assert_allclose(again, ref, rtol=0, atol=atol)
         # (1b) device-resident, queued passes (bench.py's timed loop): five passes back to back, one wait
         Kd, Vd, Qd = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (K[first:first + count], V[first:first + count], Q))
         out = torch.zeros(m, d, dtype=torch.float64, device="cuda") if rank == 0 else None
