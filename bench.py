@@ -686,8 +686,9 @@ def run_ours(args) -> None:
                                                         "overlap": "root merge kernel on the comm stream reads every shard's state over NVLink",
                                                         "push": "shards push their states into the root's inbox, background merge kernel on the root",
                                                         "pushsync": "shards push their states into the root's inbox, final merge on the root's compute stream",
-                                                                                                            "auto": "single-batch passes: shards push their states into the root's inbox, final merge on the root's compute "
-                                                                "stream; passes of several Q batches: root merge on the comm stream reads the states over NVLink",
+                                                                                                            "auto": "single-batch passes: 2 GPUs = one merge kernel on the root's compute stream (own pieces + the other "
+                                                                "shard's state over NVLink), more GPUs = shards push their states into the root's inbox, final merge on the "
+                                                                "root's compute stream; passes of several Q batches: root merge on the comm stream reads the states over NVLink",
                                                     }.get(os.environ.get("SDPA_ROOT_MERGE", "auto"), "root merge"),
                                                     "nccl2": "nccl allreduce(MAX) + reduce(SUM over [contrib|lsum])",
                                                     "nccl3": "nccl allreduce(MAX), allreduce(SUM), reduce(SUM)"}[args.merge],

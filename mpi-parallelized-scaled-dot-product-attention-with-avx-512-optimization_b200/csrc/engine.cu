@@ -221,7 +221,8 @@ struct Shard {
 using namespace sdpa;
 
 // Root form of the device-side exchange: in-stream (one merge kernel on the root per batch) or on the comm stream.
-// "auto": pushsync for single-batch passes, overlap (comm-stream merge, measured on c4 at 4 GPUs) for passes of several Q batches.
+// "auto": single-batch passes take instream at two GPUs and pushsync beyond; passes of several Q batches take overlap (the
+// comm-stream merge, measured on c4 at 4 GPUs).
 static constexpr const char* kRootMergeDefault = "auto";
 // Deferred guard repair on contexts with several K/V shards (agreement by all-reduce at sdpa_synchronize): default.
 static constexpr bool kDeferAcrossGpus = false;
@@ -955,7 +956,14 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
 
     if (use_ipc) {
         SDPA_TRY(ipc_setup(ctx, std::max(B, 8192), dv));
-        if (ctx->ipc.auto_form) ctx->ipc.push = ctx->ipc.push_sync = (num_iter == 1);   // the forms share slots, epochs and the "consumed" flag
+        if (ctx->ipc.auto_form) {
+            // The forms share slots, epochs and the "consumed" flag, and the other shards cannot tell `instream` from `overlap`.
+            // Single-batch passes: two GPUs -> instream (257 us per c3 step against 269 for pushsync), more -> pushsync (265 us at
+            // four GPUs against 312); passes of several Q batches -> overlap.
+            const bool single_batch = num_iter == 1;
+            ctx->ipc.instream = single_batch && world == 2;
+            ctx->ipc.push = ctx->ipc.push_sync = single_batch && world > 2;
+        }
     }
 
     int fused_launches = 0, all_launches = 0;
