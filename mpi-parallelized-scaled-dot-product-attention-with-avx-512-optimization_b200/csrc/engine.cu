@@ -177,6 +177,11 @@ struct Shard {
     int kv_set = 0;
     bool ahead_call = false;                 // the pass being issued casts ahead (set by load_kv, consumed by attention_impl)
     cudaEvent_t ev_fence = nullptr;
+    // Queued passes that do NOT cast ahead (several Q batches, another shape) keep their own slot order and record no per-slot
+    // events: the end of each one is recorded here, and every later side-stream cast waits for it as well (a completed event
+    // costs nothing), so that a cast never overwrites a K/V set or Q slot such a pass still reads.
+    cudaEvent_t ev_plain_end = nullptr;
+    bool ahead_ever = false, plain_end_recorded = false;
     size_t k_lo_off = 0, v_lo_off = 0, q_lo_off = 0;   // split precision: elements from an operand's hi array to its lo array
     int n_local = 0;
     // staging for fp64 uploads of K/V (two chunks in flight)
@@ -496,6 +501,7 @@ static void shard_destroy(Shard& s, const NcclApi* api)
     for (cudaEvent_t e : s.marks) cudaEventDestroy(e);
     if (s.ev_begin) cudaEventDestroy(s.ev_begin);
     if (s.ev_fence) cudaEventDestroy(s.ev_fence);
+    if (s.ev_plain_end) cudaEventDestroy(s.ev_plain_end);
     cudaStream_t sts[] = {s.s_in, s.s_compute, s.s_comm, s.s_out, s.s_cast};
     for (cudaStream_t st : sts)
         if (st) cudaStreamDestroy(st);
@@ -1006,6 +1012,8 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
             if (cast_aside) {
                 if (s.kv_guard[s.kv_set]) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_cast, s.kv_guard[s.kv_set], 0));
                 SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_cast, s.ev_compute_done[b], 0));
+                if (s.plain_end_recorded) SDPA_CUDA_TRY(cudaStreamWaitEvent(s.s_cast, s.ev_plain_end, 0));
+                s.ahead_ever = true;
             }
             SDPA_TRY(time_begin(s, 0, cst));
             if (s.npend > 0) {
@@ -1457,6 +1465,12 @@ static sdpa_status attention_impl(sdpa_ctx* ctx, const double* Q_host, const dou
     for (Shard& s : ctx->shards) {
         s.last_call_queued = !blocking;
         s.ahead_call = false;
+        if (!ahead && !blocking && s.ahead_ever) {   // a queued pass outside the cast-ahead scheme on a context that uses it
+            SDPA_CUDA_TRY(cudaSetDevice(s.dev));
+            if (!s.ev_plain_end) SDPA_CUDA_TRY(cudaEventCreateWithFlags(&s.ev_plain_end, cudaEventDisableTiming));
+            SDPA_CUDA_TRY(cudaEventRecord(s.ev_plain_end, s.s_compute));
+            s.plain_end_recorded = true;
+        }
     }
     if (marked) {
         ctx->last_timing_valid = false;   // evaluated lazily by sdpa_last_timings / sdpa_accumulated_timings

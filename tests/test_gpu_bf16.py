@@ -166,3 +166,24 @@ def test_cast_ahead_queued_passes(sdpa, oracle, monkeypatch):
             np.testing.assert_allclose(g, r, rtol=0, atol=BF16_KERNEL_ATOL)
     for a, b in zip(results["1"], results["0"]):
         assert np.array_equal(a, b)
+
+
+def test_cast_ahead_mixed_with_plain_queued_passes(sdpa, oracle):
+    """One context, one queue: passes that cast ahead (persistent kernel) interleaved with passes that do not (few keys: the
+    plain-grid kernel, casts in the compute stream, slots by batch index).  A side-stream cast must never overwrite a K/V set or
+    Q slot that an earlier plain pass still reads."""
+    import torch
+    m, d = 600, 128
+    shapes = (16384, 1500, 20000, 16384 + 136, 900, 16384)
+    cases = [oracle.make_inputs(m, n, d, d, seed=60 + k) for k, n in enumerate(shapes)]
+    refs = [oracle.attention_f64_numpy(*(oracle.bf16_round(a).astype(np.float64) for a in c)) for c in cases]
+    with sdpa.Context(precision="bf16") as ctx:
+        dev = [[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (K, V, Q)] for (Q, K, V) in cases]
+        outs = [torch.zeros(m, d, dtype=torch.float64, device="cuda") for _ in cases]
+        for rep in range(3):
+            for (Kd, Vd, Qd), out in zip(dev, outs):
+                ctx.attention_device_full([Kd.data_ptr()], [Vd.data_ptr()], [Kd.shape[0]], d, d, [Qd.data_ptr()], out.data_ptr(), m,
+                                          blocking=False)
+        ctx.synchronize()
+        for out, ref in zip(outs, refs):
+            np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=BF16_KERNEL_ATOL)
