@@ -169,7 +169,9 @@ sdpa_status sdpa_attention_device_full(sdpa_ctx* ctx, const double* const* K_sha
 
 /* The same pass, queued instead of blocking: returns once the work is enqueued on the context's streams.  Consecutive
  * passes run back to back in stream order (they share the context's buffers), which removes the host round trip
- * between passes; every array must stay valid and unmodified until sdpa_synchronize() returns.  This is the form
+ * between passes; every array must be complete when the call is made and stay valid and unmodified until
+ * sdpa_synchronize() returns -- the K/V/Q of a queued pass may be read (cast to compute precision on a side stream) while
+ * the PREVIOUS pass is still computing, and its result may not be read by the caller before sdpa_synchronize().  This is the form
  * bench.py times for the HBM-resident metric -- the blocking calls above keep the reference's semantics
  * (attention() returns with the result complete, attention-mpi.c:521-523). */
 sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shards, const double* const* V_shards,
