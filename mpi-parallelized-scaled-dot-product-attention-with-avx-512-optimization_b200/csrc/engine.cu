@@ -272,6 +272,8 @@ struct sdpa_ctx {
     DevBuf cast_trace;                      // SDPA_CAST_TRACE=<path> (developer aid, single-GPU contexts): per-CTA stamps of the background cast
     std::string cast_trace_path;            // + [600..603] begin/end stamps of the fused kernels of the last two passes, dumped at destroy
     unsigned long long trace_pass = 0;
+    struct ByteRange { const char* p; size_t n; };
+    std::vector<ByteRange> queued_results;  // results of the queued passes still in flight (a pass that reads one of them cannot cast ahead)
     bool cast_ahead = true;                 // SDPA_CAST_AHEAD=0: the casts of a queued pass stay on the compute stream
     unsigned long long batch_seq = 0;       // batches issued by queued passes with sequence slots (slot = batch_seq & 1)
     bool exchange_pending = false;          // overlap mode left exchange work behind: drain before freeing / reallocating slots
@@ -2057,9 +2059,26 @@ sdpa_status sdpa_enqueue_device_full(sdpa_ctx* ctx, const double* const* K_shard
         // still run, and its CTAs pile up on the SMs that happen to have room (see the gate of the pushsync root form)
         const int B = pick_q_batch(ctx, m);
         ahead = (ctx->world == 1 || ipc) && m <= B && persistent_pieces(ctx, prec, dk, dv, B, n_local) > 1;
+        // a pass whose operands ARE an earlier queued pass's result (chained passes) must see that result: its casts stay in
+        // the compute stream, behind the merge that writes it
+        auto aliases_result = [&](const void* ptr, size_t bytes) {
+            const char* a = static_cast<const char*>(ptr);
+            for (const sdpa_ctx::ByteRange& r : ctx->queued_results)
+                if (a && a < r.p + r.n && r.p < a + bytes) return true;
+            return false;
+        };
+        for (int i = 0; i < L && ahead; ++i)
+            if ((K_shards && aliases_result(K_shards[i], (size_t)n_local[i] * dk * sizeof(double))) ||
+                (V_shards && aliases_result(V_shards[i], (size_t)n_local[i] * dv * sizeof(double))) ||
+                aliases_result(Q_dev[i], (size_t)m * dk * sizeof(double)))
+                ahead = false;
     }
     SDPA_TRY(load_kv(ctx, K_shards, V_shards, n_local, dk, dv, true, true, ahead));
     SDPA_TRY(attention_impl(ctx, nullptr, Q_dev, result_dev, true, m, false, false));
+    if (result_dev && m > 0) {
+        if (ctx->queued_results.size() >= 64) ctx->queued_results.erase(ctx->queued_results.begin());   // bounded: older ones are long complete
+        ctx->queued_results.push_back({reinterpret_cast<const char*>(result_dev), (size_t)m * dv * sizeof(double)});
+    }
     if (ctx->deferring && !ctx->call_guards.empty()) {
         const size_t L = ctx->shards.size();
         sdpa_ctx::PendingPass p;
@@ -2139,6 +2158,7 @@ sdpa_status sdpa_synchronize(sdpa_ctx* ctx)
         SDPA_CUDA_TRY(cudaSetDevice(s.dev));
         SDPA_CUDA_TRY(cudaStreamSynchronize(s.s_compute));
     }
+    ctx->queued_results.clear();
     return resolve_pending(ctx);   // collective when the context spans several processes
 }
 

@@ -187,3 +187,31 @@ def test_cast_ahead_mixed_with_plain_queued_passes(sdpa, oracle):
         ctx.synchronize()
         for out, ref in zip(outs, refs):
             np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=BF16_KERNEL_ATOL)
+
+
+def test_chained_queued_passes_see_the_previous_result(sdpa, oracle):
+    """Queued passes whose Q IS the previous queued pass's result: such a pass cannot cast ahead (its operand does not exist yet
+    when the previous fused kernel starts) -- the library keeps its casts in the compute stream, behind the merge that writes
+    the result."""
+    import torch
+    m, d, n = 600, 128, 16384
+    Q, K, V = oracle.make_inputs(m, n, d, d, seed=81)
+    V = V * 50.0   # results of magnitude ~0.6: as the next Q they move the scores (a stale, still-zero Q would give the plain mean of V,
+    #                which the oracle puts up to 1.4 away from the right answer, median 0.19)
+    Qb, Kb, Vb = (oracle.bf16_round(a).astype(np.float64) for a in (Q, K, V))
+    tol = 5e-2     # values are 50x those of the other tests
+    with sdpa.Context(precision="bf16") as ctx:
+        Kd, Vd, Qd = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (K, V, Q))
+        r1 = torch.zeros(m, d, dtype=torch.float64, device="cuda")
+        r2 = torch.zeros(m, d, dtype=torch.float64, device="cuda")
+        r3 = torch.zeros(m, d, dtype=torch.float64, device="cuda")
+        args = ([Kd.data_ptr()], [Vd.data_ptr()], [n], d, d)
+        ctx.attention_device_full(*args, [Qd.data_ptr()], r1.data_ptr(), m, blocking=False)
+        ctx.attention_device_full(*args, [r1.data_ptr()], r2.data_ptr(), m, blocking=False)   # Q = result of the first pass
+        ctx.attention_device_full(*args, [r2.data_ptr()], r3.data_ptr(), m, blocking=False)   # ... and again
+        ctx.synchronize()
+        g1, g2, g3 = (t.cpu().numpy() for t in (r1, r2, r3))
+    np.testing.assert_allclose(g1, oracle.attention_f64_numpy(Qb, Kb, Vb), rtol=0, atol=tol)
+    for got, q in ((g2, g1), (g3, g2)):   # each against the oracle on the operand the library was given
+        np.testing.assert_allclose(got, oracle.attention_f64_numpy(oracle.bf16_round(q).astype(np.float64), Kb, Vb), rtol=0, atol=tol)
+    assert np.abs(g2 - Vb.mean(axis=0)).max() > 0.5   # the chain mattered
