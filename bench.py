@@ -600,8 +600,14 @@ def run_ours(args) -> None:
     extra_names = [x for x in (args.extra.split(",") if args.extra else EXTRAS_BY_GPUS.get(world, [])) if x and x != "none"]
     if args.m or args.n_per_gpu or args.config != "c3":
         extra_names = [x for x in extra_names if args.extra]   # shape overrides / other headline: only what was asked for
+    extra_errors = {}
     for name in extra_names:
-        r = measure(name, 3, max(3, min(K, 10)))
+        try:
+            r = measure(name, 3, max(3, min(K, 10)))
+        except Exception as exc:   # an extra configuration must not cost the headline line; the failure is reported in it
+            extra_errors[name] = repr(exc)
+            print("bench: extra configuration %s failed: %r" % (name, exc), file=sys.stderr)
+            continue
         if rank == 0:
             extras[name] = {
                 "workload": CONFIGS[name]["desc"], "m": r["m"], "n": r["n"], "n_per_gpu": r["n_local"], "kernel": r["kernel"],
@@ -714,7 +720,9 @@ def run_ours(args) -> None:
             "parity_check": head["parity"],
             "configs": extras,
         }
-        failed = not head["parity"]["ok"] or any(not e["parity_check"]["ok"] for e in extras.values())
+        failed = not head["parity"]["ok"] or any(not e["parity_check"]["ok"] for e in extras.values()) or bool(extra_errors)
+        if extra_errors:
+            line["config_errors"] = extra_errors
     # ---- CPU baseline beside it (rank 0, N=1 only) --------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
