@@ -497,10 +497,13 @@ def run_ours(args) -> None:
     host_enqueue_us = [0.0]
 
     def timed(ctx, fn, steps, collect=None):
-        barrier()
         if collect is not None:
             ctx.accumulated_timings(reset=True)   # stage events are queried once, after the loop
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # Nothing rank-local between the barrier and the first step: a rank that starts late makes the others wait inside the
+        # timed region (seen once: 5.8 ms of one 4-GPU run's first exchange step, profiles/r02/visit19_*), and the elapsed time
+        # is the MAX over ranks.
+        barrier()
         e0.record()
         h0 = time.perf_counter()
         for _ in range(steps):
